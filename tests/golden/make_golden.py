@@ -1,0 +1,141 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference planner
+(/root/reference/src/algorithm/tdmpc.py: TDMPC.plan) on CPU with injected random draws.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+
+What is stored: only the reference's OUTPUTS (per-iteration trajectory values, top-k
+indices, final mean, action, metrics).  Inputs (weights, observations, noise) are
+regenerated from seeds by tests/synth.py, which is importable everywhere.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shims  # noqa: E402
+
+ref_shims.install()
+
+from tests import synth  # noqa: E402
+from oracle import tdmpc_oracle as O  # noqa: E402
+
+import algorithm.helper as ref_h  # noqa: E402
+from algorithm.tdmpc import TDMPC  # noqa: E402
+
+
+class Injector:
+    """Replaces torch.randn / helper._standard_normal / np.random.choice by queues of
+    pre-drawn values, in the order the reference consumes them."""
+
+    def __init__(self):
+        self.randn_q, self.stdn_q, self.u = [], [], None
+        self.topk_log, self.value_log = [], []
+
+    def __enter__(self):
+        self._randn, self._stdn, self._choice, self._topk = torch.randn, ref_h._standard_normal, np.random.choice, torch.topk
+
+        def randn(*shape, **kw):
+            x = self.randn_q.pop(0)
+            assert tuple(x.shape) == tuple(shape), (x.shape, shape)
+            return x.clone()
+
+        def stdn(shape, dtype=None, device=None):
+            x = self.stdn_q.pop(0)
+            assert tuple(x.shape) == tuple(shape), (x.shape, shape)
+            return x.clone()
+
+        def choice(arr, p=None):
+            # numpy's algorithm for choice(p=...): inverse CDF on the float64 cumsum.
+            cdf = np.cumsum(np.asarray(p, dtype=np.float64)); cdf /= cdf[-1]
+            return arr[int(np.searchsorted(cdf, self.u, side="right"))]
+
+        def topk(x, k, dim=0):
+            r = self._topk(x, k, dim=dim)
+            self.topk_log.append(r.indices.clone())
+            return r
+
+        torch.randn, ref_h._standard_normal, np.random.choice, torch.topk = randn, stdn, choice, topk
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, ref_h._standard_normal, np.random.choice, torch.topk = self._randn, self._stdn, self._choice, self._topk
+
+
+def check_choice_replica():
+    """The injected categorical pick must be numpy's own algorithm."""
+    for s in range(50):
+        p = np.random.RandomState(s).dirichlet(np.ones(64)).astype(np.float32)
+        np.random.seed(s); u = np.random.random_sample()
+        np.random.seed(s); j = np.random.choice(np.arange(64), p=p)
+        cdf = np.cumsum(p.astype(np.float64)); cdf /= cdf[-1]
+        assert j == int(np.searchsorted(cdf, u, side="right")), s
+
+
+def run_case(name, cfg_name, steps=3, eval_mode=True, seed=0, std_floor=None, **over):
+    cfg = synth.make_cfg(cfg_name, **over)
+    torch.manual_seed(0)
+    agent = TDMPC(cfg)
+    sd = synth.make_told_weights(cfg, seed)
+    agent.model.load_state_dict(sd)
+    agent.std = cfg.min_std if std_floor is None else std_floor
+    step = 10 ** 6
+    out = {}
+    prev_mean_oracle = None
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise(cfg, seed * 100 + s, step)
+        H, N, P, T = synth.plan_dims(cfg, step)
+        inj = Injector()
+        for t in range(H):
+            inj.stdn_q.append(nz["pi"][t])
+        for i in range(cfg.iterations):
+            inj.randn_q.append(nz["cem"][i])
+            inj.stdn_q.append(nz["term"][i])
+        inj.randn_q.append(nz["out"])
+        inj.u = nz["u"]
+        ev = agent.estimate_value
+
+        def ev_logged(z, actions, horizon, _ev=ev, _inj=inj):
+            v, r = _ev(z, actions, horizon)
+            _inj.value_log.append(v.squeeze(1).clone())
+            return v, r
+
+        agent.estimate_value = ev_logged
+        with inj:
+            a, metrics = agent.plan(obs, eval_mode=eval_mode, step=step, t0=(s == 0))
+        agent.estimate_value = ev
+        out[f"s{s}_action"] = a.numpy().copy()
+        out[f"s{s}_prev_mean"] = agent._prev_mean.numpy().copy()
+        out[f"s{s}_values"] = torch.stack(inj.value_log).numpy()
+        out[f"s{s}_elite_idx"] = torch.stack(inj.topk_log).numpy().astype(np.int32)
+        out[f"s{s}_metrics"] = np.array([metrics["external_reward_mean"], metrics["current_std"]], dtype=np.float64)
+
+        # the oracle restatement must agree with the reference it restates (same machine => tight)
+        a_o, m_o, mean_o, taps = O.plan_tdmpc(sd, cfg, obs, eval_mode=eval_mode, step=step, t0=(s == 0),
+                                              prev_mean=prev_mean_oracle, std_floor=agent.std, noise=nz)
+        prev_mean_oracle = mean_o
+        dv = (torch.stack(taps["values"]) - torch.stack(inj.value_log)).abs().max().item()
+        da = (a_o - a).abs().max().item()
+        dm = (mean_o - agent._prev_mean).abs().max().item()
+        print(f"[{name}] step {s}: |dvalue|={dv:.3e} |daction|={da:.3e} |dmean|={dm:.3e} "
+              f"metrics ref={metrics} oracle={m_o}")
+        assert dv < 1e-5 and da < 1e-5 and dm < 1e-5
+    out["meta"] = np.array([seed, steps, int(eval_mode)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
+if __name__ == "__main__":
+    check_choice_replica()
+    run_case("tdmpc_tiny", "tiny", steps=3)
+    run_case("tdmpc_tiny_train", "tiny", steps=2, eval_mode=False, seed=3, std_floor=0.1)
+    run_case("tdmpc_cfg1", "cfg1", steps=3)
+    run_case("tdmpc_cfg3", "cfg3", steps=2, seed=1)
+    run_case("tdmpc_cfg2s", "cfg2s", steps=2, seed=2)
+    print("golden fixtures written to", HERE)

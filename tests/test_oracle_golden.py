@@ -1,0 +1,78 @@
+"""Pins oracle/tdmpc_oracle.py against fixtures produced by the real reference planner
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tdmpc_oracle as O
+from tests import synth
+
+CASES = [("tdmpc_tiny", "tiny", {}), ("tdmpc_tiny_train", "tiny", {"std_floor": 0.1}),
+         ("tdmpc_cfg1", "cfg1", {}), ("tdmpc_cfg3", "cfg3", {}), ("tdmpc_cfg2s", "cfg2s", {})]
+
+# fixtures were generated on another host CPU; MKL may pick different GEMM kernels there
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("name,cfg_name,kw", CASES)
+def test_oracle_matches_reference_fixture(golden_dir, name, cfg_name, kw):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, steps, eval_mode = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    std_floor = kw.get("std_floor", cfg.min_std)
+    step = 10 ** 6
+    prev = None
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise(cfg, seed * 100 + s, step)
+        a, m, prev, taps = O.plan_tdmpc(sd, cfg, obs, eval_mode=bool(eval_mode), step=step, t0=(s == 0),
+                                        prev_mean=prev, std_floor=std_floor, noise=nz)
+        vals = torch.stack(taps["values"]).numpy()
+        ref_vals = g[f"s{s}_values"]
+        scale = np.abs(ref_vals).max()
+        assert np.abs(vals - ref_vals).max() <= TOL * scale
+        # elite sets: identical wherever the K-th / (K+1)-th gap is resolvable
+        for i in range(cfg.iterations):
+            srt = np.sort(ref_vals[i])[::-1]
+            K = cfg.num_elites
+            if srt[K - 1] - srt[K] > 4 * TOL * scale:
+                assert set(taps["elite_idx"][i].tolist()) == set(g[f"s{s}_elite_idx"][i].tolist())
+        np.testing.assert_allclose(prev.numpy(), g[f"s{s}_prev_mean"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(a.numpy(), g[f"s{s}_action"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose([m["external_reward_mean"], m["current_std"]], g[f"s{s}_metrics"], rtol=1e-4, atol=1e-5)
+
+
+def test_seed_steps_early_return():
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 0)
+    nz = synth.make_noise(cfg, 0)
+    a, m, prev, _ = O.plan_tdmpc(sd, cfg, synth.make_obs(cfg), eval_mode=False, step=10, t0=True,
+                                 prev_mean=None, std_floor=0.05, noise=nz)
+    assert torch.equal(a, nz["seed_uniform"]) and m == {"external_reward_mean": 0.0, "current_std": 0.0}
+
+
+def test_linear_schedule():
+    assert O.linear_schedule("0.25", 7) == 0.25
+    assert O.linear_schedule("linear(0.5, 0.05, 25000, 0)", 0) == 0.5
+    assert abs(O.linear_schedule("linear(0.5, 0.05, 25000, 0)", 12500) - 0.275) < 1e-12
+    assert O.linear_schedule("linear(2, 5, 25000, 0)", 10 ** 6) == 5.0
+    with pytest.raises(NotImplementedError):
+        O.linear_schedule("cosine(1,2)", 0)
+
+
+def test_categorical_pick_is_numpy_choice():
+    for s in range(40):
+        p = np.random.RandomState(s).dirichlet(np.ones(32)).astype(np.float32)
+        np.random.seed(s); u = np.random.random_sample()
+        np.random.seed(s); j = np.random.choice(np.arange(32), p=p)
+        assert O.categorical_pick(torch.from_numpy(p).unsqueeze(1), u) == j
+
+
+def test_flop_accounting_matches_survey():
+    # cfg1 = 25.15 GFLOP / plan, 16,235 sample-steps
+    f = O.flops_per_plan(D=5, A=1, L=50, M=512, E=256, H=5, rows_per_iter=[537] * 6, P=25)
+    assert abs(f / 1e9 - 25.15) < 0.05
+    assert O.sample_steps_per_plan(5, [537] * 6, 25) == 16235
