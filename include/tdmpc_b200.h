@@ -1,0 +1,202 @@
+/*
+ * tdmpc_b200 -- C ABI of the B200-native TD-MPC planner (libtdmpc_b200.so).
+ *
+ * The reference (Slienteagle-wyb/tdmpc) is pure Python/PyTorch and has no FFI of its own;
+ * the boundary it offers is the Python object surface `TDMPC.plan(obs, eval_mode, step, t0)`
+ * and `TOLD.h/next/pi/Q`.  Each entry point below names the reference function it replaces
+ * (paths relative to the reference's src/).  A ctypes binding (tdmpc_b200/_lib.py) sits on
+ * top; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the
+ *     caller; `stream` is a cudaStream_t passed as void*.
+ *   - all calls are stream-ordered and asynchronous; nothing synchronises the host.
+ *   - no allocation inside tdmpc_plan / tdmpc_estimate_value (CUDA-graph capturable) once
+ *     tdmpc_reserve() has been called for the shapes in use.
+ *   - return 0 on success, a negative tdmpc_status otherwise; tdmpc_last_error() gives text.
+ *   - there is NO CPU fallback: on a machine without an sm_100 GPU tdmpc_create() fails.
+ *   - tensors are fp32 row-major unless stated.  Row layout of action tensors is
+ *     [problem][trajectory][t][a]  (the reference uses [t][trajectory][a]; the Python wrapper
+ *     converts where the reference layout is user-visible, i.e. `_prev_mean` [H,A]).
+ */
+#ifndef TDMPC_B200_H
+#define TDMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDMPC_MAX_ITERS 16
+
+#if defined(__GNUC__)
+#define TDMPC_API __attribute__((visibility("default")))
+#else
+#define TDMPC_API
+#endif
+
+typedef enum {
+  TDMPC_OK = 0,
+  TDMPC_ERR_INVALID = -1,     /* bad argument / unsupported shape            */
+  TDMPC_ERR_CUDA = -2,        /* a CUDA runtime call failed                  */
+  TDMPC_ERR_ARCH = -3,        /* device is not sm_100 (no fallback path)     */
+  TDMPC_ERR_WORKSPACE = -4,   /* tdmpc_reserve() not called / too small      */
+  TDMPC_ERR_STATE = -5        /* weights not set                             */
+} tdmpc_status;
+
+typedef enum {
+  TDMPC_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: the 1e-5 parity mode              */
+  TDMPC_PREC_BF16 = 1    /* tcgen05 bf16 operands, fp32 accumulate: the throughput mode  */
+} tdmpc_precision;
+
+typedef enum {
+  TDMPC_DYN_MLP = 0,     /* TOLD._dynamics = helper.mlp (algorithm/tdmpc.py:16)                          */
+  TDMPC_DYN_DRNN = 1     /* DGruDyna: NormGRUCell + BN prior MLP (models/gru_dyna.py:11-29)              */
+} tdmpc_dynamics;
+
+/* Static model description: algorithm/tdmpc.py:12-23 (TOLD.__init__) + cfg fields it reads. */
+typedef struct {
+  int32_t obs_dim;        /* cfg.obs_shape[0]                                  */
+  int32_t action_dim;     /* cfg.action_dim                                    */
+  int32_t latent_dim;     /* cfg.latent_dim                                    */
+  int32_t mlp_dim;        /* cfg.mlp_dim  (bf16 path requires 512)             */
+  int32_t enc_dim;        /* cfg.enc_dim                                       */
+  int32_t hidden_dim;     /* cfg.hidden_dim (DRNN only)                        */
+  int32_t enc_layernorm;  /* 1: helper.dmlab_enc_norm state branch (helper.py:161-165) */
+  int32_t dynamics;       /* tdmpc_dynamics                                    */
+  int32_t precision;      /* tdmpc_precision                                   */
+  int32_t device;         /* CUDA device ordinal                               */
+} tdmpc_model_cfg;
+
+/* fp32 device pointers to the reference's parameters, nn.Linear layout [out, in].
+ * Names follow the reference state_dict (tdmpc.py:12-23, helper.py:131-133,169-176,197-201). */
+typedef struct {
+  const float* enc_w[2];      /* _encoder.0.weight [E,D]; _encoder.{2|3}.weight [L,E]              */
+  const float* enc_b[2];
+  const float* enc_ln_g;      /* _encoder.1.{weight,bias} [E] when enc_layernorm, else NULL       */
+  const float* enc_ln_b;
+  const float* dyn_w[3];      /* _dynamics.{0,2,4}.weight [M,L+A] [M,M] [L,M]                     */
+  const float* dyn_b[3];
+  const float* rew_w[3];      /* _reward.{0,2,4}.weight   [M,L+A] [M,M] [1,M]                     */
+  const float* rew_b[3];
+  const float* pi_w[3];       /* _pi.{0,2,4}.weight       [M,L]   [M,M] [A,M]                     */
+  const float* pi_b[3];
+  const float* q_w[2][3];     /* _Q{1,2}.{0,3,6}.weight   [M,L+A] [M,M] [1,M]                     */
+  const float* q_b[2][3];
+  const float* q_ln_g[2][2];  /* _Q{1,2}.{1,4}.weight [M]                                          */
+  const float* q_ln_b[2][2];
+} tdmpc_weights;
+
+/* One call of TDMPC.plan (algorithm/tdmpc.py:94-163) for `batch` independent problems. */
+typedef struct {
+  int32_t batch;            /* B: independent planning problems (the reference has B = 1)        */
+  int32_t horizon;          /* H = int(min(cfg.horizon, linear_schedule(horizon_schedule, step)))  tdmpc.py:111 */
+  int32_t iterations;       /* cfg.iterations (<= TDMPC_MAX_ITERS)                                */
+  int32_t num_elites;       /* cfg.num_elites                                                     */
+  int32_t num_pi_trajs;     /* P of the policy rollout: int(mixture_coef * num_samples)  tdmpc.py:112 */
+  /* rows per iteration, in the reference's concatenation order [sampled | reused elites | pi]
+   * (tdmpc.py:134; tdmpc_icem_similarity_mlp.py:230-233).  TDMPC: n_samples[i]=N, n_reuse[i]=0, n_pi[i]=P. */
+  int32_t n_samples[TDMPC_MAX_ITERS];
+  int32_t n_reuse[TDMPC_MAX_ITERS];
+  int32_t n_pi[TDMPC_MAX_ITERS];
+  double discount;          /* cfg.discount (double: the reference accumulates gamma^t in Python floats) */
+  double momentum;          /* cfg.momentum (double: 1 - momentum is formed in double, tdmpc.py:149)     */
+  float temperature;        /* cfg.temperature                                                    */
+  float min_std;            /* cfg.min_std: policy noise in rollouts (tdmpc.py:91,117)            */
+  float std_floor;          /* agent.std: lower clamp of the CEM std (tdmpc.py:148)               */
+  float std_max;            /* upper clamp, 2 (tdmpc.py:148)                                      */
+  float init_std;           /* 2 for TDMPC (tdmpc.py:123), 0.5 for iCEM                           */
+  int32_t eval_mode;        /* 1: no exploration noise on the returned action (tdmpc.py:157)      */
+  int32_t t0_all;           /* 1/0: every problem is / is not at the first step; -1: read t0[]    */
+  int32_t warm_last;        /* iCEM: mean[-1] = prev_mean[-1] (tdmpc_icem_similarity_mlp.py:180)  */
+  int32_t best_a_last;      /* iCEM: sample 0 of the last iteration := mean (:213-214)            */
+  int32_t shift_elites;     /* iCEM: iteration-0 reuse = previous step's elites shifted by one (:217-224) */
+  int32_t has_prev;         /* 0: prev_mean holds nothing yet (hasattr(self,'_prev_mean') False)  */
+
+  const float* obs;         /* device [B, obs_dim]                                                */
+  const float* z0;          /* device [B, latent_dim] or NULL; when set the encoder is skipped    */
+  const uint8_t* t0;        /* device [B] or NULL (t0_all != -1)                                  */
+  float* prev_mean;         /* device [B, H, A] in/out: agent._prev_mean (tdmpc.py:125,154)       */
+  float* elite_actions;     /* device [B, K, H, A] in/out or NULL: iCEM agent._elite_actions      */
+
+  /* randomness: either injected draws (parity tests; consumption order = SURVEY Appendix B)
+   * or, where a pointer is NULL, the built-in Philox4x32-10 stream keyed by (seed, call).        */
+  uint64_t seed;
+  uint64_t call;            /* plan-call counter: distinct noise per call                         */
+  const float* noise_pi;    /* device [B, H, P, A]           TruncatedNormal draws of the pi rollout  */
+  const float* noise_cem;   /* device [B, I, H, Nmax, A]     torch.randn(H,N,A) of each iteration     */
+  const float* noise_term;  /* device [B, I, Tmax, A]        terminal-policy draws in estimate_value  */
+  const float* noise_out;   /* device [B, A]                 exploration noise (tdmpc.py:158)         */
+  const double* u_pick;     /* device [B]                    uniform of np.random.choice (:153)       */
+
+  float* action;            /* device [B, A] out                                                  */
+  float* metrics;           /* device [B, 2] out: external_reward_mean, current_std (tdmpc.py:160-161) */
+
+  /* optional debug taps (NULL to skip) */
+  float* tap_values;        /* device [I, B, Tmax]                                                */
+  int32_t* tap_elite_idx;   /* device [I, B, K]                                                   */
+  float* tap_mean;          /* device [I, B, H, A]                                                */
+  float* tap_std;           /* device [I, B, H, A]                                                */
+  float* tap_z0;            /* device [B, L]                                                      */
+} tdmpc_plan_args;
+
+typedef struct tdmpc_handle tdmpc_handle;
+
+/* Replaces: TDMPC.__init__ / TOLD.__init__ as far as planning needs them (tdmpc.py:12-23,56-66). */
+TDMPC_API int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out);
+TDMPC_API int tdmpc_destroy(tdmpc_handle* h);
+TDMPC_API const char* tdmpc_last_error(const tdmpc_handle* h);   /* h may be NULL: error of the last failed create */
+
+/* Grow the library-owned scratch (trajectory actions, values, packed weights ...) so that plans
+ * with up to `batch` problems x `max_rows` trajectories x `max_horizon` steps need no allocation. */
+TDMPC_API int tdmpc_reserve(tdmpc_handle* h, int32_t batch, int32_t max_rows, int32_t max_horizon, int32_t max_elites);
+
+/* Re-pack the reference's fp32 parameters for the kernels (transposed fp32 for the CUDA-core
+ * path, bf16 swizzled 16 KB tiles in consumption order for the tcgen05 path).  Call after every
+ * agent.update()/load() (tdmpc.py:80,230 mutate the parameters). Idempotent. */
+TDMPC_API int tdmpc_set_weights(tdmpc_handle* h, const tdmpc_weights* w, void* stream);
+
+/* Replaces TOLD.h (tdmpc.py:30-32): z[B,L] = encoder(obs[B,D]). */
+TDMPC_API int tdmpc_encode(tdmpc_handle* h, const float* obs, int32_t batch, float* z_out, void* stream);
+
+/* Replaces TDMPC.estimate_value (tdmpc.py:83-92) for B problems x T trajectories:
+ *   values[b,j] = nan_to_num( sum_t gamma^t r_t + gamma^H min(Q1,Q2)(z_H, pi(z_H, min_std)) )
+ * z0 [B,L]; actions [B,T,H,A]; noise_term [B,T,A] (or NULL -> Philox (seed, call, iteration 0));
+ * values [B,T]; last_reward [B,T] (reward of the final step; may be NULL). */
+TDMPC_API int tdmpc_estimate_value(tdmpc_handle* h, const float* z0, const float* actions, const float* noise_term,
+                         int32_t batch, int32_t rows, int32_t horizon, double discount, float min_std,
+                         uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream);
+
+/* Replaces the policy rollout of TDMPC.plan (tdmpc.py:113-118):
+ * for t: a_t = pi(z, min_std); z = next(z, a_t).  pi_actions [B,P,H,A]; noise_pi [B,H,P,A] or NULL. */
+TDMPC_API int tdmpc_pi_rollout(tdmpc_handle* h, const float* z0, const float* noise_pi, int32_t batch, int32_t rows,
+                     int32_t horizon, float min_std, uint64_t seed, uint64_t call, float* pi_actions, void* stream);
+
+/* Replaces tdmpc.py:138-149 for B problems: top-K (sorted descending, ties -> lower index),
+ * softmax weights, weighted mean/std, clamp, momentum.  values [B,T]; actions [B,T,H,A];
+ * mean/std [B,H,A] in/out; elite_idx [B,K] out; score [B,K] out (may be NULL). */
+TDMPC_API int tdmpc_select_update(tdmpc_handle* h, const float* values, const float* actions, int32_t batch, int32_t rows,
+                        int32_t horizon, int32_t num_elites, float temperature, double momentum, float std_floor,
+                        float std_max, float* mean, float* std, int32_t* elite_idx, float* score, void* stream);
+
+/* Replaces TDMPC.plan (tdmpc.py:94-163) -- and, with the iCEM fields, TdICemSimMlp.plan
+ * (tdmpc_icem_similarity_mlp.py:159-265) -- for `batch` problems. */
+TDMPC_API int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* args, void* stream);
+
+/* The built-in noise stream, exposed so tests can feed the SAME draws to the oracle:
+ * out[i] = i-th standard normal of stream `stream_id` (0 pi, 1 cem, 2 term, 3 out) for (seed, call);
+ * stream 4 writes uniforms in [0,1) as float64 (u_pick). */
+TDMPC_API int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,
+                     void* out, void* stream);
+
+/* Number of kernels of THIS library launched by the handle so far (bench.py's gpu_launches). */
+TDMPC_API uint64_t tdmpc_launch_count(const tdmpc_handle* h);
+
+/* Build information: "sm_100a;tcgen05=1;..." */
+TDMPC_API const char* tdmpc_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDMPC_B200_H */

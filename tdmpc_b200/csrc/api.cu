@@ -1,0 +1,405 @@
+// C-ABI entry points of libtdmpc_b200.so (declared in include/tdmpc_b200.h): handle management,
+// weight packing, scratch reservation and the host-side orchestration of one TDMPC.plan call
+// (algorithm/tdmpc.py:94-163) as a fixed sequence of stream-ordered kernel launches.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_model.cuh"
+
+int select_max_rows();
+int select_max_elites();
+int select_max_ha();
+
+struct tdmpc_handle {
+  tdmpc_model_cfg cfg;
+  int num_sms = 0;
+  std::string err;
+  // packed parameters
+  float* arena32 = nullptr; size_t arena32_floats = 0;
+  ModelFp32 m32{};
+  TcModel tc{};
+  void* arena_tc = nullptr; size_t arena_tc_bytes = 0;
+  bool weights_set = false;
+  // scratch
+  int capB = 0, capT = 0, capH = 0, capK = 0;
+  float *z0 = nullptr, *actions = nullptr, *pi_actions = nullptr, *values = nullptr, *last_reward = nullptr;
+  float *mean = nullptr, *std = nullptr, *score = nullptr, *elites = nullptr;
+  int* elite_idx = nullptr;
+  uint64_t launches = 0;
+};
+
+static std::string g_create_err;
+
+#define FAIL(h, code, ...)                                   \
+  do {                                                       \
+    char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__);     \
+    (h)->err = _b; return (code);                            \
+  } while (0)
+
+#define CUDA_OK(h, call)                                                                        \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess) FAIL(h, TDMPC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int check_launch(tdmpc_handle* h, const char* what, int n = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) FAIL(h, TDMPC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  h->launches += n;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static size_t lin_floats(int N, int K) { return (size_t)((K + 3) & ~3) * N + (size_t)((N + 3) & ~3); }
+
+static size_t arena32_size(const tdmpc_model_cfg& c) {
+  const int D = c.obs_dim, A = c.action_dim, L = c.latent_dim, M = c.mlp_dim, E = c.enc_dim;
+  size_t n = lin_floats(E, D) + lin_floats(L, E) + 2 * (size_t)E;
+  n += lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(L, M);        // dyn
+  n += lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(1, M);        // rew
+  n += lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(A, M);        // pi (K padded to L+A)
+  n += 2 * (lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(1, M) + 4 * (size_t)M);
+  return n + 64;
+}
+
+extern "C" int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out) {
+  if (!cfg || !out) { g_create_err = "null argument"; return TDMPC_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_err = "no CUDA device: tdmpc_b200 has no CPU fallback";
+    return TDMPC_ERR_ARCH;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return TDMPC_ERR_INVALID; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { g_create_err = "cudaGetDeviceProperties failed"; return TDMPC_ERR_CUDA; }
+  if (prop.major != 10) {
+    char b[256];
+    snprintf(b, sizeof(b), "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", cfg->device, prop.major, prop.minor);
+    g_create_err = b;
+    return TDMPC_ERR_ARCH;
+  }
+  if (cfg->obs_dim <= 0 || cfg->action_dim <= 0 || cfg->latent_dim <= 0 || cfg->mlp_dim <= 0 || cfg->enc_dim <= 0) {
+    g_create_err = "model dims must be positive"; return TDMPC_ERR_INVALID;
+  }
+  if (cfg->action_dim > 64) { g_create_err = "action_dim > 64 unsupported"; return TDMPC_ERR_INVALID; }
+  if (cfg->dynamics != TDMPC_DYN_MLP) { g_create_err = "only MLP dynamics are implemented in this build"; return TDMPC_ERR_INVALID; }
+  if (cfg->precision == TDMPC_PREC_BF16) {
+    const char* why = tc_supported(*cfg);
+    if (why) { g_create_err = std::string("bf16 tcgen05 path: ") + why; return TDMPC_ERR_INVALID; }
+  } else if (cfg->precision != TDMPC_PREC_FP32) { g_create_err = "unknown precision"; return TDMPC_ERR_INVALID; }
+  tdmpc_handle* h = new tdmpc_handle();
+  h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
+  cudaSetDevice(cfg->device);
+  h->arena32_floats = arena32_size(*cfg);
+  if (cudaMalloc(&h->arena32, h->arena32_floats * sizeof(float)) != cudaSuccess) { g_create_err = "cudaMalloc(arena32) failed"; delete h; return TDMPC_ERR_CUDA; }
+  if (cfg->precision == TDMPC_PREC_BF16) {
+    h->arena_tc_bytes = tc_arena_bytes(*cfg);
+    if (cudaMalloc(&h->arena_tc, h->arena_tc_bytes) != cudaSuccess) { g_create_err = "cudaMalloc(arena_tc) failed"; cudaFree(h->arena32); delete h; return TDMPC_ERR_CUDA; }
+  }
+  *out = h;
+  return TDMPC_OK;
+}
+
+static void free_scratch(tdmpc_handle* h) {
+  cudaFree(h->z0); cudaFree(h->actions); cudaFree(h->pi_actions); cudaFree(h->values); cudaFree(h->last_reward);
+  cudaFree(h->mean); cudaFree(h->std); cudaFree(h->score); cudaFree(h->elites); cudaFree(h->elite_idx);
+  h->z0 = h->actions = h->pi_actions = h->values = h->last_reward = h->mean = h->std = h->score = h->elites = nullptr;
+  h->elite_idx = nullptr;
+}
+
+extern "C" int tdmpc_destroy(tdmpc_handle* h) {
+  if (!h) return TDMPC_OK;
+  cudaSetDevice(h->cfg.device);
+  free_scratch(h);
+  cudaFree(h->arena32);
+  cudaFree(h->arena_tc);
+  delete h;
+  return TDMPC_OK;
+}
+
+extern "C" const char* tdmpc_last_error(const tdmpc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+extern "C" uint64_t tdmpc_launch_count(const tdmpc_handle* h) { return h ? h->launches : 0; }
+extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;select=bitonic"; }
+
+extern "C" int tdmpc_reserve(tdmpc_handle* h, int32_t batch, int32_t max_rows, int32_t max_horizon, int32_t max_elites) {
+  if (!h) return TDMPC_ERR_INVALID;
+  if (batch <= 0 || max_rows <= 0 || max_horizon <= 0 || max_elites <= 0) FAIL(h, TDMPC_ERR_INVALID, "reserve: non-positive size");
+  if (max_rows > select_max_rows()) FAIL(h, TDMPC_ERR_INVALID, "reserve: %d trajectories per problem > %d", max_rows, select_max_rows());
+  if (max_horizon > TDMPC_MAX_H) FAIL(h, TDMPC_ERR_INVALID, "reserve: horizon %d > %d", max_horizon, TDMPC_MAX_H);
+  if (max_elites > select_max_elites()) FAIL(h, TDMPC_ERR_INVALID, "reserve: num_elites %d > %d", max_elites, select_max_elites());
+  if (batch <= h->capB && max_rows <= h->capT && max_horizon <= h->capH && max_elites <= h->capK) return TDMPC_OK;
+  cudaSetDevice(h->cfg.device);
+  CUDA_OK(h, cudaDeviceSynchronize());
+  free_scratch(h);
+  const int B = batch > h->capB ? batch : h->capB, T = max_rows > h->capT ? max_rows : h->capT;
+  const int H = max_horizon > h->capH ? max_horizon : h->capH, K = max_elites > h->capK ? max_elites : h->capK;
+  const size_t A = h->cfg.action_dim, L = h->cfg.latent_dim;
+  CUDA_OK(h, cudaMalloc(&h->z0, sizeof(float) * B * L));
+  CUDA_OK(h, cudaMalloc(&h->actions, sizeof(float) * (size_t)B * T * H * A));
+  CUDA_OK(h, cudaMalloc(&h->pi_actions, sizeof(float) * (size_t)B * T * H * A));
+  CUDA_OK(h, cudaMalloc(&h->values, sizeof(float) * (size_t)B * T));
+  CUDA_OK(h, cudaMalloc(&h->last_reward, sizeof(float) * (size_t)B * T));
+  CUDA_OK(h, cudaMalloc(&h->mean, sizeof(float) * (size_t)B * H * A));
+  CUDA_OK(h, cudaMalloc(&h->std, sizeof(float) * (size_t)B * H * A));
+  CUDA_OK(h, cudaMalloc(&h->score, sizeof(float) * (size_t)B * K));
+  CUDA_OK(h, cudaMalloc(&h->elites, sizeof(float) * (size_t)B * K * H * A));
+  CUDA_OK(h, cudaMalloc(&h->elite_idx, sizeof(int) * (size_t)B * K));
+  h->capB = B; h->capT = T; h->capH = H; h->capK = K;
+  return TDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ArenaCursor { float* base; size_t off; };
+
+static int pack_linear(tdmpc_handle* h, ArenaCursor& c, const float* w, const float* b, int N, int K, int Kfull,
+                       LinearT* out, cudaStream_t st) {
+  // Wt [Kp][N] with Kp = roundup4(Kfull); only the first K rows are filled (rest stay zero).
+  const int Kp = (Kfull + 3) & ~3;
+  float* wt = c.base + c.off; c.off += (size_t)Kp * N;
+  float* bp = c.base + c.off; c.off += (size_t)((N + 3) & ~3);
+  if (!w) FAIL(h, TDMPC_ERR_INVALID, "set_weights: a weight pointer is NULL");
+  launch_transpose_pack(w, N, K, Kp, 0, wt, st);
+  if (int r = check_launch(h, "transpose_pack")) return r;
+  if (b) CUDA_OK(h, cudaMemcpyAsync(bp, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+  out->wt = wt; out->b = b ? bp : nullptr; out->K = Kfull; out->Kp = Kp; out->N = N;
+  return 0;
+}
+
+static int pack_ln(tdmpc_handle* h, ArenaCursor& c, const float* g, const float* b, int n, LayerNormP* out, cudaStream_t st) {
+  if (!g || !b) FAIL(h, TDMPC_ERR_INVALID, "set_weights: a LayerNorm pointer is NULL");
+  float* gp = c.base + c.off; c.off += n;
+  float* bp = c.base + c.off; c.off += n;
+  CUDA_OK(h, cudaMemcpyAsync(gp, g, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(h, cudaMemcpyAsync(bp, b, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  out->g = gp; out->b = bp;
+  return 0;
+}
+
+extern "C" int tdmpc_set_weights(tdmpc_handle* h, const tdmpc_weights* w, void* stream) {
+  if (!h || !w) return TDMPC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaSetDevice(h->cfg.device);
+  const tdmpc_model_cfg& c = h->cfg;
+  const int D = c.obs_dim, A = c.action_dim, L = c.latent_dim, M = c.mlp_dim, E = c.enc_dim;
+  CUDA_OK(h, cudaMemsetAsync(h->arena32, 0, h->arena32_floats * sizeof(float), st));
+  ArenaCursor cur{h->arena32, 0};
+  ModelFp32& m = h->m32;
+  int r;
+#define PL(...) if ((r = pack_linear(h, cur, __VA_ARGS__, st))) return r
+  PL(w->enc_w[0], w->enc_b[0], E, D, D, &m.enc[0]);
+  PL(w->enc_w[1], w->enc_b[1], L, E, E, &m.enc[1]);
+  m.enc_has_ln = c.enc_layernorm;
+  if (c.enc_layernorm) { if ((r = pack_ln(h, cur, w->enc_ln_g, w->enc_ln_b, E, &m.enc_ln, st))) return r; }
+  PL(w->dyn_w[0], w->dyn_b[0], M, L + A, L + A, &m.dyn[0]);
+  PL(w->dyn_w[1], w->dyn_b[1], M, M, M, &m.dyn[1]);
+  PL(w->dyn_w[2], w->dyn_b[2], L, M, M, &m.dyn[2]);
+  PL(w->rew_w[0], w->rew_b[0], M, L + A, L + A, &m.rew[0]);
+  PL(w->rew_w[1], w->rew_b[1], M, M, M, &m.rew[1]);
+  PL(w->rew_w[2], w->rew_b[2], 1, M, M, &m.rew[2]);
+  PL(w->pi_w[0], w->pi_b[0], M, L, L + A, &m.pi[0]);     // action rows stay zero
+  PL(w->pi_w[1], w->pi_b[1], M, M, M, &m.pi[1]);
+  PL(w->pi_w[2], w->pi_b[2], A, M, M, &m.pi[2]);
+  for (int q = 0; q < 2; ++q) {
+    PL(w->q_w[q][0], w->q_b[q][0], M, L + A, L + A, &m.q[q][0]);
+    PL(w->q_w[q][1], w->q_b[q][1], M, M, M, &m.q[q][1]);
+    PL(w->q_w[q][2], w->q_b[q][2], 1, M, M, &m.q[q][2]);
+    for (int j = 0; j < 2; ++j)
+      if ((r = pack_ln(h, cur, w->q_ln_g[q][j], w->q_ln_b[q][j], M, &m.q_ln[q][j], st))) return r;
+  }
+#undef PL
+  if (cur.off > h->arena32_floats) FAIL(h, TDMPC_ERR_INVALID, "internal: fp32 arena overflow");
+  if (c.precision == TDMPC_PREC_BF16) {
+    int n = tc_pack(c, *w, h->m32, h->arena_tc, &h->tc, st);
+    if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "tcgen05 weight packing failed");
+    if ((r = check_launch(h, "tc_pack", n))) return r;
+  }
+  h->weights_set = true;
+  return TDMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static void fill_disc(double gamma, int H, float* disc) {
+  double d = 1.0;                      // G, discount = 0, 1 ... discount *= cfg.discount  (tdmpc.py:86-90)
+  for (int t = 0; t <= H; ++t) { disc[t] = (float)d; d *= gamma; }
+}
+
+static int run_rollout(tdmpc_handle* h, const RolloutParams& p, cudaStream_t st) {
+  if ((long long)p.B * p.T <= 0) return 0;
+  if (h->cfg.precision == TDMPC_PREC_BF16) {
+    int n = launch_rollout_tc(h->tc, p, h->num_sms, st);
+    if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "tcgen05 rollout launch failed");
+    return check_launch(h, "rollout_tc", n);
+  }
+  launch_rollout_fp32(h->m32, p, st);
+  return check_launch(h, "rollout_fp32");
+}
+
+extern "C" int tdmpc_encode(tdmpc_handle* h, const float* obs, int32_t batch, float* z_out, void* stream) {
+  if (!h || !obs || !z_out || batch <= 0) return TDMPC_ERR_INVALID;
+  if (!h->weights_set) FAIL(h, TDMPC_ERR_STATE, "encode: weights not set");
+  cudaSetDevice(h->cfg.device);
+  launch_encode(h->m32, obs, batch, h->cfg.obs_dim, h->cfg.enc_dim, h->cfg.latent_dim, z_out, (cudaStream_t)stream);
+  return check_launch(h, "encode");
+}
+
+extern "C" int tdmpc_estimate_value(tdmpc_handle* h, const float* z0, const float* actions, const float* noise_term,
+                                    int32_t batch, int32_t rows, int32_t horizon, double discount, float min_std,
+                                    uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream) {
+  if (!h || !z0 || !actions || !values) return TDMPC_ERR_INVALID;
+  if (!h->weights_set) FAIL(h, TDMPC_ERR_STATE, "estimate_value: weights not set");
+  if (batch <= 0 || rows <= 0 || horizon <= 0 || horizon > TDMPC_MAX_H) FAIL(h, TDMPC_ERR_INVALID, "estimate_value: bad shape");
+  cudaSetDevice(h->cfg.device);
+  RolloutParams p{};
+  p.mode = MODE_VALUE; p.B = batch; p.T = rows; p.Tcap = rows; p.H = horizon;
+  p.L = h->cfg.latent_dim; p.A = h->cfg.action_dim; p.M = h->cfg.mlp_dim;
+  p.z0 = z0; p.actions = actions; p.values = values; p.last_reward = last_reward;
+  p.noise = NoiseSrc{noise_term, seed, call, NS_TERM};
+  p.noise_base = 0; p.noise_bstride = (uint64_t)rows * p.A; p.noise_tstride = 0;
+  p.min_std = min_std;
+  fill_disc(discount, horizon, p.disc);
+  return run_rollout(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int tdmpc_pi_rollout(tdmpc_handle* h, const float* z0, const float* noise_pi, int32_t batch, int32_t rows,
+                                int32_t horizon, float min_std, uint64_t seed, uint64_t call, float* pi_actions, void* stream) {
+  if (!h || !z0 || !pi_actions) return TDMPC_ERR_INVALID;
+  if (!h->weights_set) FAIL(h, TDMPC_ERR_STATE, "pi_rollout: weights not set");
+  if (batch <= 0 || rows <= 0 || horizon <= 0 || horizon > TDMPC_MAX_H) FAIL(h, TDMPC_ERR_INVALID, "pi_rollout: bad shape");
+  cudaSetDevice(h->cfg.device);
+  RolloutParams p{};
+  p.mode = MODE_PI; p.B = batch; p.T = rows; p.Tcap = rows; p.H = horizon;
+  p.L = h->cfg.latent_dim; p.A = h->cfg.action_dim; p.M = h->cfg.mlp_dim;
+  p.z0 = z0; p.pi_actions = pi_actions;
+  p.noise = NoiseSrc{noise_pi, seed, call, NS_PI};
+  p.noise_base = 0; p.noise_bstride = (uint64_t)horizon * rows * p.A; p.noise_tstride = (uint64_t)rows * p.A;
+  p.min_std = min_std;
+  return run_rollout(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int tdmpc_select_update(tdmpc_handle* h, const float* values, const float* actions, int32_t batch, int32_t rows,
+                                   int32_t horizon, int32_t num_elites, float temperature, double momentum, float std_floor,
+                                   float std_max, float* mean, float* std, int32_t* elite_idx, float* score, void* stream) {
+  if (!h || !values || !actions || !mean || !std || !elite_idx) return TDMPC_ERR_INVALID;
+  if (batch <= 0 || rows <= 0 || rows > select_max_rows() || horizon <= 0 || horizon > TDMPC_MAX_H ||
+      num_elites <= 0 || num_elites > rows || num_elites > select_max_elites())
+    FAIL(h, TDMPC_ERR_INVALID, "select_update: bad shape (rows=%d K=%d H=%d)", rows, num_elites, horizon);
+  cudaSetDevice(h->cfg.device);
+  SelectParams p{};
+  p.B = batch; p.T = rows; p.Tcap = rows; p.H = horizon; p.A = h->cfg.action_dim; p.K = num_elites;
+  p.iter = 0; p.n_iters = 1; p.values = values; p.actions = const_cast<float*>(actions);
+  p.mean = mean; p.std = std; p.temperature = temperature; p.momentum = (float)momentum;
+  p.one_minus_momentum = (float)(1.0 - momentum); p.std_floor = std_floor; p.std_max = std_max;
+  p.elite_idx = elite_idx; p.score = score;
+  launch_select(p, (cudaStream_t)stream);
+  return check_launch(h, "select");
+}
+
+extern "C" int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,
+                                void* out, void* stream) {
+  if (!h || !out || stream_id < 0 || stream_id > NS_PICK) return TDMPC_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  launch_fill_noise(stream_id, seed, call, count, out, (cudaStream_t)stream);
+  return check_launch(h, "fill_noise");
+}
+
+extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* stream) {
+  if (!h || !a) return TDMPC_ERR_INVALID;
+  if (!h->weights_set) FAIL(h, TDMPC_ERR_STATE, "plan: weights not set (call tdmpc_set_weights)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = a->batch, H = a->horizon, I = a->iterations, K = a->num_elites, P0 = a->num_pi_trajs;
+  const int A = h->cfg.action_dim, L = h->cfg.latent_dim;
+  if (B <= 0 || H <= 0 || H > TDMPC_MAX_H || I <= 0 || I > TDMPC_MAX_ITERS || K <= 0 || P0 < 0)
+    FAIL(h, TDMPC_ERR_INVALID, "plan: bad sizes B=%d H=%d I=%d K=%d P=%d", B, H, I, K, P0);
+  if (H * A > select_max_ha()) FAIL(h, TDMPC_ERR_INVALID, "plan: H*A=%d too large", H * A);
+  int Tmax = 0, Nmax = 0;
+  for (int i = 0; i < I; ++i) {
+    if (a->n_samples[i] < 0 || a->n_reuse[i] < 0 || a->n_pi[i] < 0 || a->n_pi[i] > P0 || a->n_reuse[i] > K)
+      FAIL(h, TDMPC_ERR_INVALID, "plan: bad row counts at iteration %d", i);
+    const int T = a->n_samples[i] + a->n_reuse[i] + a->n_pi[i];
+    if (T < K) FAIL(h, TDMPC_ERR_INVALID, "plan: iteration %d has %d trajectories < num_elites %d", i, T, K);
+    Tmax = T > Tmax ? T : Tmax;
+    Nmax = a->n_samples[i] > Nmax ? a->n_samples[i] : Nmax;
+  }
+  if (B > h->capB || Tmax > h->capT || P0 > h->capT || H > h->capH || K > h->capK)
+    FAIL(h, TDMPC_ERR_WORKSPACE, "plan: call tdmpc_reserve(%d, %d, %d, %d) first", B, Tmax > P0 ? Tmax : P0, H, K);
+  if (!a->z0 && !a->obs) FAIL(h, TDMPC_ERR_INVALID, "plan: obs and z0 both NULL");
+  if (!a->action || !a->metrics || !a->prev_mean) FAIL(h, TDMPC_ERR_INVALID, "plan: action/metrics/prev_mean must be set");
+  if (a->t0_all < 0 && !a->t0) FAIL(h, TDMPC_ERR_INVALID, "plan: t0_all=-1 needs t0[]");
+  cudaSetDevice(h->cfg.device);
+
+  const float* z0 = a->z0;
+  if (!z0) {
+    launch_encode(h->m32, a->obs, B, h->cfg.obs_dim, h->cfg.enc_dim, L, h->z0, st);
+    if (int r = check_launch(h, "encode")) return r;
+    z0 = h->z0;
+  }
+  if (a->tap_z0) CUDA_OK(h, cudaMemcpyAsync(a->tap_z0, z0, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+
+  RolloutParams rp{};
+  rp.B = B; rp.H = H; rp.L = L; rp.A = A; rp.M = h->cfg.mlp_dim; rp.z0 = z0; rp.min_std = a->min_std;
+  fill_disc(a->discount, H, rp.disc);
+
+  // policy trajectories (tdmpc.py:113-118)
+  if (P0 > 0) {
+    RolloutParams pp = rp;
+    pp.mode = MODE_PI; pp.T = P0; pp.Tcap = P0; pp.pi_actions = h->pi_actions;
+    pp.noise = NoiseSrc{a->noise_pi, a->seed, a->call, NS_PI};
+    pp.noise_base = 0; pp.noise_bstride = (uint64_t)H * P0 * A; pp.noise_tstride = (uint64_t)P0 * A;
+    if (int r = run_rollout(h, pp, st)) return r;
+  }
+
+  float* elites = a->elite_actions ? a->elite_actions : h->elites;
+  const NoiseSrc cem{a->noise_cem, a->seed, a->call, NS_CEM};
+  const uint64_t cem_bstride = (uint64_t)I * H * Nmax * A;
+
+  InitParams ip{};
+  ip.B = B; ip.H = H; ip.A = A; ip.N = a->n_samples[0]; ip.E = a->n_reuse[0]; ip.P = a->n_pi[0]; ip.Tcap = Tmax;
+  ip.init_std = a->init_std; ip.t0_all = a->t0_all; ip.t0 = a->t0; ip.has_prev = a->has_prev; ip.warm_last = a->warm_last;
+  ip.prev_mean = a->prev_mean; ip.mean = h->mean; ip.std = h->std; ip.actions = h->actions;
+  ip.pi_actions = h->pi_actions; ip.P0 = P0; ip.elite_actions = elites; ip.K = K; ip.shift_elites = a->shift_elites;
+  ip.cem = cem; ip.cem_base = 0; ip.cem_bstride = cem_bstride; ip.cem_rows = Nmax;
+  ip.best_a = (a->best_a_last && I == 1) ? 1 : 0;
+  launch_init(ip, st);
+  if (int r = check_launch(h, "init")) return r;
+
+  for (int i = 0; i < I; ++i) {
+    const int T = a->n_samples[i] + a->n_reuse[i] + a->n_pi[i];
+    float* values = a->tap_values ? a->tap_values + (size_t)i * B * Tmax : h->values;
+    RolloutParams vp = rp;
+    vp.mode = MODE_VALUE; vp.T = T; vp.Tcap = Tmax; vp.actions = h->actions; vp.values = values; vp.last_reward = h->last_reward;
+    vp.noise = NoiseSrc{a->noise_term, a->seed, a->call, NS_TERM};
+    vp.noise_base = (uint64_t)i * Tmax * A; vp.noise_bstride = (uint64_t)I * Tmax * A;
+    if (int r = run_rollout(h, vp, st)) return r;
+
+    SelectParams sp{};
+    sp.B = B; sp.T = T; sp.Tcap = Tmax; sp.H = H; sp.A = A; sp.K = K; sp.iter = i; sp.n_iters = I;
+    sp.values = values; sp.last_reward = h->last_reward; sp.actions = h->actions;
+    sp.mean = h->mean; sp.std = h->std;
+    sp.temperature = a->temperature; sp.momentum = (float)a->momentum; sp.one_minus_momentum = (float)(1.0 - a->momentum);
+    sp.std_floor = a->std_floor; sp.std_max = a->std_max;
+    sp.elite_idx = h->elite_idx; sp.score = h->score;
+    sp.elite_actions = (a->elite_actions || a->n_reuse[i + 1 < I ? i + 1 : i] > 0) ? elites : nullptr;
+    const bool last = i == I - 1;
+    sp.do_sample = !last; sp.do_output = last;
+    if (!last) {
+      sp.next_N = a->n_samples[i + 1]; sp.next_E = a->n_reuse[i + 1]; sp.next_P = a->n_pi[i + 1];
+      sp.best_a = (a->best_a_last && i + 1 == I - 1) ? 1 : 0;
+      sp.pi_actions = h->pi_actions; sp.P0 = P0;
+      sp.cem = cem; sp.cem_base = (uint64_t)(i + 1) * H * Nmax * A; sp.cem_bstride = cem_bstride; sp.cem_rows = Nmax;
+    }
+    sp.eval_mode = a->eval_mode;
+    sp.out_noise = NoiseSrc{a->noise_out, a->seed, a->call, NS_OUT};
+    sp.pick = NoiseSrc{nullptr, a->seed, a->call, NS_PICK};
+    sp.u_pick = a->u_pick;
+    sp.action = a->action; sp.metrics = a->metrics; sp.prev_mean = a->prev_mean;
+    sp.tap_elite_idx = a->tap_elite_idx; sp.tap_mean = a->tap_mean; sp.tap_std = a->tap_std;
+    launch_select(sp, st);
+    if (int r = check_launch(h, "select")) return r;
+  }
+  return TDMPC_OK;
+}

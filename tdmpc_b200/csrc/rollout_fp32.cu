@@ -1,0 +1,246 @@
+// CUDA-core fp32 trajectory rollout: the "fp32 mode" of the planner (1e-5 parity with the
+// reference).  One CTA owns a tile of 32 trajectories and walks them through the whole horizon
+// with the activations resident in shared memory; weights stream from L2 (they are shared by
+// every CTA).  Restates TDMPC.estimate_value (algorithm/tdmpc.py:83-92) and the policy rollout
+// of TDMPC.plan (tdmpc.py:113-118) on top of TOLD.next / pi / Q (tdmpc.py:34-50).
+#include "common.cuh"
+
+namespace {
+
+constexpr int R = 32;          // trajectories per CTA
+constexpr int NT = 256;        // threads per CTA
+constexpr int NW = NT / 32;
+
+enum Act { ACT_NONE = 0, ACT_ELU = 1 };
+
+// out[r][n] = act( sum_k x[r][k] * Wt[k][n] + b[n] ),  N == 512: 8 rows x 8 cols per thread.
+template <int ACT>
+__device__ void layer512(const float* __restrict__ x, int ldx, const LinearT& lin, float* __restrict__ out, int ldo) {
+  const int tid = threadIdx.x;
+  const int c0 = (tid & 63) * 8;
+  const int r0 = (tid >> 6) * 8;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  const float* wt = lin.wt + c0;
+  for (int k = 0; k < lin.Kp; k += 4) {
+    float4 xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(x + (r0 + i) * ldx + k);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(k + kk) * 512));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(k + kk) * 512 + 4));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xs = kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w;
+        acc[i][0] = fmaf(xs, w0.x, acc[i][0]); acc[i][1] = fmaf(xs, w0.y, acc[i][1]);
+        acc[i][2] = fmaf(xs, w0.z, acc[i][2]); acc[i][3] = fmaf(xs, w0.w, acc[i][3]);
+        acc[i][4] = fmaf(xs, w1.x, acc[i][4]); acc[i][5] = fmaf(xs, w1.y, acc[i][5]);
+        acc[i][6] = fmaf(xs, w1.z, acc[i][6]); acc[i][7] = fmaf(xs, w1.w, acc[i][7]);
+      }
+    }
+  }
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = lin.b ? __ldg(lin.b + c0 + j) : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = acc[i][j] + bv[j];
+      if (ACT == ACT_ELU) v[j] = elu1(v[j]);
+    }
+    float* o = out + (r0 + i) * ldo + c0;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// Generic (any N, K) layer: one output per thread-iteration, lanes sweep n.
+template <int ACT>
+__device__ void layer_any(const float* __restrict__ x, int ldx, const LinearT& lin, float* __restrict__ out, int ldo) {
+  const int N = lin.N;
+  for (int idx = threadIdx.x; idx < R * N; idx += NT) {
+    const int r = idx / N, n = idx - r * N;
+    float acc = 0.0f;
+    const float* xr = x + r * ldx;
+    for (int k = 0; k < lin.K; ++k) acc = fmaf(xr[k], __ldg(lin.wt + (size_t)k * N + n), acc);
+    acc += lin.b ? __ldg(lin.b + n) : 0.0f;
+    if (ACT == ACT_ELU) acc = elu1(acc);
+    out[r * ldo + n] = acc;
+  }
+}
+
+template <int ACT>
+__device__ void layer(const float* x, int ldx, const LinearT& lin, float* out, int ldo) {
+  if (lin.N == 512) layer512<ACT>(x, ldx, lin, out, ldo);
+  else layer_any<ACT>(x, ldx, lin, out, ldo);
+  __syncthreads();
+}
+
+// N == 1 head: out[r] = x[r][:] . w + b  (warp per row)
+__device__ void head_dot(const float* __restrict__ x, int ldx, const LinearT& lin, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += NW) {
+    float acc = 0.0f;
+    for (int k = lane; k < lin.K; k += 32) acc = fmaf(x[r * ldx + k], __ldg(lin.wt + k), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = acc + (lin.b ? __ldg(lin.b) : 0.0f);
+  }
+  __syncthreads();
+}
+
+// nn.LayerNorm over the last dim (biased variance, eps), then tanh or ELU, in place. Warp per row.
+template <bool TANH>
+__device__ void layernorm_act(float* __restrict__ x, int ldx, int n, const LayerNormP& ln, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += NW) {
+    float* xr = x + r * ldx;
+    float s = 0.0f;
+    for (int k = lane; k < n; k += 32) s += xr[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s / (float)n;
+    float v = 0.0f;
+    for (int k = lane; k < n; k += 32) { const float d = xr[k] - mu; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = 1.0f / sqrtf(v / (float)n + eps);
+    for (int k = lane; k < n; k += 32) {
+      const float y = (xr[k] - mu) * rstd * __ldg(ln.g + k) + __ldg(ln.b + k);
+      xr[k] = TANH ? tanhf(y) : elu1(y);
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1) rollout_fp32_kernel(ModelFp32 m, RolloutParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int L = p.L, A = p.A, M = p.M;
+  const int ldz = m.dyn[0].Kp;                 // padded L+A
+  const int ldn = (L + 3) & ~3;
+  float* xa = smem;                            // [R][M]
+  float* xb = xa + R * M;                      // [R][M]
+  float* za = xb + R * M;                      // [R][ldz]   [z | a | 0 pad]
+  float* zn = za + R * ldz;                    // [R][ldn]
+  float* act = zn + R * ldn;                   // [R][A]
+  float* G = act + R * A;                      // [R]
+  float* rr = G + R;                           // [R]
+  float* q1 = rr + R;                          // [R]
+  float* q2 = q1 + R;                          // [R]
+
+  const long long total = (long long)p.B * p.T;
+  const long long g0 = (long long)blockIdx.x * R;
+  const int tid = threadIdx.x;
+
+  for (int idx = tid; idx < R * ldz; idx += NT) {
+    const int r = idx / ldz, c = idx - r * ldz;
+    const long long g = g0 + r;
+    float v = 0.0f;
+    if (g < total && c < L) v = __ldg(p.z0 + (size_t)(g / p.T) * L + c);
+    za[idx] = v;
+  }
+  if (tid < R) { G[tid] = 0.0f; rr[tid] = 0.0f; }
+  __syncthreads();
+
+  // a = pi(z, min_std): tanh(MLP(z)) + truncated noise; written into za[:, L:L+A]
+  auto policy = [&](uint64_t noise_off) {
+    layer<ACT_ELU>(za, ldz, m.pi[0], xa, M);
+    layer<ACT_ELU>(xa, M, m.pi[1], xb, M);
+    layer<ACT_NONE>(xb, M, m.pi[2], act, A);
+    for (int idx = tid; idx < R * A; idx += NT) {
+      const int r = idx / A, a = idx - r * A;
+      const long long g = g0 + r;
+      float v = 0.0f;
+      if (g < total) {
+        const long long b = g / p.T, j = g - b * p.T;
+        const float eps = noise_at(p.noise, p.noise_base + noise_off + (uint64_t)b * p.noise_bstride + (uint64_t)j * A + a);
+        v = policy_sample(tanhf(act[idx]), p.min_std, eps);
+      }
+      za[r * ldz + L + a] = v;
+    }
+    __syncthreads();
+  };
+
+  for (int t = 0; t < p.H; ++t) {
+    if (p.mode == MODE_VALUE) {
+      for (int idx = tid; idx < R * A; idx += NT) {
+        const int r = idx / A, a = idx - r * A;
+        const long long g = g0 + r;
+        float v = 0.0f;
+        if (g < total) {
+          const long long b = g / p.T, j = g - b * p.T;
+          v = __ldg(p.actions + ((size_t)(b * p.Tcap + j) * p.H + t) * A + a);
+        }
+        za[r * ldz + L + a] = v;
+      }
+      __syncthreads();
+    } else {
+      policy((uint64_t)t * p.noise_tstride);
+      for (int idx = tid; idx < R * A; idx += NT) {
+        const int r = idx / A, a = idx - r * A;
+        const long long g = g0 + r;
+        if (g < total) {
+          const long long b = g / p.T, j = g - b * p.T;
+          p.pi_actions[((size_t)(b * p.Tcap + j) * p.H + t) * A + a] = za[r * ldz + L + a];
+        }
+      }
+    }
+    // z' = dynamics([z, a])
+    layer<ACT_ELU>(za, ldz, m.dyn[0], xa, M);
+    layer<ACT_ELU>(xa, M, m.dyn[1], xb, M);
+    layer<ACT_NONE>(xb, M, m.dyn[2], zn, ldn);
+    if (p.mode == MODE_VALUE) {
+      // r = reward([z, a]);  G += gamma^t r
+      layer<ACT_ELU>(za, ldz, m.rew[0], xa, M);
+      layer<ACT_ELU>(xa, M, m.rew[1], xb, M);
+      head_dot(xb, M, m.rew[2], rr);
+      if (tid < R) G[tid] += p.disc[t] * rr[tid];
+    }
+    for (int idx = tid; idx < R * L; idx += NT) {
+      const int r = idx / L, c = idx - r * L;
+      za[r * ldz + c] = zn[r * ldn + c];
+    }
+    __syncthreads();
+  }
+
+  if (p.mode == MODE_VALUE) {
+    policy(0);
+    for (int h = 0; h < 2; ++h) {
+      layer<ACT_NONE>(za, ldz, m.q[h][0], xa, M);
+      layernorm_act<true>(xa, M, M, m.q_ln[h][0], 1e-5f);
+      layer<ACT_NONE>(xa, M, m.q[h][1], xb, M);
+      layernorm_act<false>(xb, M, M, m.q_ln[h][1], 1e-5f);
+      head_dot(xb, M, m.q[h][2], h == 0 ? q1 : q2);
+    }
+    if (tid < R) {
+      const long long g = g0 + tid;
+      if (g < total) {
+        const float v = G[tid] + p.disc[p.H] * min_nanprop(q1[tid], q2[tid]);
+        const long long b = g / p.T, j = g - b * p.T;
+        p.values[b * p.Tcap + j] = nan_to_num0(v);
+        if (p.last_reward) p.last_reward[b * p.Tcap + j] = rr[tid];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void launch_rollout_fp32(const ModelFp32& m, const RolloutParams& p, cudaStream_t st) {
+  const long long total = (long long)p.B * p.T;
+  const int tiles = (int)((total + R - 1) / R);
+  const int ldz = m.dyn[0].Kp, ldn = (p.L + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)2 * R * p.M + (size_t)R * ldz + (size_t)R * ldn + (size_t)R * p.A + 4 * R);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(rollout_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  rollout_fp32_kernel<<<tiles, NT, smem, st>>>(m, p);
+}

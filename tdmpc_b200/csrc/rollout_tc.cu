@@ -1,0 +1,702 @@
+// tcgen05 trajectory rollout: the bf16-operand / fp32-accumulate throughput mode of the planner.
+//
+// One persistent CTA per SM owns tiles of 128 trajectories (TMEM lane = trajectory) and walks
+// each tile through the whole horizon -- TOLD.next (dynamics + reward) per step, then the
+// terminal pi / min(Q1,Q2) (algorithm/tdmpc.py:83-92), or pi + dynamics for the policy rollout
+// (tdmpc.py:113-118) -- without the latent state ever leaving the SM:
+//
+//   warp 0   producer: streams the pre-swizzled bf16 weight tiles (16 KB each, laid out in global
+//            memory in exactly the order they are consumed) from L2 into a shared-memory ring with
+//            bulk-TMA copies (cp.async.bulk ... mbarrier::complete_tx).
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) per k-step.
+//            layer 1: A = [z,a] tile in shared memory (SS);  layer 2: A = h1 in TENSOR MEMORY (TS),
+//            so the 128x512 hidden activation never touches shared memory; layer 3: A = h2 in smem.
+//   warps 2-5 epilogue: thread = trajectory.  tcgen05.ld the fp32 accumulator, add bias, ELU /
+//            LayerNorm+tanh / tanh, then write the next layer's bf16 operand (tcgen05.st to TMEM
+//            or 128B-swizzled st.shared), or reduce the N=1 reward / Q heads as fp32 dot products
+//            and accumulate the discounted return in registers.
+//
+// TMEM map (512 columns): [0,128) [128,256) accumulator ping-pong, [256,512) h1 as bf16x2 (K=512).
+// The Q heads need the whole 512-wide pre-LayerNorm row, so their jobs use all 512 columns.
+// All three roles walk the same job list (tc_model.cuh), which keeps the mbarrier phases aligned.
+#include <cstdio>
+#include <vector>
+
+#include "tc_model.cuh"
+#include "tc_prims.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_ROWS = 128;
+constexpr int NTHREADS = 192;
+constexpr int TILE_BYTES = 16384;
+constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
+constexpr int MAX_JOBS = 17 * TDMPC_MAX_H + 16;
+constexpr uint32_t TM_ACC = 0, TM_A = 256;
+constexpr int MAX_STAGES = 6;
+constexpr int SMEM_LIMIT = 232448;
+
+struct KParams {
+  TcModel m;
+  RolloutParams p;
+  const uint32_t* jobs;
+  int njobs;
+  int stages;
+  int num_tiles;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float elu_fast(float x) {
+  const float e = ex2_approx(x * 1.4426950408889634f) - 1.0f;
+  return x > 0.0f ? x : e;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = ex2_approx(x * 2.8853900817779268f);       // exp(2x)
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+__device__ __forceinline__ float4 ldg4(const float* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
+
+__device__ __forceinline__ int job_tiles(const TcModel& m, uint32_t job) {
+  const int type = job & 7, chain = (job >> 3) & 7;
+  switch (type) {
+    case J_L1: return m.nkb1;
+    case J_L2: return 8;
+    case J_L3: return m.l3rows[chain] == 128 ? 8 : 4;
+    case J_QL1: return 4 * m.nkb1;
+    default: return 32;
+  }
+}
+__device__ __forceinline__ uint32_t job_first_tile(const TcModel& m, uint32_t job) {
+  const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3;
+  const TcChain& c = m.chain[chain];
+  switch (type) {
+    case J_L1: return c.l1_tile + chunk * m.nkb1;
+    case J_L2: return c.l2_tile + chunk * 8;
+    case J_L3: return c.l3_tile;
+    case J_QL1: return c.l1_tile;
+    default: return c.l2_tile;
+  }
+}
+
+// bf16 store of one element of the [z,a] operand (128B-swizzled k-blocks of 64)
+__device__ __forceinline__ void za_store1(uint8_t* za, int row, int k, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(za + (k >> 6) * TILE_BYTES + sw128_offset(row, k & 63)) = __float2bfloat16(v);
+}
+// 8 consecutive k (k0 % 8 == 0) as one 16-byte store
+__device__ __forceinline__ void sw_store8(uint8_t* base, int row, int k0, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(base + (k0 >> 6) * TILE_BYTES + sw128_offset(row, k0 & 63)) = u;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams kp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const TcModel& m = kp.m;
+  const RolloutParams& p = kp.p;
+  const int S = kp.stages;
+
+  // 1024-byte aligned carve-up (the swizzle atoms need it)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* xs = smem;
+  uint8_t* za = xs + XS_BYTES;
+  uint8_t* wring = za + m.nkb1 * TILE_BYTES;
+  uint32_t* sjobs = reinterpret_cast<uint32_t*>(wring + S * TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sjobs + ((kp.njobs + 3) & ~3));
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + MAX_STAGES;
+  uint64_t* acc_full = w_empty + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* act_full = acc_empty + 2;
+  uint64_t* za_full = act_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(za_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < kp.njobs; i += NTHREADS) sjobs[i] = kp.jobs[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 4; ++i) mbar_init(&act_full[i], 128);
+    mbar_init(za_full, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ============================== producer: weight tiles, L2 -> smem ring ==============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int j = 0; j < kp.njobs; ++j) {
+          const uint32_t job = sjobs[j];
+          const int nt = job_tiles(m, job);
+          const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
+          for (int i = 0; i < nt; ++i) {
+            mbar_wait(&w_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
+            bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
+            if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      uint32_t stage = 0, wphase = 0;
+      uint32_t use[2] = {0, 0}, nbuf = 0, za_phase = 0;
+      uint32_t act_phase = 0;                         // bit c = parity to wait for on act_full[c]
+      const uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
+      const int ks1_total = m.K1p / 16;
+
+      auto tile_wait = [&]() -> uint32_t {
+        mbar_wait(&w_full[stage], wphase);
+        tcgen05_fence_after();
+        return ring_addr + stage * TILE_BYTES;
+      };
+      auto tile_release = [&]() {
+        umma_commit(&w_empty[stage]);
+        if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
+      };
+      auto acc_acquire = [&](int b) {
+        mbar_wait(&acc_empty[b], (use[b] & 1) ^ 1);
+        ++use[b];
+      };
+      auto act_wait = [&](int c) {
+        mbar_wait(&act_full[c], (act_phase >> c) & 1);
+        act_phase ^= 1u << c;
+      };
+
+      for (int it = 0; it < my_tiles; ++it)
+        for (int j = 0; j < kp.njobs; ++j) {
+          const uint32_t job = sjobs[j];
+          const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
+          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase); za_phase ^= 1; }
+          if (type == J_L1) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            for (int kb = 0; kb < m.nkb1; ++kb) {
+              const uint32_t wt = tile_wait();
+              const int nks = min(4, ks1_total - kb * 4);
+              for (int ks = 0; ks < nks; ++ks)
+                umma_ss(d, umma_desc_sw128(za_addr + kb * TILE_BYTES + ks * 32), umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
+              tile_release();
+            }
+            umma_commit(&acc_full[b]);
+          } else if (type == J_L2) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            for (int kb = 0; kb < 8; ++kb) {
+              if (chunk == 0 && (kb & 1) == 0) { act_wait(kb >> 1); tcgen05_fence_after(); }
+              const uint32_t wt = tile_wait();
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts(d, tmem + TM_A + kb * 32 + ks * 8, umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
+              tile_release();
+            }
+            umma_commit(&acc_full[b]);
+          } else if (type == J_L3) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
+            const bool half = m.l3rows[chain] == 64;
+            uint32_t wt = 0;
+            for (int kb = 0; kb < 8; ++kb) {
+              if ((kb & 1) == 0) { act_wait(kb >> 1); tcgen05_fence_after(); }
+              if (!half || (kb & 1) == 0) wt = tile_wait();
+              const uint32_t bb = wt + ((half && (kb & 1)) ? 8192u : 0u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ss(d, umma_desc_sw128(xs_addr + kb * TILE_BYTES + ks * 32), umma_desc_sw128(bb + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+              if (!half || (kb & 1)) tile_release();
+            }
+            umma_commit(&acc_full[b]);
+          } else {
+            // Q-head layers: one 512-column accumulator = both ping-pong buffers + the h1 region
+            acc_acquire(0); acc_acquire(1);
+            tcgen05_fence_after();
+            const bool first = type == J_QL1;
+            const int nkb = first ? m.nkb1 : 8;
+            for (int c = 0; c < 4; ++c)
+              for (int kb = 0; kb < nkb; ++kb) {
+                if (!first && c == 0 && (kb & 1) == 0) { act_wait(kb >> 1); tcgen05_fence_after(); }
+                const uint32_t wt = tile_wait();
+                const int nks = first ? min(4, ks1_total - kb * 4) : 4;
+                const uint32_t abase = (first ? za_addr : xs_addr) + kb * TILE_BYTES;
+                for (int ks = 0; ks < nks; ++ks)
+                  umma_ss(tmem + c * 128, umma_desc_sw128(abase + ks * 32), umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
+                tile_release();
+              }
+            umma_commit(&acc_full[0]);
+            umma_commit(&acc_full[1]);
+          }
+        }
+    }
+  } else {
+    // ============================== epilogue: thread = trajectory ==============================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const int L = m.L, A = m.A;
+    const long long total = (long long)p.B * p.T;
+    uint32_t use[2] = {0, 0}, nbuf = 0;
+
+    auto acc_wait = [&](int b) {
+      mbar_wait(&acc_full[b], use[b] & 1);
+      ++use[b];
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const long long g = ((long long)blockIdx.x + (long long)it * gridDim.x) * TILE_ROWS + row;
+      const bool valid = g < total;
+      const long long pb = valid ? g / p.T : 0;
+      const long long pj = valid ? g - pb * p.T : 0;
+      const float* act_row = p.actions ? p.actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
+      float* pi_row = p.pi_actions ? p.pi_actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
+      float G = 0.0f, rlast = 0.0f, dot = 0.0f, q1v = 0.0f;
+
+      // initial [z0, a0, 0...] row
+      {
+        const float* zr = p.z0 + (size_t)pb * L;
+        for (int k0 = 0; k0 < m.nkb1 * 64; k0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            float x = 0.0f;
+            if (valid) {
+              if (k < L) x = __ldg(zr + k);
+              else if (k < L + A && p.mode == MODE_VALUE) x = __ldg(act_row + (k - L));
+            }
+            v[i] = x;
+          }
+          sw_store8(za, row, k0, v);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(za_full);
+      }
+
+      for (int j = 0; j < kp.njobs; ++j) {
+        const uint32_t job = sjobs[j];
+        const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, t = (job >> 8) & 31, flags = job >> 13;
+        const TcChain& ch = m.chain[chain];
+
+        if (type == J_L1) {
+          // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
+          const int b = nbuf; nbuf ^= 1;
+          acc_wait(b);
+          tcgen05_fence_after();
+#pragma unroll 1
+          for (int s = 0; s < 4; ++s) {
+            uint32_t v[32];
+            tmem_ld32(tlane + TM_ACC + b * 128 + s * 32, v);
+            float bias[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = ldg4(ch.b1, chunk * 32 + s * 8 + i);
+              bias[4 * i] = f.x; bias[4 * i + 1] = f.y; bias[4 * i + 2] = f.z; bias[4 * i + 3] = f.w;
+            }
+            tmem_wait_ld();
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              o[i] = pack_bf16x2(elu_fast(__uint_as_float(v[2 * i]) + bias[2 * i]), elu_fast(__uint_as_float(v[2 * i + 1]) + bias[2 * i + 1]));
+            tmem_st16(tlane + TM_A + chunk * 64 + s * 16, o);
+          }
+          tmem_wait_st();
+          tcgen05_fence_before();
+          mbar_arrive(&act_full[chunk]);
+          mbar_arrive(&acc_empty[b]);
+        } else if (type == J_L2) {
+          const int b = nbuf; nbuf ^= 1;
+          acc_wait(b);
+          tcgen05_fence_after();
+          const bool to_xs = chain != CH_REW;
+#pragma unroll 1
+          for (int s = 0; s < 4; ++s) {
+            uint32_t v[32];
+            tmem_ld32(tlane + TM_ACC + b * 128 + s * 32, v);
+            float bias[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = ldg4(ch.b2, chunk * 32 + s * 8 + i);
+              bias[4 * i] = f.x; bias[4 * i + 1] = f.y; bias[4 * i + 2] = f.z; bias[4 * i + 3] = f.w;
+            }
+            tmem_wait_ld();
+            float h[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) h[i] = elu_fast(__uint_as_float(v[i]) + bias[i]);
+            if (to_xs) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sw_store8(xs, row, chunk * 128 + s * 32 + i * 8, h + i * 8);
+            } else {
+              // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 f = ldg4(ch.w3, chunk * 32 + s * 8 + i);
+                dot = fmaf(h[4 * i], f.x, dot); dot = fmaf(h[4 * i + 1], f.y, dot);
+                dot = fmaf(h[4 * i + 2], f.z, dot); dot = fmaf(h[4 * i + 3], f.w, dot);
+              }
+            }
+          }
+          if (to_xs) {
+            fence_proxy_async_smem();
+            mbar_arrive(&act_full[chunk]);
+          } else if (chunk == 3) {
+            const float r = dot + __ldg(ch.b3);
+            G += p.disc[t] * r;                     // G += discount * reward   (tdmpc.py:89)
+            rlast = r;
+            dot = 0.0f;
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&acc_empty[b]);
+        } else if (type == J_L3) {
+          const int b = nbuf; nbuf ^= 1;
+          acc_wait(b);
+          tcgen05_fence_after();
+          if (chain == CH_DYN) {
+            // z' = acc + b3 -> [z', a_{t+1}, 0...] row of the next step
+            const bool next_act = p.mode == MODE_VALUE && !(flags & F_LAST_STEP);
+            // columns >= L+A of the row are zero padding written once per tile and never touched again
+            for (int k0 = 0; k0 < L + A; k0 += 32) {
+              uint32_t v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+              if (k0 < L) { tmem_ld32(tlane + TM_ACC + b * 128 + k0, v); tmem_wait_ld(); }
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const int kk = k0 + c8 * 8;
+                if (kk < L + A) {
+                  float o[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int k = kk + i;
+                    float x = 0.0f;
+                    if (k < L) x = __uint_as_float(v[c8 * 8 + i]) + __ldg(ch.b3 + k);
+                    else if (k < L + A && next_act && valid) x = __ldg(act_row + (size_t)(t + 1) * A + (k - L));
+                    o[i] = x;
+                  }
+                  if (kk + 8 <= L || next_act) sw_store8(za, row, kk, o);     // pure-z group, or the action is replaced too
+                  else {
+                    // group holds action columns that must survive (policy rollout / last step): z elements only
+                    for (int i = 0; i < 8; ++i) if (kk + i < L) za_store1(za, row, kk + i, o[i]);
+                  }
+                }
+              }
+            }
+          } else {
+            // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
+            uint32_t v[32];
+            const bool terminal = (flags & F_TERMINAL) != 0;
+            const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
+            for (int a0 = 0; a0 < A; a0 += 32) {
+              tmem_ld32(tlane + TM_ACC + b * 128 + a0, v);
+              tmem_wait_ld();
+              for (int i = 0; i < 32 && a0 + i < A; ++i) {
+                const int a = a0 + i;
+                float x = 0.0f;
+                if (valid) {
+                  const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
+                  x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
+                  if (!terminal) pi_row[(size_t)t * A + a] = x;
+                }
+                if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
+              }
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&acc_empty[b]);
+          if (!(chain == CH_PI && (flags & F_LAST_STEP))) {
+            fence_proxy_async_smem();
+            mbar_arrive(za_full);
+          }
+        } else {
+          // Q head layer: x = acc + b over all 512 columns, LayerNorm (two-pass statistics), then
+          //   J_QL1: tanh -> bf16 -> XS        J_QL2: ELU -> dot with w3 -> q
+          acc_wait(0); acc_wait(1);
+          tcgen05_fence_after();
+          const bool first = type == J_QL1;
+          const float* bias = first ? ch.b1 : ch.b2;
+          const float* lg = ch.ln_g[first ? 0 : 1];
+          const float* lb = ch.ln_b[first ? 0 : 1];
+          float sum = 0.0f;
+#pragma unroll 1
+          for (int s = 0; s < 16; ++s) {
+            uint32_t v[32];
+            tmem_ld32(tlane + s * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = ldg4(bias, s * 8 + i);
+              sum += (__uint_as_float(v[4 * i]) + f.x) + (__uint_as_float(v[4 * i + 1]) + f.y) +
+                     (__uint_as_float(v[4 * i + 2]) + f.z) + (__uint_as_float(v[4 * i + 3]) + f.w);
+            }
+          }
+          const float mu = sum * (1.0f / 512.0f);
+          float ssq = 0.0f;
+#pragma unroll 1
+          for (int s = 0; s < 16; ++s) {
+            uint32_t v[32];
+            tmem_ld32(tlane + s * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = ldg4(bias, s * 8 + i);
+              float d0 = __uint_as_float(v[4 * i]) + f.x - mu, d1 = __uint_as_float(v[4 * i + 1]) + f.y - mu;
+              float d2 = __uint_as_float(v[4 * i + 2]) + f.z - mu, d3 = __uint_as_float(v[4 * i + 3]) + f.w - mu;
+              ssq = fmaf(d0, d0, ssq); ssq = fmaf(d1, d1, ssq); ssq = fmaf(d2, d2, ssq); ssq = fmaf(d3, d3, ssq);
+            }
+          }
+          const float rstd = 1.0f / sqrtf(ssq * (1.0f / 512.0f) + 1e-5f);
+          float qdot = 0.0f;
+#pragma unroll 1
+          for (int s = 0; s < 16; ++s) {
+            uint32_t v[32];
+            tmem_ld32(tlane + s * 32, v);
+            tmem_wait_ld();
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = ldg4(bias, s * 8 + i), gg = ldg4(lg, s * 8 + i), bb = ldg4(lb, s * 8 + i);
+              y[4 * i] = (__uint_as_float(v[4 * i]) + f.x - mu) * rstd * gg.x + bb.x;
+              y[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + f.y - mu) * rstd * gg.y + bb.y;
+              y[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + f.z - mu) * rstd * gg.z + bb.z;
+              y[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + f.w - mu) * rstd * gg.w + bb.w;
+            }
+            if (first) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = tanh_fast(y[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sw_store8(xs, row, s * 32 + i * 8, y + i * 8);
+              if ((s & 3) == 3) { fence_proxy_async_smem(); mbar_arrive(&act_full[s >> 2]); }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 f = ldg4(ch.w3, s * 8 + i);
+                qdot = fmaf(elu_fast(y[4 * i]), f.x, qdot); qdot = fmaf(elu_fast(y[4 * i + 1]), f.y, qdot);
+                qdot = fmaf(elu_fast(y[4 * i + 2]), f.z, qdot); qdot = fmaf(elu_fast(y[4 * i + 3]), f.w, qdot);
+              }
+            }
+          }
+          if (!first) {
+            const float qv = qdot + __ldg(ch.b3);
+            if (chain == CH_Q1) q1v = qv;
+            else if (valid) {
+              // G += discount * min(Q1, Q2); nan_to_num_   (tdmpc.py:91-92)
+              const float val = G + p.disc[p.H] * min_nanprop(q1v, qv);
+              p.values[pb * p.Tcap + pj] = nan_to_num0(val);
+              if (p.last_reward) p.last_reward[pb * p.Tcap + pj] = rlast;
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&acc_empty[0]);
+          mbar_arrive(&acc_empty[1]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 nn.Linear [N][K] -> bf16 tiles [tile_rows x 64], 128B-swizzled, chunk-major.
+__global__ void pack_tiles_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ dst,
+                                  int n_chunks, int nkb, int tile_rows) {
+  // one thread per 16-byte group (8 consecutive k of one row)
+  const long long total = (long long)n_chunks * nkb * tile_rows * 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i & 7);
+  const int r = (int)((i >> 3) % tile_rows);
+  const long long ckb = (i >> 3) / tile_rows;
+  const int kb = (int)(ckb % nkb), c = (int)(ckb / nkb);
+  const int n = c * 128 + r;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kb * 64 + g * 8 + e;
+    v[e] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.0f;
+  }
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  const size_t tile_off = (size_t)(c * nkb + kb) * tile_rows * 128;
+  *reinterpret_cast<uint4*>(dst + tile_off + sw128_offset(r, g * 8)) = u;
+}
+
+int launch_pack(const float* W, int N, int K, uint8_t* dst, int n_chunks, int nkb, int tile_rows, cudaStream_t st) {
+  const long long total = (long long)n_chunks * nkb * tile_rows * 8;
+  pack_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, N, K, dst, n_chunks, nkb, tile_rows);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+std::vector<uint32_t> build_jobs(int mode, int H) {
+  std::vector<uint32_t> j;
+  auto chain12 = [&](int type, int chain, int t, int first_flags) {
+    for (int c = 0; c < 4; ++c) j.push_back(tc_job(type, chain, c, t, c == 0 ? first_flags : 0));
+  };
+  if (mode == MODE_VALUE) {
+    for (int t = 0; t < H; ++t) {
+      chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
+      chain12(J_L2, CH_DYN, t, 0);
+      chain12(J_L1, CH_REW, t, 0);
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, t == H - 1 ? F_LAST_STEP : 0));
+      chain12(J_L2, CH_REW, t, 0);
+    }
+    chain12(J_L1, CH_PI, 0, F_WAIT_ZA);
+    chain12(J_L2, CH_PI, 0, 0);
+    j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
+    j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
+    j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
+    j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+  } else {
+    for (int t = 0; t < H; ++t) {
+      const bool last = t == H - 1;
+      chain12(J_L1, CH_PI, t, F_WAIT_ZA);
+      chain12(J_L2, CH_PI, t, 0);
+      j.push_back(tc_job(J_L3, CH_PI, 0, t, last ? F_LAST_STEP : 0));
+      if (!last) {                      // the reference also steps z after the last action; its result is unused
+        chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
+        chain12(J_L2, CH_DYN, t, 0);
+        j.push_back(tc_job(J_L3, CH_DYN, 0, t, 0));
+      }
+    }
+  }
+  return j;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+const char* tc_supported(const tdmpc_model_cfg& c) {
+  if (c.mlp_dim != 512) return "mlp_dim must be 512";
+  if (c.latent_dim > 128) return "latent_dim must be <= 128";
+  if (c.latent_dim + c.action_dim > 192) return "latent_dim + action_dim must be <= 192";
+  return nullptr;
+}
+
+static int tc_tiles_total(const tdmpc_model_cfg& c, int* nkb1_out, int l3rows[CH_COUNT]) {
+  const int K1p = (c.latent_dim + c.action_dim + 15) & ~15;
+  const int nkb1 = (K1p + 63) / 64;
+  *nkb1_out = nkb1;
+  const int n3_dyn = (c.latent_dim + 15) & ~15, n3_pi = (c.action_dim + 15) & ~15;
+  for (int i = 0; i < CH_COUNT; ++i) l3rows[i] = 0;
+  l3rows[CH_DYN] = n3_dyn <= 64 ? 64 : 128;
+  l3rows[CH_PI] = n3_pi <= 64 ? 64 : 128;
+  int tiles = 0;
+  for (int ch = 0; ch < CH_COUNT; ++ch) {
+    tiles += 4 * nkb1 + 32;
+    if (l3rows[ch]) tiles += l3rows[ch] == 128 ? 8 : 4;
+  }
+  return tiles;
+}
+
+static size_t jobs_bytes_total() {
+  size_t n = 0;
+  for (int mode = 0; mode < 2; ++mode)
+    for (int H = 1; H <= TDMPC_MAX_H; ++H) n += (build_jobs(mode, H).size() + 3) & ~(size_t)3;
+  return n * sizeof(uint32_t);
+}
+
+size_t tc_arena_bytes(const tdmpc_model_cfg& c) {
+  int nkb1, l3rows[CH_COUNT];
+  return (size_t)tc_tiles_total(c, &nkb1, l3rows) * TILE_BYTES + jobs_bytes_total() + 1024;
+}
+
+int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m32, void* arena, TcModel* out, cudaStream_t st) {
+  TcModel m{};
+  const int L = c.latent_dim, A = c.action_dim;
+  m.L = L; m.A = A;
+  m.K1p = (L + A + 15) & ~15;
+  int nkb1;
+  const int tiles = tc_tiles_total(c, &nkb1, m.l3rows);
+  m.nkb1 = nkb1;
+  m.n3p[CH_DYN] = (L + 15) & ~15;
+  m.n3p[CH_PI] = (A + 15) & ~15;
+  m.tiles = reinterpret_cast<const uint8_t*>(arena);
+  uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  if (cudaMemsetAsync(base, 0, (size_t)tiles * TILE_BYTES, st) != cudaSuccess) return -1;
+
+  const float* W1[CH_COUNT] = {w.dyn_w[0], w.rew_w[0], w.pi_w[0], w.q_w[0][0], w.q_w[1][0]};
+  const float* W2[CH_COUNT] = {w.dyn_w[1], w.rew_w[1], w.pi_w[1], w.q_w[0][1], w.q_w[1][1]};
+  const float* W3[CH_COUNT] = {w.dyn_w[2], nullptr, w.pi_w[2], nullptr, nullptr};
+  const int K1[CH_COUNT] = {L + A, L + A, L, L + A, L + A};
+  const int N3[CH_COUNT] = {L, 0, A, 0, 0};
+  const LinearT* lin[CH_COUNT] = {m32.dyn, m32.rew, m32.pi, m32.q[0], m32.q[1]};
+
+  int launches = 0;
+  uint32_t tile = 0;
+  for (int ch = 0; ch < CH_COUNT; ++ch) {
+    TcChain& t = m.chain[ch];
+    t.l1_tile = tile;
+    if (launch_pack(W1[ch], 512, K1[ch], base + (size_t)tile * TILE_BYTES, 4, nkb1, 128, st) < 0) return -1;
+    tile += 4 * nkb1; ++launches;
+    t.l2_tile = tile;
+    if (launch_pack(W2[ch], 512, 512, base + (size_t)tile * TILE_BYTES, 4, 8, 128, st) < 0) return -1;
+    tile += 32; ++launches;
+    t.l3_tile = tile;
+    if (W3[ch]) {
+      if (launch_pack(W3[ch], N3[ch], 512, base + (size_t)tile * TILE_BYTES, 1, 8, m.l3rows[ch], st) < 0) return -1;
+      tile += m.l3rows[ch] == 128 ? 8 : 4; ++launches;
+    }
+    t.b1 = lin[ch][0].b; t.b2 = lin[ch][1].b; t.b3 = lin[ch][2].b;
+    t.w3 = N3[ch] == 0 ? lin[ch][2].wt : nullptr;      // [512][1] transposed == the weight row itself
+    if (ch >= CH_Q1) {
+      for (int i = 0; i < 2; ++i) { t.ln_g[i] = m32.q_ln[ch - CH_Q1][i].g; t.ln_b[i] = m32.q_ln[ch - CH_Q1][i].b; }
+    }
+  }
+  // job programs for every (mode, horizon)
+  uint32_t* jdst = reinterpret_cast<uint32_t*>(base + (size_t)tiles * TILE_BYTES);
+  std::vector<uint32_t> all;
+  size_t off = 0;
+  for (int mode = 0; mode < 2; ++mode)
+    for (int H = 1; H <= TDMPC_MAX_H; ++H) {
+      std::vector<uint32_t> j = build_jobs(mode, H);
+      m.jobs[mode][H] = jdst + off;
+      m.njobs[mode][H] = (int)j.size();
+      j.resize((j.size() + 3) & ~(size_t)3, 0);
+      all.insert(all.end(), j.begin(), j.end());
+      off += j.size();
+    }
+  // pageable-host source: the runtime stages the bytes before returning, so `all` may die here
+  if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+
+  // shared-memory budget -> weight ring depth
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + MAX_JOBS * 4 + (2 * MAX_STAGES + 9) * 8 + 16 + 1024;
+  int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return -1;
+  m.stages = stages;
+  m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
+  if (cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem_bytes) != cudaSuccess) return -1;
+  *out = m;
+  return launches;
+}
+
+int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st) {
+  if (p.H < 1 || p.H > TDMPC_MAX_H) return -1;
+  KParams kp;
+  kp.m = m; kp.p = p;
+  kp.jobs = m.jobs[p.mode][p.H];
+  kp.njobs = m.njobs[p.mode][p.H];
+  kp.stages = m.stages;
+  const long long total = (long long)p.B * p.T;
+  kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
+  const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
+  rollout_tc_kernel<<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  return 1;
+}

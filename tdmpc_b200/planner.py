@@ -1,0 +1,340 @@
+"""Host side of the B200 planner: a thin Python layer over the C ABI (include/tdmpc_b200.h).
+
+`Planner`    -- batched, stage-level interface (encode / estimate_value / pi_rollout /
+                select_update / plan) on device tensors; PyTorch is used only for device memory and
+                the current CUDA stream.
+`TDMPC`      -- drop-in for the reference agent's planning surface (src/algorithm/tdmpc.py:53-163):
+                same constructor argument, attributes (cfg, device, std, model, model_target,
+                _prev_mean), `plan(obs, eval_mode, step, t0)` signature, return types and side
+                effects.  Training (`update`) is out of scope and stays in the reference.
+`accelerate` -- binds the fast `plan` onto an existing reference agent object in place.
+"""
+import ctypes as C
+import types
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from . import _lib
+from .told import TOLD, linear_schedule
+
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class Planner:
+    """One handle = one model on one GPU.  Not thread-safe; stream-ordered on torch's current stream."""
+
+    def __init__(self, obs_dim, action_dim, latent_dim, mlp_dim=512, enc_dim=256, enc_layernorm=False,
+                 precision="bf16", device=None):
+        self.lib = _lib.load()          # raises if libtdmpc_b200.so is missing: there is no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("tdmpc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.D, self.A, self.L, self.M, self.E = obs_dim, action_dim, latent_dim, mlp_dim, enc_dim
+        self.precision = precision
+        cfg = _lib.ModelCfg(obs_dim, action_dim, latent_dim, mlp_dim, enc_dim, 0, int(bool(enc_layernorm)),
+                            _lib.DYN_MLP, _PREC[precision], self.device.index)
+        self._h = C.c_void_p()
+        rc = self.lib.tdmpc_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"tdmpc_create failed ({rc}): {self.lib.tdmpc_last_error(None).decode()}")
+        self._keep = None               # tensors whose pointers the last set_weights used
+        self._wver = None
+        self._cap = (0, 0, 0, 0)
+        self.call = 0
+        self.seed = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self.lib.tdmpc_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.tdmpc_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.tdmpc_launch_count(self._h))
+
+    def reserve(self, batch, rows, horizon, elites):
+        cap = self._cap
+        if batch > cap[0] or rows > cap[1] or horizon > cap[2] or elites > cap[3]:
+            new = (max(batch, cap[0]), max(rows, cap[1]), max(horizon, cap[2]), max(elites, cap[3]))
+            self._check(self.lib.tdmpc_reserve(self._h, *new), "tdmpc_reserve")
+            self._cap = new
+
+    # ------------------------------------------------------------------ weights
+    def sync_weights(self, model_or_sd, force=False):
+        """(Re)pack the parameters of a TOLD-like module / state_dict.  Cheap no-op when no
+        parameter changed since the last call (tracked through Tensor._version + data_ptr)."""
+        sd = model_or_sd if isinstance(model_or_sd, dict) else dict(model_or_sd.state_dict(keep_vars=True))
+        ln = "_encoder.3.weight" in sd
+        last = "_encoder.3" if ln else "_encoder.2"
+        names = ["_encoder.0", last] + [f"{m}.{i}" for m in ("_dynamics", "_reward", "_pi") for i in (0, 2, 4)] + \
+                [f"{m}.{i}" for m in ("_Q1", "_Q2") for i in (0, 3, 6)]
+        keys = [n + s for n in names for s in (".weight", ".bias")] + \
+               [f"{m}.{i}{s}" for m in ("_Q1", "_Q2") for i in (1, 4) for s in (".weight", ".bias")] + \
+               (["_encoder.1.weight", "_encoder.1.bias"] if ln else [])
+        ver = tuple((sd[k].data_ptr(), sd[k]._version) for k in keys)
+        if not force and ver == self._wver:
+            return False
+        t = {k: _f32(sd[k], self.device) for k in keys}
+        w = _lib.Weights()
+
+        def P(k):
+            return t[k].data_ptr()
+
+        w.enc_w[0], w.enc_b[0] = P("_encoder.0.weight"), P("_encoder.0.bias")
+        w.enc_w[1], w.enc_b[1] = P(last + ".weight"), P(last + ".bias")
+        if ln:
+            w.enc_ln_g, w.enc_ln_b = P("_encoder.1.weight"), P("_encoder.1.bias")
+        for dst_w, dst_b, mod in ((w.dyn_w, w.dyn_b, "_dynamics"), (w.rew_w, w.rew_b, "_reward"), (w.pi_w, w.pi_b, "_pi")):
+            for j, i in enumerate((0, 2, 4)):
+                dst_w[j], dst_b[j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
+        for qi, mod in enumerate(("_Q1", "_Q2")):
+            for j, i in enumerate((0, 3, 6)):
+                w.q_w[qi][j], w.q_b[qi][j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
+            for j, i in enumerate((1, 4)):
+                w.q_ln_g[qi][j], w.q_ln_b[qi][j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
+        shapes = {"_encoder.0.weight": (self.E, self.D), last + ".weight": (self.L, self.E),
+                  "_dynamics.0.weight": (self.M, self.L + self.A), "_dynamics.4.weight": (self.L, self.M),
+                  "_pi.0.weight": (self.M, self.L), "_pi.4.weight": (self.A, self.M), "_Q1.6.weight": (1, self.M)}
+        for k, s in shapes.items():
+            if tuple(t[k].shape) != s:
+                raise RuntimeError(f"sync_weights: {k} has shape {tuple(t[k].shape)}, expected {s}")
+        self._check(self.lib.tdmpc_set_weights(self._h, C.byref(w), self._stream()), "tdmpc_set_weights")
+        self._keep, self._wver = t, ver
+        return True
+
+    # ------------------------------------------------------------------ stage-level entry points
+    def encode(self, obs):
+        """TOLD.h (tdmpc.py:30-32) for obs [B, D] -> z [B, L]."""
+        obs = _f32(obs, self.device)
+        z = torch.empty(obs.shape[0], self.L, device=self.device)
+        self._check(self.lib.tdmpc_encode(self._h, _ptr(obs), obs.shape[0], _ptr(z), self._stream()), "tdmpc_encode")
+        return z
+
+    def estimate_value(self, z0, actions, *, discount, min_std, noise_term=None, seed=0, call=0):
+        """TDMPC.estimate_value (tdmpc.py:83-92).  z0 [B,L]; actions [B,T,H,A]; noise_term [B,T,A]."""
+        z0, actions = _f32(z0, self.device), _f32(actions, self.device)
+        B, T, H, _ = actions.shape
+        values = torch.empty(B, T, device=self.device)
+        last_r = torch.empty(B, T, device=self.device)
+        nz = _f32(noise_term, self.device) if noise_term is not None else None
+        self._check(self.lib.tdmpc_estimate_value(self._h, _ptr(z0), _ptr(actions), _ptr(nz), B, T, H, float(discount),
+                                                  float(min_std), seed, call, _ptr(values), _ptr(last_r), self._stream()),
+                    "tdmpc_estimate_value")
+        return values, last_r
+
+    def pi_rollout(self, z0, rows, horizon, *, min_std, noise_pi=None, seed=0, call=0):
+        """Policy rollout of TDMPC.plan (tdmpc.py:113-118): returns pi_actions [B, P, H, A]."""
+        z0 = _f32(z0, self.device)
+        B = z0.shape[0]
+        out = torch.empty(B, rows, horizon, self.A, device=self.device)
+        nz = _f32(noise_pi, self.device) if noise_pi is not None else None
+        self._check(self.lib.tdmpc_pi_rollout(self._h, _ptr(z0), _ptr(nz), B, rows, horizon, float(min_std), seed, call,
+                                              _ptr(out), self._stream()), "tdmpc_pi_rollout")
+        return out
+
+    def select_update(self, values, actions, mean, std, *, num_elites, temperature, momentum, std_floor, std_max=2.0):
+        """tdmpc.py:138-149.  Updates mean/std [B,H,A] in place; returns (elite_idx [B,K], score [B,K])."""
+        values, actions = _f32(values, self.device), _f32(actions, self.device)
+        B, T, H, _ = actions.shape
+        idx = torch.empty(B, num_elites, dtype=torch.int32, device=self.device)
+        score = torch.empty(B, num_elites, device=self.device)
+        self._check(self.lib.tdmpc_select_update(self._h, _ptr(values), _ptr(actions), B, T, H, num_elites,
+                                                 float(temperature), float(momentum), float(std_floor), float(std_max),
+                                                 _ptr(mean), _ptr(std), _ptr(idx), _ptr(score), self._stream()),
+                    "tdmpc_select_update")
+        return idx, score
+
+    def fill_noise(self, stream_id, count, seed, call):
+        """The built-in Philox stream (so tests can hand the same draws to the oracle)."""
+        out = torch.empty(count, dtype=torch.float64 if stream_id == 4 else torch.float32, device=self.device)
+        self._check(self.lib.tdmpc_fill_noise(self._h, stream_id, seed, call, count, _ptr(out), self._stream()), "tdmpc_fill_noise")
+        return out
+
+    # ------------------------------------------------------------------ the hot path
+    def plan(self, obs=None, *, z0=None, horizon, num_samples, num_pi_trajs, num_elites, iterations, discount,
+             temperature, momentum, min_std, std_floor, std_max=2.0, init_std=2.0, eval_mode=False, t0=True,
+             prev_mean=None, has_prev=None, noise=None, taps=False, seed=None, call=None,
+             n_samples=None, n_reuse=None, n_pi=None, out=None):
+        """TDMPC.plan (tdmpc.py:94-163) for a batch of independent problems.
+
+        obs [B,D] (or z0 [B,L]) on the device.  prev_mean [B,H,A] is read (warm start) and
+        overwritten with the new mean.  Returns dict(action [B,A], metrics [B,2], prev_mean, taps).
+        Everything is enqueued on the current stream; nothing synchronises.
+        """
+        src = obs if z0 is None else z0
+        B = src.shape[0]
+        H, I, K, A = int(horizon), int(iterations), int(num_elites), self.A
+        ns = list(n_samples) if n_samples is not None else [int(num_samples)] * I
+        nr = list(n_reuse) if n_reuse is not None else [0] * I
+        npi = list(n_pi) if n_pi is not None else [int(num_pi_trajs)] * I
+        Tmax = max(a + b + c for a, b, c in zip(ns, nr, npi))
+        Nmax = max(ns)
+        self.reserve(B, max(Tmax, int(num_pi_trajs)), H, K)
+        if prev_mean is None:
+            prev_mean = torch.zeros(B, H, A, device=self.device)
+            has_prev = False if has_prev is None else has_prev
+        elif has_prev is None:
+            has_prev = True
+        a = _lib.PlanArgs()
+        a.batch, a.horizon, a.iterations, a.num_elites, a.num_pi_trajs = B, H, I, K, int(num_pi_trajs)
+        for i in range(I):
+            a.n_samples[i], a.n_reuse[i], a.n_pi[i] = ns[i], nr[i], npi[i]
+        a.discount, a.momentum = float(discount), float(momentum)
+        a.temperature, a.min_std, a.std_floor, a.std_max, a.init_std = temperature, min_std, std_floor, std_max, init_std
+        a.eval_mode = int(bool(eval_mode))
+        keep = []
+        if isinstance(t0, torch.Tensor):
+            t0t = t0.to(device=self.device, dtype=torch.uint8).contiguous(); keep.append(t0t)
+            a.t0_all, a.t0 = -1, t0t.data_ptr()
+        else:
+            a.t0_all = int(bool(t0))
+        a.has_prev = int(bool(has_prev))
+        if z0 is None:
+            obs = _f32(obs, self.device); keep.append(obs); a.obs = obs.data_ptr()
+        else:
+            z0 = _f32(z0, self.device); keep.append(z0); a.z0 = z0.data_ptr()
+        assert prev_mean.is_contiguous() and prev_mean.dtype == torch.float32 and tuple(prev_mean.shape) == (B, H, A)
+        a.prev_mean = prev_mean.data_ptr()
+        a.seed = self.seed if seed is None else seed
+        if call is None:
+            self.call += 1
+            call = self.call
+        a.call = call
+        if noise is not None:
+            exp = {"pi": (B, H, int(num_pi_trajs), A), "cem": (B, I, H, Nmax, A), "term": (B, I, Tmax, A), "out": (B, A)}
+            for k, fld in (("pi", "noise_pi"), ("cem", "noise_cem"), ("term", "noise_term"), ("out", "noise_out")):
+                if noise.get(k) is not None:
+                    t = _f32(noise[k], self.device)
+                    assert tuple(t.shape) == exp[k], (k, tuple(t.shape), exp[k])
+                    keep.append(t); setattr(a, fld, t.data_ptr())
+            if noise.get("u") is not None:
+                u = torch.as_tensor(noise["u"], dtype=torch.float64).reshape(B).to(self.device); keep.append(u)
+                a.u_pick = u.data_ptr()
+        if out is None:
+            out = {"action": torch.empty(B, A, device=self.device), "metrics": torch.empty(B, 2, device=self.device)}
+        a.action, a.metrics = out["action"].data_ptr(), out["metrics"].data_ptr()
+        tp = None
+        if taps:
+            tp = {"values": torch.zeros(I, B, Tmax, device=self.device),
+                  "elite_idx": torch.zeros(I, B, K, dtype=torch.int32, device=self.device),
+                  "mean": torch.zeros(I, B, H, A, device=self.device), "std": torch.zeros(I, B, H, A, device=self.device),
+                  "z0": torch.zeros(B, self.L, device=self.device)}
+            a.tap_values, a.tap_elite_idx = tp["values"].data_ptr(), tp["elite_idx"].data_ptr()
+            a.tap_mean, a.tap_std, a.tap_z0 = tp["mean"].data_ptr(), tp["std"].data_ptr(), tp["z0"].data_ptr()
+        self._check(self.lib.tdmpc_plan(self._h, C.byref(a), self._stream()), "tdmpc_plan")
+        self._keep_call = keep          # inputs must outlive the enqueued kernels
+        return {"action": out["action"], "metrics": out["metrics"], "prev_mean": prev_mean, "taps": tp}
+
+
+# ======================================================================================= drop-in
+def _fast_plan(self, obs, eval_mode=False, step=None, t0=True):
+    """Drop-in for TDMPC.plan (src/algorithm/tdmpc.py:94-163): same arguments, same return
+    `(action Tensor[A] on self.device, {'external_reward_mean': float, 'current_std': float})`,
+    same `self._prev_mean` side effect, same seed-step early return."""
+    cfg = self.cfg
+    plan_metrics = {"external_reward_mean": 0.0, "current_std": 0.0}
+    if step < cfg.seed_steps and not eval_mode:
+        return torch.empty(cfg.action_dim, dtype=torch.float32, device=self.device).uniform_(-1, 1), plan_metrics
+    pl = self._planner
+    pl.sync_weights(self.model)
+    horizon = int(min(cfg.horizon, linear_schedule(cfg.horizon_schedule, step)))
+    num_pi_trajs = int(cfg.mixture_coef * cfg.num_samples)
+    obs_t = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.device, non_blocking=True).reshape(1, -1)
+    prev = getattr(self, "_prev_mean", None)
+    has_prev = prev is not None
+    if has_prev and prev.shape[0] != horizon:
+        # the reference relies on broadcasting `mean[:-1] = prev[1:]`; only an equal-length (or
+        # length-2, i.e. broadcastable) history is meaningful -- emulate it, else fail like torch would
+        tail = prev[1:]
+        if tail.shape[0] not in (1, horizon - 1):
+            raise RuntimeError(f"shape mismatch: _prev_mean has horizon {prev.shape[0]}, plan horizon is {horizon}")
+        prev = torch.cat([prev[:1], tail.expand(horizon - 1, -1)], 0)
+    buf = prev.reshape(1, horizon, cfg.action_dim).contiguous().clone() if has_prev else None
+    noise = getattr(self, "_inject_noise", None)
+    res = pl.plan(obs_t, horizon=horizon, num_samples=cfg.num_samples, num_pi_trajs=num_pi_trajs,
+                  num_elites=cfg.num_elites, iterations=cfg.iterations, discount=cfg.discount,
+                  temperature=cfg.temperature, momentum=cfg.momentum, min_std=cfg.min_std, std_floor=self.std,
+                  eval_mode=eval_mode, t0=bool(t0), prev_mean=buf, has_prev=has_prev, noise=noise,
+                  taps=getattr(self, "_want_taps", False))
+    self._prev_mean = res["prev_mean"][0]
+    self._last_taps = res["taps"]
+    m = res["metrics"][0].tolist()          # one D2H read; the reference syncs here too (.item())
+    plan_metrics.update({"current_std": m[1], "external_reward_mean": m[0]})
+    return res["action"][0], plan_metrics
+
+
+def accelerate(agent, precision="bf16"):
+    """Give an existing reference-style agent (attributes cfg, model, std, device) the CUDA `plan`.
+    The agent's nn.Module keeps owning the parameters; they are re-packed whenever they change."""
+    cfg = agent.cfg
+    sd = agent.model.state_dict()
+    agent._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
+                             enc_layernorm="_encoder.3.weight" in sd, precision=precision, device=agent.device)
+    agent.plan = types.MethodType(_fast_plan, agent)
+    return agent
+
+
+class TDMPC:
+    """Planning half of the reference's TDMPC agent (tdmpc.py:53-163) on the B200 planner."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        dev = getattr(cfg, "device", "cuda")
+        self.device = torch.device(dev if dev != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        self.std = linear_schedule(cfg.std_schedule, 0)
+        self.model = TOLD(cfg).to(self.device)
+        self.model_target = deepcopy(self.model)
+        self.model.eval()
+        self.model_target.eval()
+        self._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
+                                enc_layernorm=getattr(cfg, "enc_layernorm", False),
+                                precision=getattr(cfg, "precision", "bf16"), device=self.device)
+
+    plan = _fast_plan
+
+    def state_dict(self):
+        return {"model": self.model.state_dict(), "model_target": self.model_target.state_dict()}
+
+    def save(self, fp):
+        torch.save(self.state_dict(), fp)
+
+    def load(self, fp):
+        d = torch.load(fp)
+        self.model.load_state_dict(d["model"])
+        self.model_target.load_state_dict(d["model_target"])
+
+    @torch.no_grad()
+    def estimate_value(self, z, actions, horizon):
+        """Reference signature (tdmpc.py:83-92): z [T,L], actions [H,T,A] -> (G [T,1], float)."""
+        self._planner.sync_weights(self.model)
+        # one "problem" per trajectory so every row may start from its own latent
+        acts = actions[:horizon].permute(1, 0, 2).unsqueeze(1).contiguous()      # [T, 1, H, A]
+        v, r = self._planner.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std)
+        return v, float(r.mean().item())
+
+    def update(self, replay_buffer, step):
+        raise NotImplementedError("training stays in the reference's PyTorch code; use tdmpc_b200.accelerate(agent) "
+                                  "on a reference TDMPC to keep update() and gain the CUDA plan()")

@@ -1,0 +1,53 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares,
+and fails loudly (no fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from tdmpc_b200 import _lib
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "tdmpc_b200.h")).read()
+    declared = re.findall(r"TDMPC_API\s+[\w\s\*]+?\b(tdmpc_\w+)\s*\(", hdr)
+    assert len(declared) >= 13 and set(declared) == set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.tdmpc_build_info()
+
+
+def test_struct_layouts_match_header_sizes():
+    # pointer-heavy structs: sizes must be multiples of 8 and the iteration arrays 16 long
+    assert C.sizeof(_lib.ModelCfg) == 40
+    assert C.sizeof(_lib.Weights) == 8 * (2 + 2 + 2 + 3 * 6 + 6 + 6 + 4 + 4)
+    assert _lib.PlanArgs.n_samples.size == 4 * _lib.TDMPC_MAX_ITERS
+    assert C.sizeof(_lib.PlanArgs) % 8 == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    h = C.c_void_p()
+    cfg = _lib.ModelCfg(5, 1, 50, 512, 256, 128, 0, 0, 0, 0)
+    assert lib.tdmpc_create(C.byref(cfg), C.byref(h)) == -3
+    assert b"no CPU fallback" in lib.tdmpc_last_error(None)
+    from tdmpc_b200 import Planner
+    with pytest.raises(RuntimeError):
+        Planner(5, 1, 50)
+
+
+def test_told_state_dict_keys_match_reference_layout():
+    from tdmpc_b200 import TOLD
+    from tests import synth
+    cfg = synth.make_cfg("tiny")
+    m = TOLD(cfg)
+    assert set(m.state_dict().keys()) == set(synth.make_told_weights(cfg).keys())
+    # the reference zero-initialises the reward / Q heads (tdmpc.py:21-23)
+    assert float(m._reward[-1].weight.abs().sum()) == 0.0 and float(m._Q2[-1].bias.abs().sum()) == 0.0
+    m.load_state_dict(synth.make_told_weights(cfg))

@@ -1,0 +1,336 @@
+"""GPU parity tests proper (pytest -m gpu): the CUDA planner, called through the C ABI, against
+the CPU oracle and against the golden fixtures produced by the real reference.
+
+Tolerances (north_star): fp32 mode 1e-5 relative; bf16-operand / fp32-accumulate mode 1e-3
+relative against the oracle run with the SAME quantised operands, compared while elite sets agree.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tdmpc_oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+def _gu():
+    from tests import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("cfg_name,seed", [("tiny", 0), ("cfg1", 0), ("cfg3", 1), ("cfg2s", 2)])
+def test_fp32_plan_matches_oracle_multi_step(cfg_name, seed):
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    pl = gu.make_planner(cfg, sd, "fp32")
+    prev_o, prev_g = None, None
+    for s in range(3):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise(cfg, seed * 100 + s)
+        out_o = gu.oracle_plan(sd, cfg, obs, nz, t0=(s == 0), prev_mean=prev_o)
+        res = pl.plan(torch.from_numpy(obs).cuda().unsqueeze(0), **gu.plan_kwargs(cfg), eval_mode=True, t0=(s == 0),
+                      prev_mean=prev_g, noise=gu.batch_noise([nz]), taps=True)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(res["taps"]["z0"][0].cpu().numpy(), out_o[3]["z0"].numpy(), rtol=1e-5, atol=1e-5)
+        ok = gu.compare_plan(res, 0, out_o, cfg, TOL_FP32, f"{cfg_name} step {s}")
+        prev_o = out_o[2]
+        prev_g = res["prev_mean"] if ok else prev_o.cuda().unsqueeze(0).contiguous()
+
+
+@pytest.mark.parametrize("name,cfg_name", [("tdmpc_tiny", "tiny"), ("tdmpc_cfg1", "cfg1"), ("tdmpc_cfg3", "cfg3"),
+                                           ("tdmpc_cfg2s", "cfg2s"), ("tdmpc_tiny_train", "tiny")])
+def test_fp32_plan_matches_reference_golden(golden_dir, name, cfg_name):
+    """Directly against what the unmodified reference produced (tests/golden/make_golden.py)."""
+    gu = _gu()
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, steps, eval_mode = [int(x) for x in g["meta"]]
+    std_floor = 0.1 if name.endswith("train") else None
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    pl = gu.make_planner(cfg, sd, "fp32")
+    prev = None
+    K = cfg.num_elites
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise(cfg, seed * 100 + s)
+        res = pl.plan(torch.from_numpy(obs).cuda().unsqueeze(0), **gu.plan_kwargs(cfg, std_floor=std_floor),
+                      eval_mode=bool(eval_mode), t0=(s == 0), prev_mean=prev, noise=gu.batch_noise([nz]), taps=True)
+        torch.cuda.synchronize()
+        ref_vals = g[f"s{s}_values"]
+        scale = np.abs(ref_vals).max()
+        same = True
+        for i in range(cfg.iterations):
+            v = res["taps"]["values"][i, 0, :ref_vals.shape[1]].cpu().numpy()
+            assert np.abs(v - ref_vals[i]).max() <= 2e-5 * scale, (s, i)
+            srt = np.sort(ref_vals[i])[::-1]
+            if srt[K - 1] - srt[K] > 1e-4 * scale:
+                assert set(res["taps"]["elite_idx"][i, 0].cpu().tolist()) == set(g[f"s{s}_elite_idx"][i].tolist())
+            else:
+                same = False
+                break
+        if not same:
+            break
+        np.testing.assert_allclose(res["prev_mean"][0].cpu().numpy(), g[f"s{s}_prev_mean"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(res["action"][0].cpu().numpy(), g[f"s{s}_action"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(res["metrics"][0].cpu().numpy().astype(np.float64), g[f"s{s}_metrics"], rtol=1e-4, atol=1e-5)
+        prev = res["prev_mean"]
+
+
+def test_batched_problems_are_independent_fp32():
+    """B problems in one call == the same problems planned one at a time."""
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 5)
+    pl = gu.make_planner(cfg, sd, "fp32")
+    B = 5
+    obs = np.stack([synth.make_obs(cfg, 50 + b) for b in range(B)])
+    nzs = [synth.make_noise(cfg, 50 + b) for b in range(B)]
+    res = pl.plan(torch.from_numpy(obs).cuda(), **gu.plan_kwargs(cfg), eval_mode=False, t0=True, noise=gu.batch_noise(nzs), taps=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        one = pl.plan(torch.from_numpy(obs[b:b + 1]).cuda(), **gu.plan_kwargs(cfg), eval_mode=False, t0=True,
+                      noise=gu.batch_noise([nzs[b]]), taps=True)
+        torch.cuda.synchronize()
+        assert torch.equal(one["action"][0], res["action"][b])
+        assert torch.equal(one["taps"]["values"][:, 0], res["taps"]["values"][:, b])
+        assert torch.equal(one["prev_mean"][0], res["prev_mean"][b])
+        out_o = gu.oracle_plan(sd, cfg, obs[b], nzs[b], t0=True, prev_mean=None, eval_mode=False)
+        gu.compare_plan(res, b, out_o, cfg, TOL_FP32, f"batched b={b}")
+
+
+def test_per_problem_t0_flags():
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 6)
+    pl = gu.make_planner(cfg, sd, "fp32")
+    B = 3
+    H, A = 3, cfg.action_dim
+    obs = np.stack([synth.make_obs(cfg, 70 + b) for b in range(B)])
+    nzs = [synth.make_noise(cfg, 70 + b) for b in range(B)]
+    prev = torch.from_numpy(np.random.RandomState(3).uniform(-0.5, 0.5, (B, H, A)).astype(np.float32))
+    t0 = torch.tensor([1, 0, 0], dtype=torch.uint8)
+    res = pl.plan(torch.from_numpy(obs).cuda(), **gu.plan_kwargs(cfg), eval_mode=True, t0=t0.cuda(), prev_mean=prev.cuda().clone(),
+                  noise=gu.batch_noise(nzs), taps=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        out_o = gu.oracle_plan(sd, cfg, obs[b], nzs[b], t0=bool(t0[b]), prev_mean=prev[b])
+        gu.compare_plan(res, b, out_o, cfg, TOL_FP32, f"t0 b={b}")
+
+
+def _stagewise(cfg_name, seed, precision, tol):
+    """Teacher-forced stage parity: estimate_value on the oracle's own action rows, so one legitimate
+    elite flip cannot compound."""
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    quant = precision == "bf16"
+    pl = gu.make_planner(cfg, sd, precision)
+    H, N, P, T = synth.plan_dims(cfg)
+    obs = synth.make_obs(cfg, seed)
+    rs = np.random.RandomState(seed + 7)
+    z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
+    zg = pl.encode(torch.from_numpy(obs).cuda().unsqueeze(0))
+    np.testing.assert_allclose(zg.cpu().numpy(), z0.numpy(), rtol=1e-5, atol=1e-5)
+    # policy rollout
+    eps_pi = torch.from_numpy(rs.standard_normal((H, P, cfg.action_dim)).astype(np.float32))
+    pi_o = torch.empty(H, P, cfg.action_dim)
+    z = z0.repeat(P, 1)
+    for t in range(H):
+        pi_o[t] = O.told_pi(sd, z, cfg.min_std, eps_pi[t], quant)
+        z, _ = O.told_next(sd, z, pi_o[t], quant)
+    pi_g = pl.pi_rollout(z0.cuda(), P, H, min_std=cfg.min_std, noise_pi=eps_pi.unsqueeze(0))
+    err_pi = (pi_g[0].permute(1, 0, 2).cpu() - pi_o).abs().max().item()
+    assert err_pi <= 20 * tol, f"pi rollout abs err {err_pi:.3e}"
+    # value of random action rows
+    actions = torch.from_numpy(rs.uniform(-1, 1, (H, T, cfg.action_dim)).astype(np.float32))
+    eps_t = torch.from_numpy(rs.standard_normal((T, cfg.action_dim)).astype(np.float32))
+    v_o, r_o = O.estimate_value(sd, z0.repeat(T, 1), actions, H, cfg.discount, cfg.min_std, eps_t, quant)
+    v_g, r_g = pl.estimate_value(z0.cuda(), actions.permute(1, 0, 2).unsqueeze(0).contiguous(), discount=cfg.discount,
+                                 min_std=cfg.min_std, noise_term=eps_t.unsqueeze(0))
+    torch.cuda.synchronize()
+    scale = v_o.abs().max().item()
+    err = (v_g[0].cpu() - v_o.squeeze(1)).abs().max().item() / scale
+    assert err <= tol, f"{cfg_name} {precision}: value rel err {err:.3e} > {tol}"
+    assert abs(r_g.mean().item() - r_o) <= 10 * tol * max(1.0, abs(r_o))
+    return err
+
+
+@pytest.mark.parametrize("cfg_name,seed", [("tiny", 0), ("cfg1", 1), ("cfg3", 2), ("cfg2s", 3), ("cfg2", 4)])
+def test_fp32_stagewise(cfg_name, seed):
+    _stagewise(cfg_name, seed, "fp32", TOL_FP32)
+
+
+@pytest.mark.parametrize("cfg_name,seed", [("tiny", 0), ("cfg1", 1), ("cfg3", 2), ("cfg2s", 3), ("cfg2", 4)])
+def test_bf16_stagewise(cfg_name, seed):
+    _stagewise(cfg_name, seed, "bf16", TOL_BF16)
+
+
+@pytest.mark.parametrize("cfg_name,seed", [("tiny", 0), ("cfg1", 0), ("cfg3", 1)])
+def test_bf16_plan_matches_quantised_oracle(cfg_name, seed):
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    prev_o = None
+    full = 0
+    for s in range(2):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise(cfg, seed * 100 + s)
+        out_o = gu.oracle_plan(sd, cfg, obs, nz, t0=(s == 0), prev_mean=prev_o, quant=True)
+        prev_g = None if prev_o is None else prev_o.cuda().unsqueeze(0).contiguous()   # teacher-forced warm start
+        res = pl.plan(torch.from_numpy(obs).cuda().unsqueeze(0), **gu.plan_kwargs(cfg), eval_mode=True, t0=(s == 0),
+                      prev_mean=prev_g, noise=gu.batch_noise([nz]), taps=True)
+        torch.cuda.synchronize()
+        full += int(gu.compare_plan(res, 0, out_o, cfg, TOL_BF16, f"bf16 {cfg_name} step {s}"))
+        prev_o = out_o[2]
+    print(f"bf16 {cfg_name}: {full}/2 plans identical elite sets through all iterations")
+
+
+def test_bf16_multi_tile_batch_matches_single():
+    """More trajectories than one 128-row tile, several problems, tiles spanning problem boundaries."""
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")            # T = 120 rows per problem -> tiles straddle problems
+    sd = synth.make_told_weights(cfg, 9)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    B = 7
+    obs = np.stack([synth.make_obs(cfg, 90 + b) for b in range(B)])
+    nzs = [synth.make_noise(cfg, 90 + b) for b in range(B)]
+    res = pl.plan(torch.from_numpy(obs).cuda(), **gu.plan_kwargs(cfg), eval_mode=True, t0=True, noise=gu.batch_noise(nzs), taps=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        one = pl.plan(torch.from_numpy(obs[b:b + 1]).cuda(), **gu.plan_kwargs(cfg), eval_mode=True, t0=True,
+                      noise=gu.batch_noise([nzs[b]]), taps=True)
+        torch.cuda.synchronize()
+        assert torch.equal(one["taps"]["values"][:, 0], res["taps"]["values"][:, b]), b
+        assert torch.equal(one["action"][0], res["action"][b])
+
+
+def test_select_update_properties():
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    pl = gu.make_planner(cfg, synth.make_told_weights(cfg, 0), "fp32")
+    A = cfg.action_dim
+    rs = np.random.RandomState(0)
+    for (B, T, H, K) in [(3, 97, 3, 16), (2, 537, 5, 64), (1, 64, 2, 64), (2, 1544, 10, 32), (1, 2048, 4, 128)]:
+        values = torch.from_numpy(rs.standard_normal((B, T)).astype(np.float32))
+        actions = torch.from_numpy(rs.uniform(-1, 1, (B, T, H, A)).astype(np.float32))
+        mean0 = torch.from_numpy(rs.uniform(-1, 1, (B, H, A)).astype(np.float32))
+        mean_g, std_g = mean0.cuda().clone(), torch.ones(B, H, A).cuda()
+        idx, score = pl.select_update(values, actions, mean_g, std_g, num_elites=K, temperature=0.5, momentum=0.1, std_floor=0.05)
+        torch.cuda.synchronize()
+        for b in range(B):
+            e = O.topk_desc(values[b], K)
+            assert idx[b].cpu().tolist() == e.tolist()                       # sorted descending, exact
+            m, s, sc = O.cem_update(values[b][e].unsqueeze(1), actions[b][e].permute(1, 0, 2), mean0[b], 0.5, 0.1, 0.05)
+            np.testing.assert_allclose(mean_g[b].cpu().numpy(), m.numpy(), atol=2e-6)
+            np.testing.assert_allclose(std_g[b].cpu().numpy(), s.numpy(), atol=2e-6)
+            np.testing.assert_allclose(score[b].cpu().numpy(), sc.squeeze(1).numpy(), atol=1e-6)
+        # permutation invariance of the update
+        perm = torch.from_numpy(rs.permutation(T))
+        mean_p, std_p = mean0.cuda().clone(), torch.ones(B, H, A).cuda()
+        idx_p, _ = pl.select_update(values[:, perm], actions[:, perm], mean_p, std_p, num_elites=K, temperature=0.5,
+                                    momentum=0.1, std_floor=0.05)
+        torch.cuda.synchronize()
+        assert torch.equal(perm.cuda()[idx_p.long()], idx.long())
+        assert torch.allclose(mean_p, mean_g, atol=1e-6) and torch.allclose(std_p, std_g, atol=1e-6)
+
+
+def test_select_update_ties_and_specials():
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    pl = gu.make_planner(cfg, synth.make_told_weights(cfg, 0), "fp32")
+    A, H, T, K = cfg.action_dim, 2, 100, 10
+    actions = torch.rand(1, T, H, A) * 2 - 1
+    # all-equal values (the reference's zero-initialised heads, SURVEY TL;DR 4): lowest indices win
+    idx, score = pl.select_update(torch.zeros(1, T), actions, torch.zeros(1, H, A).cuda(), torch.ones(1, H, A).cuda(),
+                                  num_elites=K, temperature=0.5, momentum=0.1, std_floor=0.05)
+    assert idx[0].cpu().tolist() == list(range(K))
+    assert torch.allclose(score.cpu(), torch.full((1, K), 1.0 / K))
+    # +-FLT_MAX (what nan_to_num produces for +-inf) and duplicates
+    v = torch.randn(1, T)
+    v[0, 7] = 3.4028234663852886e38; v[0, 9] = -3.4028234663852886e38; v[0, 20] = v[0, 21] = 5.0
+    mean, std = torch.zeros(1, H, A).cuda(), torch.ones(1, H, A).cuda()
+    idx, score = pl.select_update(v, actions, mean, std, num_elites=K, temperature=0.5, momentum=0.1, std_floor=0.05)
+    l = idx[0].cpu().tolist()
+    assert l[0] == 7 and l[1:3] == [20, 21] and 9 not in l
+    assert torch.isfinite(mean).all() and torch.isfinite(std).all()
+
+
+def test_value_nan_guard():
+    """nan_to_num_(0) of estimate_value (tdmpc.py:92): a NaN weight must give value 0, not NaN."""
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 0)
+    sd["_reward.4.bias"] = torch.tensor([float("nan")])
+    for prec in ("fp32", "bf16"):
+        pl = gu.make_planner(cfg, sd, prec)
+        z0 = torch.randn(1, cfg.latent_dim)
+        acts = torch.rand(1, 40, 3, cfg.action_dim) * 2 - 1
+        v, _ = pl.estimate_value(z0, acts, discount=0.99, min_std=0.05)
+        assert torch.equal(v.cpu(), torch.zeros(1, 40))
+
+
+def test_philox_stream_statistics_and_replay():
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 0)
+    pl = gu.make_planner(cfg, sd, "fp32")
+    x = pl.fill_noise(1, 1 << 20, seed=123, call=7).cpu().double()
+    assert abs(x.mean().item()) < 5e-3 and abs(x.std().item() - 1) < 5e-3
+    assert abs((x ** 4).mean().item() - 3) < 0.05
+    u = pl.fill_noise(4, 1 << 16, seed=123, call=7).cpu()
+    assert 0 <= u.min().item() and u.max().item() < 1 and abs(u.mean().item() - 0.5) < 5e-3
+    assert not torch.equal(pl.fill_noise(1, 64, 123, 8), pl.fill_noise(1, 64, 123, 7))
+    # a plan driven by the built-in stream == the same plan with that stream injected as buffers
+    H, N, P, T = synth.plan_dims(cfg)
+    A, I, B = cfg.action_dim, cfg.iterations, 2
+    obs = torch.from_numpy(np.stack([synth.make_obs(cfg, b) for b in range(B)])).cuda()
+    kw = gu.plan_kwargs(cfg)
+    r1 = pl.plan(obs, **kw, eval_mode=False, t0=True, seed=99, call=5, taps=True)
+    noise = {"pi": pl.fill_noise(0, B * H * P * A, 99, 5).view(B, H, P, A), "cem": pl.fill_noise(1, B * I * H * N * A, 99, 5).view(B, I, H, N, A),
+             "term": pl.fill_noise(2, B * I * T * A, 99, 5).view(B, I, T, A), "out": pl.fill_noise(3, B * A, 99, 5).view(B, A),
+             "u": pl.fill_noise(4, B, 99, 5).cpu().numpy()}
+    r2 = pl.plan(obs, **kw, eval_mode=False, t0=True, seed=1, call=1, noise=noise, taps=True)
+    torch.cuda.synchronize()
+    assert torch.equal(r1["action"], r2["action"]) and torch.equal(r1["taps"]["values"], r2["taps"]["values"])
+
+
+def test_dropin_agent_surface():
+    """TDMPC drop-in: signature, return types, seed-step early return, _prev_mean side effect, weight refresh."""
+    from tdmpc_b200 import TDMPC
+    gu = _gu()
+    cfg = synth.make_cfg("tiny", device="cuda", precision="fp32")
+    agent = TDMPC(cfg)
+    sd = synth.make_told_weights(cfg, 0)
+    agent.model.load_state_dict(sd)
+    assert agent.std == 0.5
+    a, m = agent.plan(synth.make_obs(cfg, 0), eval_mode=False, step=0, t0=True)           # seed step
+    assert a.shape == (cfg.action_dim,) and a.is_cuda and m == {"external_reward_mean": 0.0, "current_std": 0.0}
+    assert not hasattr(agent, "_prev_mean")
+    agent.std = cfg.min_std
+    prev_o = None
+    for s in range(2):
+        obs, nz = synth.make_obs(cfg, s), synth.make_noise(cfg, s)
+        agent._inject_noise = gu.batch_noise([nz]); agent._want_taps = True
+        a, m = agent.plan(obs, eval_mode=True, step=10 ** 6, t0=(s == 0))
+        a_o, m_o, prev_o, _ = gu.oracle_plan(sd, cfg, obs, nz, t0=(s == 0), prev_mean=prev_o)
+        assert isinstance(m["current_std"], float) and a.shape == (cfg.action_dim,) and a.is_cuda
+        np.testing.assert_allclose(a.cpu().numpy(), a_o.numpy(), atol=5e-4)
+        np.testing.assert_allclose(agent._prev_mean.cpu().numpy(), prev_o.numpy(), atol=5e-4)
+        assert abs(m["external_reward_mean"] - m_o["external_reward_mean"]) < 1e-3
+    # an in-place parameter update (what agent.update() does) must be picked up by the next plan
+    with torch.no_grad():
+        agent.model._reward[-1].bias.add_(1.0)
+    sd2 = {k: v.clone() for k, v in sd.items()}; sd2["_reward.4.bias"] = sd["_reward.4.bias"] + 1.0
+    obs, nz = synth.make_obs(cfg, 5), synth.make_noise(cfg, 5)
+    agent._inject_noise = gu.batch_noise([nz])
+    a, m = agent.plan(obs, eval_mode=True, step=10 ** 6, t0=True)
+    _, m_o, _, _ = gu.oracle_plan(sd2, cfg, obs, nz, t0=True, prev_mean=None)
+    assert abs(m["external_reward_mean"] - m_o["external_reward_mean"]) < 1e-3
