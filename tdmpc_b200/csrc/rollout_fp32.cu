@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_fp32_kernel(ModelFp32 m, Rollou
       layer<ACT_ELU>(za, ldz, m.rew[0], xa, M);
       layer<ACT_ELU>(xa, M, m.rew[1], xb, M);
       head_dot(xb, M, m.rew[2], rr);
-      if (tid < R) G[tid] += p.disc[t] * rr[tid];
+      if (tid < R) G[tid] = __fadd_rn(G[tid], __fmul_rn(p.disc[t], rr[tid]));   // mul, then add, as torch does
     }
     for (int idx = tid; idx < R * L; idx += NT) {
       const int r = idx / L, c = idx - r * L;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_fp32_kernel(ModelFp32 m, Rollou
     if (tid < R) {
       const long long g = g0 + tid;
       if (g < total) {
-        const float v = G[tid] + p.disc[p.H] * min_nanprop(q1[tid], q2[tid]);
+        const float v = __fadd_rn(G[tid], __fmul_rn(p.disc[p.H], min_nanprop(q1[tid], q2[tid])));
         const long long b = g / p.T, j = g - b * p.T;
         p.values[b * p.Tcap + j] = nan_to_num0(v);
         if (p.last_reward) p.last_reward[b * p.Tcap + j] = rr[tid];

@@ -108,8 +108,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint64_t* w_empty = w_full + MAX_STAGES;
   uint64_t* acc_full = w_empty + MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* act_full = acc_empty + 2;
-  uint64_t* za_full = act_full + 4;
+  uint64_t* h1_full = acc_empty + 2;     // h1 chunk c written to TMEM (layer-1 epilogue -> layer-2 MMAs)
+  uint64_t* xs_full = h1_full + 4;       // XS chunk c written to smem  (layer-2 / QL1 epilogue -> layer-3 / QL2 MMAs)
+  uint64_t* za_full = xs_full + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(za_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-    for (int i = 0; i < 4; ++i) mbar_init(&act_full[i], 128);
+    for (int i = 0; i < 4; ++i) { mbar_init(&h1_full[i], 128); mbar_init(&xs_full[i], 128); }
     mbar_init(za_full, 128);
     fence_barrier_init();
   }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           const int nt = job_tiles(m, job);
           const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
           for (int i = 0; i < nt; ++i) {
-            mbar_wait(&w_empty[stage], phase ^ 1);
+            mbar_wait(&w_empty[stage], phase ^ 1, 1);
             mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
             bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
             if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
@@ -151,13 +152,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     if (lane == 0) {
       uint32_t stage = 0, wphase = 0;
       uint32_t use[2] = {0, 0}, nbuf = 0, za_phase = 0;
-      uint32_t act_phase = 0;                         // bit c = parity to wait for on act_full[c]
+      // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
+      // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
+      // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
+      uint32_t h1_phase = 0, xs_phase = 0;
       const uint32_t idesc128 = umma_idesc_bf16(128, 128);
       const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
       const int ks1_total = m.K1p / 16;
 
       auto tile_wait = [&]() -> uint32_t {
-        mbar_wait(&w_full[stage], wphase);
+        mbar_wait(&w_full[stage], wphase, 2);
         tcgen05_fence_after();
         return ring_addr + stage * TILE_BYTES;
       };
@@ -166,19 +170,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
       };
       auto acc_acquire = [&](int b) {
-        mbar_wait(&acc_empty[b], (use[b] & 1) ^ 1);
+        mbar_wait(&acc_empty[b], (use[b] & 1) ^ 1, 3);
         ++use[b];
       };
-      auto act_wait = [&](int c) {
-        mbar_wait(&act_full[c], (act_phase >> c) & 1);
-        act_phase ^= 1u << c;
+      auto h1_wait = [&](int c) {
+        mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
+        h1_phase ^= 1u << c;
+      };
+      auto xs_wait = [&](int c) {
+        mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
+        xs_phase ^= 1u << c;
       };
 
       for (int it = 0; it < my_tiles; ++it)
         for (int j = 0; j < kp.njobs; ++j) {
           const uint32_t job = sjobs[j];
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
-          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase); za_phase ^= 1; }
+          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tcgen05_fence_after();
             const uint32_t d = tmem + TM_ACC + b * 128;
             for (int kb = 0; kb < 8; ++kb) {
-              if (chunk == 0 && (kb & 1) == 0) { act_wait(kb >> 1); tcgen05_fence_after(); }
+              if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
               const uint32_t wt = tile_wait();
               for (int ks = 0; ks < 4; ++ks)
                 umma_ts(d, tmem + TM_A + kb * 32 + ks * 8, umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const bool half = m.l3rows[chain] == 64;
             uint32_t wt = 0;
             for (int kb = 0; kb < 8; ++kb) {
-              if ((kb & 1) == 0) { act_wait(kb >> 1); tcgen05_fence_after(); }
+              if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
               if (!half || (kb & 1) == 0) wt = tile_wait();
               const uint32_t bb = wt + ((half && (kb & 1)) ? 8192u : 0u);
               for (int ks = 0; ks < 4; ++ks)
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const int nkb = first ? m.nkb1 : 8;
             for (int c = 0; c < 4; ++c)
               for (int kb = 0; kb < nkb; ++kb) {
-                if (!first && c == 0 && (kb & 1) == 0) { act_wait(kb >> 1); tcgen05_fence_after(); }
+                if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
                 const uint32_t wt = tile_wait();
                 const int nks = first ? min(4, ks1_total - kb * 4) : 4;
                 const uint32_t abase = (first ? za_addr : xs_addr) + kb * TILE_BYTES;
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     uint32_t use[2] = {0, 0}, nbuf = 0;
 
     auto acc_wait = [&](int b) {
-      mbar_wait(&acc_full[b], use[b] & 1);
+      mbar_wait(&acc_full[b], use[b] & 1, 7);
       ++use[b];
     };
 
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           }
           tmem_wait_st();
           tcgen05_fence_before();
-          mbar_arrive(&act_full[chunk]);
+          mbar_arrive(&h1_full[chunk]);
           mbar_arrive(&acc_empty[b]);
         } else if (type == J_L2) {
           const int b = nbuf; nbuf ^= 1;
@@ -352,10 +360,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           }
           if (to_xs) {
             fence_proxy_async_smem();
-            mbar_arrive(&act_full[chunk]);
+            mbar_arrive(&xs_full[chunk]);
           } else if (chunk == 3) {
             const float r = dot + __ldg(ch.b3);
-            G += p.disc[t] * r;                     // G += discount * reward   (tdmpc.py:89)
+            G = __fadd_rn(G, __fmul_rn(p.disc[t], r));   // G += discount * reward (tdmpc.py:89): mul, then add, as torch does
             rlast = r;
             dot = 0.0f;
           }
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int i = 0; i < 32; ++i) y[i] = tanh_fast(y[i]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) sw_store8(xs, row, s * 32 + i * 8, y + i * 8);
-              if ((s & 3) == 3) { fence_proxy_async_smem(); mbar_arrive(&act_full[s >> 2]); }
+              if ((s & 3) == 3) { fence_proxy_async_smem(); mbar_arrive(&xs_full[s >> 2]); }
             } else {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -494,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             if (chain == CH_Q1) q1v = qv;
             else if (valid) {
               // G += discount * min(Q1, Q2); nan_to_num_   (tdmpc.py:91-92)
-              const float val = G + p.disc[p.H] * min_nanprop(q1v, qv);
+              const float val = __fadd_rn(G, __fmul_rn(p.disc[p.H], min_nanprop(q1v, qv)));
               p.values[pb * p.Tcap + pj] = nan_to_num0(val);
               if (p.last_reward) p.last_reward[pb * p.Tcap + pj] = rlast;
             }
@@ -676,7 +684,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + MAX_JOBS * 4 + (2 * MAX_STAGES + 9) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + MAX_JOBS * 4 + (2 * MAX_STAGES + 13) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return -1;

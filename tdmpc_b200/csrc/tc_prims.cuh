@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace tc {
 
@@ -31,8 +32,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+// Bounded wait: a protocol bug must end in a trap with a diagnostic, never in a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar_smem, uint32_t parity, int tag) {
+  printf("tdmpc_b200: mbarrier wait timed out (tag %d, smem 0x%x, parity %u, block %d, thread %d)\n", tag, bar_smem, parity,
+         (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(smem_u32(bar), parity, tag);
+  }
 }
 
 // ------------------------------------------------------------------------------- fences
