@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the TD-MPC planning hot path (BASELINE.json metric: plans/sec and rollout
+sample-steps/sec at 1/2/4/8 B200 next to the host-CPU plan()).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--batch B] [--precision bf16]
+  python bench.py --impl reference ...     # the reference's CPU plan() (oracle port) on the host cores
+
+A "step" is one TDMPC.plan() over one batch of B independent environments (synthetic observations,
+random-init TOLD weights with re-randomised heads).  Default workload = BASELINE.json configs[2]
+(quadrotor batched planning, 4096 env instances per GPU): the largest configuration the metric is
+quoted on; configs[0]/[1] (single-env cartpole / dog-run) are B=1 latency cases and are reported
+under "extra".  N>1: one process per GPU (torchrun), weak scaling -- every rank plans its own B
+environments, no data-path collective, one all-gather of the planned actions per step.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import synth  # noqa: E402  (deterministic synthetic weights / observations)
+
+WORKLOADS = {
+    # name: (cfg name in tests/synth.py, default batch per GPU, description)
+    "cfg3": ("cfg3", 4096, "quadrotor batched planning: obs 18, act 4, L=50, M=512, H=5, N=512, P=25, K=64, I=6"),
+    "cfg1": ("cfg1", 1, "TD-MPC state default (cartpole dims): obs 5, act 1, L=50, M=512, H=5, N=512, P=25, K=64, I=6"),
+    "cfg2": ("cfg2", 1, "dog-run dims: obs 223, act 38, L=100, M=512, H=5, N=512, P=25, K=64, I=8"),
+    "cfg2s": ("cfg2s", 1, "dog-run dims with L=50, I=6"),
+}
+
+
+def flops_and_steps(cfg):
+    from oracle.tdmpc_oracle import flops_per_plan, sample_steps_per_plan  # accounting formulas only
+    H, N, P, T = synth.plan_dims(cfg)
+    rows = [T] * cfg.iterations
+    f = flops_per_plan(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, H, rows, P)
+    return f, sample_steps_per_plan(H, rows, P), (H, N, P, T)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1420.0), d.get("bf16_tflops", 1701.7), d.get("hbm_gbs", 6448.7), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_plan_rate(cfg, sd, budget_s, max_plans=64):
+    """The reference's CPU plan() restated (oracle/tdmpc_oracle.py issues the same aten CPU ops in the
+    same order as /root/reference/src/algorithm/tdmpc.py:94-163), timed on this box's host cores.
+    Bounded sample: single-environment plans until `budget_s` seconds are spent."""
+    from oracle import tdmpc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    prev, times = None, []
+    t_start = time.perf_counter()
+    i = 0
+    while True:
+        obs = synth.make_obs(cfg, 9000 + i)
+        nz = synth.make_noise(cfg, 9000 + i)
+        t = time.perf_counter()
+        _, _, prev, _ = O.plan_tdmpc(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(i == 0), prev_mean=prev,
+                                     std_floor=cfg.min_std, noise=nz)
+        dt = time.perf_counter() - t
+        if i >= 2:            # first calls warm MKL / allocator
+            times.append(dt)
+        i += 1
+        if (time.perf_counter() - t_start > budget_s and len(times) >= 3) or len(times) >= max_plans:
+            break
+    med = float(np.median(times))
+    return 1.0 / med, len(times), med
+
+
+def run_reference(args, cfg, desc, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python
+    reference itself cannot travel to the GPU box), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    sd = synth.make_told_weights(cfg, 0)
+    F, S, (H, N, P, T) = flops_and_steps(cfg)
+    per_step = 4                      # plans per "step": a bounded sample of the B-environment batch
+    times = []
+    from oracle import tdmpc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    prev = None
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        for j in range(per_step):
+            obs, nz = synth.make_obs(cfg, 100 * s + j), synth.make_noise(cfg, 100 * s + j)
+            _, _, prev, _ = O.plan_tdmpc(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(s == 0 and j == 0), prev_mean=prev,
+                                         std_floor=cfg.min_std, noise=nz)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t)
+    ms = 1e3 * float(np.mean(times))
+    value = per_step / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "plans/sec", "value": value, "unit": "plans/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "plans_per_step_sample": per_step,
+                   "note": "reference has no batch API (tdmpc.py:110): single-environment plans, sequential"},
+        "sample_steps_per_sec": value * S,
+        "cpu_baseline": {"value": value, "unit": "plans/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{per_step} single-env plan() calls per step x {args.steps} steps, oracle port (same aten CPU ops as the reference)"},
+        "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="environments per GPU (default: workload's)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg_name, def_batch, desc = WORKLOADS[args.workload]
+    cfg = synth.make_cfg(cfg_name)
+
+    if args.impl == "reference":
+        run_reference(args, cfg, desc, rank)
+        return
+
+    import torch.distributed as dist
+    from tdmpc_b200 import Planner
+    from tdmpc_b200.parallel import gather_actions
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch or def_batch
+    F, S, (H, N, P, T) = flops_and_steps(cfg)
+    sd = synth.make_told_weights(cfg, 0)
+    pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, precision=args.precision, device=dev)
+    pl.sync_weights({k: v.to(dev) for k, v in sd.items()})
+    pl.seed = 1234 + rank
+    kw = dict(horizon=H, num_samples=N, num_pi_trajs=P, num_elites=cfg.num_elites, iterations=cfg.iterations,
+              discount=cfg.discount, temperature=cfg.temperature, momentum=cfg.momentum, min_std=cfg.min_std,
+              std_floor=cfg.min_std, eval_mode=True)
+
+    # synthetic observations: pinned host buffer (e2e path) and a device-resident copy (kernel path)
+    obs_host = torch.from_numpy(synth.make_obs(cfg, 10 + rank, batch=B)).pin_memory()
+    obs_dev = obs_host.to(dev)
+    prev_mean = torch.zeros(B, H, cfg.action_dim, device=dev)
+    out = {"action": torch.empty(B, cfg.action_dim, device=dev), "metrics": torch.empty(B, 2, device=dev)}
+    act_host = torch.empty(B, cfg.action_dim).pin_memory()
+    met_host = torch.empty(B, 2).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step_device(first):
+        pl.plan(obs_dev, prev_mean=prev_mean, has_prev=not first, t0=first, out=out, **kw)
+        if world > 1:
+            gather_actions(out["action"], B * world)
+
+    def step_e2e(first):
+        o = obs_host.to(dev, non_blocking=True)                                  # H2D of this step's inputs
+        pl.plan(o, prev_mean=prev_mean, has_prev=not first, t0=first, out=out, **kw)
+        a = gather_actions(out["action"], B * world) if world > 1 else out["action"]
+        act_host.copy_(a[:B] if world > 1 else a, non_blocking=True)             # D2H of the planned actions
+        met_host.copy_(out["metrics"], non_blocking=True)                        # ... and plan_metrics
+        torch.cuda.current_stream().synchronize()                                # the env loop needs them on the host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i == 0)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = pl.launch_count
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)                       # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record()
+            fn(False)
+            ev[i][1].record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)    # max over ranks
+        return t.item() / steps, pl.launch_count - l0, clocks, wall
+
+    ms_dev, launches, clocks, _ = timed(step_device, args.steps, args.warmup)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, 1)
+
+    # dominant kernel alone: one estimate_value launch over all B*T trajectories (same shape the plan uses)
+    roof = None
+    extra = {}
+    if rank == 0:
+        sus, burst, hbm, src = measured_peaks()
+        L, A, M = cfg.latent_dim, cfg.action_dim, cfg.mlp_dim
+        f_dyn = 2 * ((L + A) * M + M * M + M * L); f_rew = 2 * ((L + A) * M + M * M + M)
+        f_pi = 2 * (L * M + M * M + M * A)
+        f_launch = float(B) * T * (H * (f_dyn + f_rew) + f_pi + 2 * f_rew)
+        z0 = pl.encode(obs_dev)
+        acts = torch.rand(B, T, H, A, device=dev) * 2 - 1
+        for _ in range(2):
+            pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
+        torch.cuda.synchronize()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kt = []
+        for _ in range(reps):
+            flush.fill_(1)
+            e0.record()
+            pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
+            e1.record()
+            torch.cuda.synchronize()
+            kt.append(e0.elapsed_time(e1))
+        k_ms = float(np.mean(kt))
+        achieved = f_launch / (k_ms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "rollout_tc_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        roof = {"bound": "tensor", "kernel": "rollout_tc_kernel (value mode)" if args.precision == "bf16" else "rollout_fp32_kernel",
+                "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": traffic,
+                "peak_source": f"{src}: bf16_tflops_sustained (kernel runs back-to-back for >1 s); burst {burst}",
+                "kernel_ms": k_ms, "flop_per_launch": f_launch,
+                "share_of_step": cfg.iterations * k_ms / ms_dev}
+        del acts
+
+        if not args.no_extra:
+            # B=1 latency cases (BASELINE.json configs[0], configs[1]): plans/s of a single environment
+            for wn in ("cfg1", "cfg2"):
+                c2 = synth.make_cfg(WORKLOADS[wn][0])
+                f2, s2, (h2, n2, p2, t2) = flops_and_steps(c2)
+                p1 = Planner(c2.obs_shape[0], c2.action_dim, c2.latent_dim, c2.mlp_dim, c2.enc_dim, precision=args.precision, device=dev)
+                p1.sync_weights({k: v.to(dev) for k, v in synth.make_told_weights(c2, 0).items()})
+                o1 = torch.from_numpy(synth.make_obs(c2, 3, batch=1)).to(dev)
+                pm = torch.zeros(1, h2, c2.action_dim, device=dev)
+                k2 = dict(horizon=h2, num_samples=n2, num_pi_trajs=p2, num_elites=c2.num_elites, iterations=c2.iterations,
+                          discount=c2.discount, temperature=c2.temperature, momentum=c2.momentum, min_std=c2.min_std,
+                          std_floor=c2.min_std, eval_mode=True)
+                for i in range(5):
+                    p1.plan(o1, prev_mean=pm, has_prev=i > 0, t0=i == 0, **k2)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(20):
+                    p1.plan(o1, prev_mean=pm, has_prev=True, t0=False, **k2)
+                e1.record(); torch.cuda.synchronize()
+                ms1 = e0.elapsed_time(e1) / 20
+                extra[wn + "_b1"] = {"workload": WORKLOADS[wn][2], "ms_per_plan": ms1, "plans_per_sec": 1e3 / ms1,
+                                     "sample_steps_per_sec": 1e3 / ms1 * s2}
+
+    if rank == 0:
+        cpu_rate, n_cpu, med = cpu_plan_rate(cfg, sd, args.cpu_budget) if world == 1 else (None, 0, None)
+        plans_per_s = B * world / (ms_dev * 1e-3)
+        e2e_rate = B * world / (ms_e2e * 1e-3)
+        line = {
+            "metric": "plans/sec", "value": plans_per_s, "unit": "plans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "envs_per_gpu": B, "envs_total": B * world,
+                       "trajectories_per_plan": T, "parallelism": f"dp{world} over independent planning problems",
+                       "l2": "flushed (256 MB write) between timed iterations; per-step working set also exceeds L2 at B>=4096",
+                       "weights": "random-init TOLD, heads re-randomised (tests/synth.py)", "precision": args.precision},
+            "sample_steps_per_sec": plans_per_s * S,
+            "flop_per_plan": F, "tflops": plans_per_s * F / 1e12,
+            "e2e": {"value": e2e_rate, "unit": "plans/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": B * cfg.obs_shape[0] * 4, "d2h_bytes_per_step": B * cfg.action_dim * 4 + B * 2 * 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "extra": extra,
+        }
+        if cpu_rate is not None:
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": "plans/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{n_cpu} single-env plan() calls of the same workload (median {med * 1e3:.1f} ms/plan); "
+                                              f"the reference has no batch API, so B envs cost B/value seconds"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint64_t* h1_full = acc_empty + 2;     // h1 chunk c written to TMEM (layer-1 epilogue -> layer-2 MMAs)
   uint64_t* xs_full = h1_full + 4;       // XS chunk c written to smem  (layer-2 / QL1 epilogue -> layer-3 / QL2 MMAs)
   uint64_t* za_full = xs_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(za_full + 1);
+  uint64_t* q_full = za_full + 1;        // Q-head accumulator chunk c complete (one barrier per chunk: never two phases ahead)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     for (int i = 0; i < 4; ++i) { mbar_init(&h1_full[i], 128); mbar_init(&xs_full[i], 128); }
     mbar_init(za_full, 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -149,108 +151,117 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      uint32_t stage = 0, wphase = 0;
-      uint32_t use[2] = {0, 0}, nbuf = 0, za_phase = 0;
-      // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
-      // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
-      // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
-      uint32_t h1_phase = 0, xs_phase = 0;
-      const uint32_t idesc128 = umma_idesc_bf16(128, 128);
-      const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
-      const int ks1_total = m.K1p / 16;
+    // The whole warp walks the job list converged (waits are warp-wide); one elected lane issues.
+    const bool leader = elect_one();        // elected once while the warp is converged; the same lane issues every MMA and commit
+    uint32_t stage = 0, wphase = 0;
+    uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
+    // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
+    // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
+    // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
+    uint32_t h1_phase = 0, xs_phase = 0;
+    const uint32_t idesc128 = umma_idesc_bf16(128, 128);
+    const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
+    const int ks1_total = m.K1p / 16;
 
-      auto tile_wait = [&]() -> uint32_t {
-        mbar_wait(&w_full[stage], wphase, 2);
-        tcgen05_fence_after();
-        return ring_addr + stage * TILE_BYTES;
-      };
-      auto tile_release = [&]() {
-        umma_commit(&w_empty[stage]);
-        if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
-      };
-      auto acc_acquire = [&](int b) {
-        mbar_wait(&acc_empty[b], (use[b] & 1) ^ 1, 3);
-        ++use[b];
-      };
-      auto h1_wait = [&](int c) {
-        mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
-        h1_phase ^= 1u << c;
-      };
-      auto xs_wait = [&](int c) {
-        mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
-        xs_phase ^= 1u << c;
-      };
+    auto tile_wait = [&]() -> uint32_t {
+      mbar_wait(&w_full[stage], wphase, 2);
+      tcgen05_fence_after();
+      return ring_addr + stage * TILE_BYTES;
+    };
+    auto tile_release = [&]() {
+      if (leader) umma_commit(&w_empty[stage]);
+      if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
+    };
+    auto acc_acquire = [&](int b) {
+      mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
+      ++ecnt[b];
+    };
+    auto h1_wait = [&](int c) {
+      mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
+      h1_phase ^= 1u << c;
+    };
+    auto xs_wait = [&](int c) {
+      mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
+      xs_phase ^= 1u << c;
+    };
+    // one k-block (<= 4 k-steps of 16) with both operands in shared memory
+    auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
+      const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        if (ks < nks) umma_ss(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (first && ks == 0) ? 0u : 1u);
+    };
 
-      for (int it = 0; it < my_tiles; ++it)
-        for (int j = 0; j < kp.njobs; ++j) {
-          const uint32_t job = sjobs[j];
-          const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
-          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
-          if (type == J_L1) {
-            const int b = nbuf; nbuf ^= 1;
-            acc_acquire(b);
-            tcgen05_fence_after();
-            const uint32_t d = tmem + TM_ACC + b * 128;
-            for (int kb = 0; kb < m.nkb1; ++kb) {
+    for (int it = 0; it < my_tiles; ++it)
+      for (int j = 0; j < kp.njobs; ++j) {
+        const uint32_t job = sjobs[j];
+        const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
+        if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
+        if (type == J_L1) {
+          const int b = nbuf; nbuf ^= 1;
+          acc_acquire(b);
+          tcgen05_fence_after();
+          const uint32_t d = tmem + TM_ACC + b * 128;
+          for (int kb = 0; kb < m.nkb1; ++kb) {
+            const uint32_t wt = tile_wait();
+            if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+            tile_release();
+          }
+          if (leader) umma_commit(&acc_full[b]);
+        } else if (type == J_L2) {
+          const int b = nbuf; nbuf ^= 1;
+          acc_acquire(b);
+          tcgen05_fence_after();
+          const uint32_t d = tmem + TM_ACC + b * 128;
+          for (int kb = 0; kb < 8; ++kb) {
+            if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+            const uint32_t wt = tile_wait();
+            if (leader) {
+              const uint32_t blo = umma_desc_lo(wt);
+              const uint32_t a = tmem + TM_A + kb * 32;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+            }
+            tile_release();
+          }
+          if (leader) umma_commit(&acc_full[b]);
+        } else if (type == J_L3) {
+          const int b = nbuf; nbuf ^= 1;
+          acc_acquire(b);
+          tcgen05_fence_after();
+          const uint32_t d = tmem + TM_ACC + b * 128;
+          const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
+          const bool half = m.l3rows[chain] == 64;
+          uint32_t wt = 0;
+          for (int kb = 0; kb < 8; ++kb) {
+            if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+            if (!half || (kb & 1) == 0) wt = tile_wait();
+            if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
+            if (!half || (kb & 1)) tile_release();
+          }
+          if (leader) umma_commit(&acc_full[b]);
+        } else {
+          // Q-head layers: one 512-column accumulator = both ping-pong buffers + the h1 region.
+          // Each 128-column chunk is committed to its own barrier so the epilogue can accumulate the
+          // LayerNorm statistics of chunk c while chunk c+1 is computed.
+          acc_acquire(0); acc_acquire(1);
+          tcgen05_fence_after();
+          const bool first = type == J_QL1;
+          const int nkb = first ? m.nkb1 : 8;
+          for (int c = 0; c < 4; ++c) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
               const uint32_t wt = tile_wait();
-              const int nks = min(4, ks1_total - kb * 4);
-              for (int ks = 0; ks < nks; ++ks)
-                umma_ss(d, umma_desc_sw128(za_addr + kb * TILE_BYTES + ks * 32), umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
+                if (leader)
+                kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
+                          first ? min(4, ks1_total - kb * 4) : 4, kb == 0);
               tile_release();
             }
-            umma_commit(&acc_full[b]);
-          } else if (type == J_L2) {
-            const int b = nbuf; nbuf ^= 1;
-            acc_acquire(b);
-            tcgen05_fence_after();
-            const uint32_t d = tmem + TM_ACC + b * 128;
-            for (int kb = 0; kb < 8; ++kb) {
-              if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
-              const uint32_t wt = tile_wait();
-              for (int ks = 0; ks < 4; ++ks)
-                umma_ts(d, tmem + TM_A + kb * 32 + ks * 8, umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
-              tile_release();
-            }
-            umma_commit(&acc_full[b]);
-          } else if (type == J_L3) {
-            const int b = nbuf; nbuf ^= 1;
-            acc_acquire(b);
-            tcgen05_fence_after();
-            const uint32_t d = tmem + TM_ACC + b * 128;
-            const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
-            const bool half = m.l3rows[chain] == 64;
-            uint32_t wt = 0;
-            for (int kb = 0; kb < 8; ++kb) {
-              if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-              if (!half || (kb & 1) == 0) wt = tile_wait();
-              const uint32_t bb = wt + ((half && (kb & 1)) ? 8192u : 0u);
-              for (int ks = 0; ks < 4; ++ks)
-                umma_ss(d, umma_desc_sw128(xs_addr + kb * TILE_BYTES + ks * 32), umma_desc_sw128(bb + ks * 32), idesc, (kb | ks) ? 1u : 0u);
-              if (!half || (kb & 1)) tile_release();
-            }
-            umma_commit(&acc_full[b]);
-          } else {
-            // Q-head layers: one 512-column accumulator = both ping-pong buffers + the h1 region
-            acc_acquire(0); acc_acquire(1);
-            tcgen05_fence_after();
-            const bool first = type == J_QL1;
-            const int nkb = first ? m.nkb1 : 8;
-            for (int c = 0; c < 4; ++c)
-              for (int kb = 0; kb < nkb; ++kb) {
-                if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-                const uint32_t wt = tile_wait();
-                const int nks = first ? min(4, ks1_total - kb * 4) : 4;
-                const uint32_t abase = (first ? za_addr : xs_addr) + kb * TILE_BYTES;
-                for (int ks = 0; ks < nks; ++ks)
-                  umma_ss(tmem + c * 128, umma_desc_sw128(abase + ks * 32), umma_desc_sw128(wt + ks * 32), idesc128, (kb | ks) ? 1u : 0u);
-                tile_release();
-              }
-            umma_commit(&acc_full[0]);
-            umma_commit(&acc_full[1]);
+            if (leader) umma_commit(&q_full[c]);
           }
         }
-    }
+        __syncwarp();
+      }
   } else {
     // ============================== epilogue: thread = trajectory ==============================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -258,11 +269,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
-    uint32_t use[2] = {0, 0}, nbuf = 0;
+    uint32_t fcnt[2] = {0, 0}, nbuf = 0, q_phase = 0;
 
     auto acc_wait = [&](int b) {
-      mbar_wait(&acc_full[b], use[b] & 1, 7);
-      ++use[b];
+      mbar_wait(&acc_full[b], fcnt[b] & 1, 7);
+      ++fcnt[b];
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -305,23 +316,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           const int b = nbuf; nbuf ^= 1;
           acc_wait(b);
           tcgen05_fence_after();
-#pragma unroll 1
-          for (int s = 0; s < 4; ++s) {
-            uint32_t v[32];
-            tmem_ld32(tlane + TM_ACC + b * 128 + s * 32, v);
-            float bias[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = ldg4(ch.b1, chunk * 32 + s * 8 + i);
-              bias[4 * i] = f.x; bias[4 * i + 1] = f.y; bias[4 * i + 2] = f.z; bias[4 * i + 3] = f.w;
-            }
-            tmem_wait_ld();
+          const float* bias = ch.b1 + chunk * 128;
+          const uint32_t dst = tlane + TM_A + chunk * 64;
+          tmem_stream(tlane + TM_ACC + b * 128, 4, [&](int s, uint32_t (&v)[32]) {
             uint32_t o[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              o[i] = pack_bf16x2(elu_fast(__uint_as_float(v[2 * i]) + bias[2 * i]), elu_fast(__uint_as_float(v[2 * i + 1]) + bias[2 * i + 1]));
-            tmem_st16(tlane + TM_A + chunk * 64 + s * 16, o);
-          }
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = ldg4(bias, s * 8 + i);
+              o[2 * i] = pack_bf16x2(elu_fast(__uint_as_float(v[4 * i]) + f.x), elu_fast(__uint_as_float(v[4 * i + 1]) + f.y));
+              o[2 * i + 1] = pack_bf16x2(elu_fast(__uint_as_float(v[4 * i + 2]) + f.z), elu_fast(__uint_as_float(v[4 * i + 3]) + f.w));
+            }
+            tmem_st16(dst + s * 16, o);
+          });
           tmem_wait_st();
           tcgen05_fence_before();
           mbar_arrive(&h1_full[chunk]);
@@ -331,41 +337,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           acc_wait(b);
           tcgen05_fence_after();
           const bool to_xs = chain != CH_REW;
-#pragma unroll 1
-          for (int s = 0; s < 4; ++s) {
-            uint32_t v[32];
-            tmem_ld32(tlane + TM_ACC + b * 128 + s * 32, v);
-            float bias[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = ldg4(ch.b2, chunk * 32 + s * 8 + i);
-              bias[4 * i] = f.x; bias[4 * i + 1] = f.y; bias[4 * i + 2] = f.z; bias[4 * i + 3] = f.w;
-            }
-            tmem_wait_ld();
-            float h[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) h[i] = elu_fast(__uint_as_float(v[i]) + bias[i]);
-            if (to_xs) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) sw_store8(xs, row, chunk * 128 + s * 32 + i * 8, h + i * 8);
-            } else {
-              // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 f = ldg4(ch.w3, chunk * 32 + s * 8 + i);
-                dot = fmaf(h[4 * i], f.x, dot); dot = fmaf(h[4 * i + 1], f.y, dot);
-                dot = fmaf(h[4 * i + 2], f.z, dot); dot = fmaf(h[4 * i + 3], f.w, dot);
-              }
-            }
-          }
+          const float* bias = ch.b2 + chunk * 128;
           if (to_xs) {
+            tmem_stream(tlane + TM_ACC + b * 128, 4, [&](int s, uint32_t (&v)[32]) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 f0 = ldg4(bias, s * 8 + 2 * i), f1 = ldg4(bias, s * 8 + 2 * i + 1);
+                float h[8];
+                h[0] = elu_fast(__uint_as_float(v[8 * i]) + f0.x); h[1] = elu_fast(__uint_as_float(v[8 * i + 1]) + f0.y);
+                h[2] = elu_fast(__uint_as_float(v[8 * i + 2]) + f0.z); h[3] = elu_fast(__uint_as_float(v[8 * i + 3]) + f0.w);
+                h[4] = elu_fast(__uint_as_float(v[8 * i + 4]) + f1.x); h[5] = elu_fast(__uint_as_float(v[8 * i + 5]) + f1.y);
+                h[6] = elu_fast(__uint_as_float(v[8 * i + 6]) + f1.z); h[7] = elu_fast(__uint_as_float(v[8 * i + 7]) + f1.w);
+                sw_store8(xs, row, chunk * 128 + s * 32 + i * 8, h);
+              }
+            });
             fence_proxy_async_smem();
             mbar_arrive(&xs_full[chunk]);
-          } else if (chunk == 3) {
-            const float r = dot + __ldg(ch.b3);
-            G = __fadd_rn(G, __fmul_rn(p.disc[t], r));   // G += discount * reward (tdmpc.py:89): mul, then add, as torch does
-            rlast = r;
-            dot = 0.0f;
+          } else {
+            // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
+            const float* w3 = ch.w3 + chunk * 128;
+            tmem_stream(tlane + TM_ACC + b * 128, 4, [&](int s, uint32_t (&v)[32]) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 f = ldg4(bias, s * 8 + i), w = ldg4(w3, s * 8 + i);
+                dot = fmaf(elu_fast(__uint_as_float(v[4 * i]) + f.x), w.x, dot);
+                dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 1]) + f.y), w.y, dot);
+                dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 2]) + f.z), w.z, dot);
+                dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 3]) + f.w), w.w, dot);
+              }
+            });
+            if (chunk == 3) {
+              const float r = dot + __ldg(ch.b3);
+              G = __fadd_rn(G, __fmul_rn(p.disc[t], r));   // G += discount * reward (tdmpc.py:89): mul, then add, as torch does
+              rlast = r;
+              dot = 0.0f;
+            }
           }
           tcgen05_fence_before();
           mbar_arrive(&acc_empty[b]);
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               uint32_t v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;
-              if (k0 < L) { tmem_ld32(tlane + TM_ACC + b * 128 + k0, v); tmem_wait_ld(); }
+              if (k0 < L) { tmem_ld32(tlane + TM_ACC + b * 128 + k0, v); tmem_wait_ld_dep(v); }
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int kk = k0 + c8 * 8;
@@ -405,21 +411,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
           } else {
             // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
-            uint32_t v[32];
             const bool terminal = (flags & F_TERMINAL) != 0;
             const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
             for (int a0 = 0; a0 < A; a0 += 32) {
+              uint32_t v[32];
               tmem_ld32(tlane + TM_ACC + b * 128 + a0, v);
-              tmem_wait_ld();
-              for (int i = 0; i < 32 && a0 + i < A; ++i) {
+              tmem_wait_ld_dep(v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
                 const int a = a0 + i;
-                float x = 0.0f;
-                if (valid) {
-                  const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
-                  x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
-                  if (!terminal) pi_row[(size_t)t * A + a] = x;
+                if (a < A) {
+                  float x = 0.0f;
+                  if (valid) {
+                    const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
+                    x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
+                    if (!terminal) pi_row[(size_t)t * A + a] = x;
+                  }
+                  if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
                 }
-                if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
               }
             }
           }
@@ -430,49 +439,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             mbar_arrive(za_full);
           }
         } else {
-          // Q head layer: x = acc + b over all 512 columns, LayerNorm (two-pass statistics), then
+          // Q head layer: x = acc + b over all 512 columns, LayerNorm, then
           //   J_QL1: tanh -> bf16 -> XS        J_QL2: ELU -> dot with w3 -> q
-          acc_wait(0); acc_wait(1);
-          tcgen05_fence_after();
+          // pass 1 (sum, sum of squares) runs chunk by chunk as the MMA warp commits them.
           const bool first = type == J_QL1;
           const float* bias = first ? ch.b1 : ch.b2;
           const float* lg = ch.ln_g[first ? 0 : 1];
           const float* lb = ch.ln_b[first ? 0 : 1];
-          float sum = 0.0f;
-#pragma unroll 1
-          for (int s = 0; s < 16; ++s) {
-            uint32_t v[32];
-            tmem_ld32(tlane + s * 32, v);
-            tmem_wait_ld();
+          float sum = 0.0f, ssq = 0.0f;
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(&q_full[c], q_phase, 8);
+            tcgen05_fence_after();
+            tmem_stream(tlane + c * 128, 4, [&](int s, uint32_t (&v)[32]) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = ldg4(bias, s * 8 + i);
-              sum += (__uint_as_float(v[4 * i]) + f.x) + (__uint_as_float(v[4 * i + 1]) + f.y) +
-                     (__uint_as_float(v[4 * i + 2]) + f.z) + (__uint_as_float(v[4 * i + 3]) + f.w);
-            }
+              for (int i = 0; i < 8; ++i) {
+                const float4 f = ldg4(bias, c * 32 + s * 8 + i);
+                const float x0 = __uint_as_float(v[4 * i]) + f.x, x1 = __uint_as_float(v[4 * i + 1]) + f.y;
+                const float x2 = __uint_as_float(v[4 * i + 2]) + f.z, x3 = __uint_as_float(v[4 * i + 3]) + f.w;
+                sum += (x0 + x1) + (x2 + x3);
+                ssq = fmaf(x0, x0, ssq); ssq = fmaf(x1, x1, ssq); ssq = fmaf(x2, x2, ssq); ssq = fmaf(x3, x3, ssq);
+              }
+            });
           }
+          q_phase ^= 1;
           const float mu = sum * (1.0f / 512.0f);
-          float ssq = 0.0f;
-#pragma unroll 1
-          for (int s = 0; s < 16; ++s) {
-            uint32_t v[32];
-            tmem_ld32(tlane + s * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = ldg4(bias, s * 8 + i);
-              float d0 = __uint_as_float(v[4 * i]) + f.x - mu, d1 = __uint_as_float(v[4 * i + 1]) + f.y - mu;
-              float d2 = __uint_as_float(v[4 * i + 2]) + f.z - mu, d3 = __uint_as_float(v[4 * i + 3]) + f.w - mu;
-              ssq = fmaf(d0, d0, ssq); ssq = fmaf(d1, d1, ssq); ssq = fmaf(d2, d2, ssq); ssq = fmaf(d3, d3, ssq);
-            }
-          }
-          const float rstd = 1.0f / sqrtf(ssq * (1.0f / 512.0f) + 1e-5f);
+          const float var = fmaxf(ssq * (1.0f / 512.0f) - mu * mu, 0.0f);      // biased variance, as nn.LayerNorm
+          const float rstd = 1.0f / sqrtf(var + 1e-5f);
           float qdot = 0.0f;
-#pragma unroll 1
-          for (int s = 0; s < 16; ++s) {
-            uint32_t v[32];
-            tmem_ld32(tlane + s * 32, v);
-            tmem_wait_ld();
+          tmem_stream(tlane, 16, [&](int s, uint32_t (&v)[32]) {
             float y[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -496,7 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 qdot = fmaf(elu_fast(y[4 * i + 2]), f.z, qdot); qdot = fmaf(elu_fast(y[4 * i + 3]), f.w, qdot);
               }
             }
-          }
+          });
           if (!first) {
             const float qv = qdot + __ldg(ch.b3);
             if (chain == CH_Q1) q1v = qv;
@@ -684,7 +678,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + MAX_JOBS * 4 + (2 * MAX_STAGES + 13) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + MAX_JOBS * 4 + (2 * MAX_STAGES + 17) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return -1;

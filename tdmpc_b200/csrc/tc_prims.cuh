@@ -85,6 +85,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+// tcgen05.wait::ld with the destination registers as in/out operands, so neither nvcc nor ptxas can
+// schedule a consumer of v[] above the wait (the loads complete asynchronously).
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+        "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+        "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :: "memory");
+}
+// Streams `nsub` consecutive 32-column groups of this warp's TMEM lanes through f(s, v[32]) with the
+// load of group s+1 in flight while group s is processed (two register buffers).
+template <typename F>
+__device__ __forceinline__ void tmem_stream(uint32_t taddr, int nsub, F&& f) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr, va);
+#pragma unroll 1
+  for (int s = 0; s < nsub; s += 2) {
+    tmem_wait_ld_dep(va);
+    if (s + 1 < nsub) tmem_ld32(taddr + (s + 1) * 32, vb);
+    f(s, va);
+    if (s + 1 < nsub) {
+      tmem_wait_ld_dep(vb);
+      if (s + 2 < nsub) tmem_ld32(taddr + (s + 2) * 32, va);
+      f(s + 1, vb);
+    }
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -114,6 +147,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr_bytes) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+
+// Same descriptor split into a constant high word and an address-dependent low word, so the MMA
+// issue loop only does one integer add per operand per k-step (+2 = 32 bytes = UMMA_K bf16).
+constexpr uint32_t UMMA_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr_bytes) { return ((saddr_bytes & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | lo; }
 
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 // [4,6) D fmt=1 (f32) | [7,10) A fmt=1 (bf16) | [10,13) B fmt=1 (bf16) | [17,23) N>>3 | [24,29) M>>4
