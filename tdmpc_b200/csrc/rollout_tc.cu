@@ -11,10 +11,11 @@
 //   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) per k-step.
 //            layer 1: A = [z,a] tile in shared memory (SS);  layer 2: A = h1 in TENSOR MEMORY (TS),
 //            so the 128x512 hidden activation never touches shared memory; layer 3: A = h2 in smem.
-//   warps 2-5 epilogue: thread = trajectory.  tcgen05.ld the fp32 accumulator, add bias, ELU /
-//            LayerNorm+tanh / tanh, then write the next layer's bf16 operand (tcgen05.st to TMEM
-//            or 128B-swizzled st.shared), or reduce the N=1 reward / Q heads as fp32 dot products
-//            and accumulate the discounted return in registers.
+//   warps 4-11 epilogue (two warpgroups, one per accumulator buffer): thread = trajectory.
+//            tcgen05.ld the fp32 accumulator (software pipelined), add bias, ELU / LayerNorm+tanh /
+//            tanh, then write the next layer's bf16 operand (tcgen05.st to TMEM or 128B-swizzled
+//            st.shared), or reduce the N=1 reward / Q heads as fp32 dot products and accumulate
+//            the discounted return in registers.  setmaxnreg moves registers from warps 0-3 to them.
 //
 // TMEM map (512 columns): [0,128) [128,256) accumulator ping-pong, [256,512) h1 as bf16x2 (K=512).
 // The Q heads need the whole 512-wide pre-LayerNorm row, so their jobs use all 512 columns.
@@ -30,7 +31,9 @@ using namespace tc;
 namespace {
 
 constexpr int TILE_ROWS = 128;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 384;              // warps 0-3: producer / MMA / 2 idle; warps 4-7, 8-11: epilogue groups 0 and 1
+constexpr int REGS_CTRL = 40, REGS_EPI = 232;   // setmaxnreg: frees (168-40)*128 = takes (232-168)*256 registers, exactly
+constexpr int XCH_FLOATS = 3 * 2 * 128;   // epilogue-group exchange: {sum, sum-of-squares, dot} x 2 groups x 128 rows
 constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
 constexpr int MAX_JOBS = 17 * TDMPC_MAX_H + 16;
@@ -102,7 +105,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint8_t* xs = smem;
   uint8_t* za = xs + XS_BYTES;
   uint8_t* wring = za + m.nkb1 * TILE_BYTES;
-  uint32_t* sjobs = reinterpret_cast<uint32_t*>(wring + S * TILE_BYTES);
+  float* xch = reinterpret_cast<float*>(wring + S * TILE_BYTES);     // [3][2 groups][128 rows] epilogue-group exchange
+  uint32_t* sjobs = reinterpret_cast<uint32_t*>(xch + XCH_FLOATS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sjobs + ((kp.njobs + 3) & ~3));
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + MAX_STAGES;
@@ -132,148 +136,169 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   const uint32_t tmem = *tmem_slot;
   const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == 0) {
-    // ============================== producer: weight tiles, L2 -> smem ring ==============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+  if (warp < 4) {
+    // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
+    // registers to the two epilogue warpgroups.
+    setmaxnreg_dec<REGS_CTRL>();
+    if (warp == 0) {
+      // ============================== producer: weight tiles, L2 -> smem ring ==============================
+      if (lane == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; it < my_tiles; ++it)
+          for (int j = 0; j < kp.njobs; ++j) {
+            const uint32_t job = sjobs[j];
+            const int nt = job_tiles(m, job);
+            const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
+            for (int i = 0; i < nt; ++i) {
+              mbar_wait(&w_empty[stage], phase ^ 1, 1);
+              mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
+              bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
+              if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+            }
+          }
+      }
+    } else if (warp == 1) {
+      // ============================== MMA issuer ==============================
+      // The whole warp walks the job list converged (waits are warp-wide); one elected lane issues.
+      const bool leader = elect_one();      // elected once while converged: the same lane issues every MMA and commit
+      uint32_t stage = 0, wphase = 0;
+      uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
+      // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
+      // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
+      // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
+      uint32_t h1_phase = 0, xs_phase = 0;
+      const uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
+      const int ks1_total = m.K1p / 16;
+
+      auto tile_wait = [&]() -> uint32_t {
+        mbar_wait(&w_full[stage], wphase, 2);
+        tcgen05_fence_after();
+        return ring_addr + stage * TILE_BYTES;
+      };
+      auto tile_release = [&]() {
+        if (leader) umma_commit(&w_empty[stage]);
+        if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
+      };
+      auto acc_acquire = [&](int b) {
+        mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
+        ++ecnt[b];
+      };
+      auto h1_wait = [&](int c) {
+        mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
+        h1_phase ^= 1u << c;
+      };
+      auto xs_wait = [&](int c) {
+        mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
+        xs_phase ^= 1u << c;
+      };
+      // one k-block (<= 4 k-steps of 16) with both operands in shared memory
+      auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
+        const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (ks < nks) umma_ss(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (first && ks == 0) ? 0u : 1u);
+      };
+
       for (int it = 0; it < my_tiles; ++it)
         for (int j = 0; j < kp.njobs; ++j) {
           const uint32_t job = sjobs[j];
-          const int nt = job_tiles(m, job);
-          const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
-          for (int i = 0; i < nt; ++i) {
-            mbar_wait(&w_empty[stage], phase ^ 1, 1);
-            mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
-            bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
-            if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
-          }
-        }
-    }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    // The whole warp walks the job list converged (waits are warp-wide); one elected lane issues.
-    const bool leader = elect_one();        // elected once while the warp is converged; the same lane issues every MMA and commit
-    uint32_t stage = 0, wphase = 0;
-    uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
-    // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
-    // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
-    // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
-    uint32_t h1_phase = 0, xs_phase = 0;
-    const uint32_t idesc128 = umma_idesc_bf16(128, 128);
-    const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
-    const int ks1_total = m.K1p / 16;
-
-    auto tile_wait = [&]() -> uint32_t {
-      mbar_wait(&w_full[stage], wphase, 2);
-      tcgen05_fence_after();
-      return ring_addr + stage * TILE_BYTES;
-    };
-    auto tile_release = [&]() {
-      if (leader) umma_commit(&w_empty[stage]);
-      if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
-    };
-    auto acc_acquire = [&](int b) {
-      mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
-      ++ecnt[b];
-    };
-    auto h1_wait = [&](int c) {
-      mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
-      h1_phase ^= 1u << c;
-    };
-    auto xs_wait = [&](int c) {
-      mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
-      xs_phase ^= 1u << c;
-    };
-    // one k-block (<= 4 k-steps of 16) with both operands in shared memory
-    auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
-      const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        if (ks < nks) umma_ss(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (first && ks == 0) ? 0u : 1u);
-    };
-
-    for (int it = 0; it < my_tiles; ++it)
-      for (int j = 0; j < kp.njobs; ++j) {
-        const uint32_t job = sjobs[j];
-        const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
-        if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
-        if (type == J_L1) {
-          const int b = nbuf; nbuf ^= 1;
-          acc_acquire(b);
-          tcgen05_fence_after();
-          const uint32_t d = tmem + TM_ACC + b * 128;
-          for (int kb = 0; kb < m.nkb1; ++kb) {
-            const uint32_t wt = tile_wait();
-            if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
-            tile_release();
-          }
-          if (leader) umma_commit(&acc_full[b]);
-        } else if (type == J_L2) {
-          const int b = nbuf; nbuf ^= 1;
-          acc_acquire(b);
-          tcgen05_fence_after();
-          const uint32_t d = tmem + TM_ACC + b * 128;
-          for (int kb = 0; kb < 8; ++kb) {
-            if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
-            const uint32_t wt = tile_wait();
-            if (leader) {
-              const uint32_t blo = umma_desc_lo(wt);
-              const uint32_t a = tmem + TM_A + kb * 32;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
-            }
-            tile_release();
-          }
-          if (leader) umma_commit(&acc_full[b]);
-        } else if (type == J_L3) {
-          const int b = nbuf; nbuf ^= 1;
-          acc_acquire(b);
-          tcgen05_fence_after();
-          const uint32_t d = tmem + TM_ACC + b * 128;
-          const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
-          const bool half = m.l3rows[chain] == 64;
-          uint32_t wt = 0;
-          for (int kb = 0; kb < 8; ++kb) {
-            if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-            if (!half || (kb & 1) == 0) wt = tile_wait();
-            if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
-            if (!half || (kb & 1)) tile_release();
-          }
-          if (leader) umma_commit(&acc_full[b]);
-        } else {
-          // Q-head layers: one 512-column accumulator = both ping-pong buffers + the h1 region.
-          // Each 128-column chunk is committed to its own barrier so the epilogue can accumulate the
-          // LayerNorm statistics of chunk c while chunk c+1 is computed.
-          acc_acquire(0); acc_acquire(1);
-          tcgen05_fence_after();
-          const bool first = type == J_QL1;
-          const int nkb = first ? m.nkb1 : 8;
-          for (int c = 0; c < 4; ++c) {
-            for (int kb = 0; kb < nkb; ++kb) {
-              if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+          const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
+          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
+          if (type == J_L1) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            for (int kb = 0; kb < m.nkb1; ++kb) {
               const uint32_t wt = tile_wait();
-                if (leader)
-                kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
-                          first ? min(4, ks1_total - kb * 4) : 4, kb == 0);
+              if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
               tile_release();
             }
-            if (leader) umma_commit(&q_full[c]);
+            if (leader) umma_commit(&acc_full[b]);
+          } else if (type == J_L2) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            for (int kb = 0; kb < 8; ++kb) {
+              if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+              const uint32_t wt = tile_wait();
+              if (leader) {
+                const uint32_t blo = umma_desc_lo(wt);
+                const uint32_t a = tmem + TM_A + kb * 32;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+              }
+              tile_release();
+            }
+            if (leader) umma_commit(&acc_full[b]);
+          } else if (type == J_L3) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
+            const bool half = m.l3rows[chain] == 64;
+            uint32_t wt = 0;
+            for (int kb = 0; kb < 8; ++kb) {
+              if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+              if (!half || (kb & 1) == 0) wt = tile_wait();
+              if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
+              if (!half || (kb & 1)) tile_release();
+            }
+            if (leader) umma_commit(&acc_full[b]);
+          } else {
+            // Q-head layers: one 512-column accumulator = both ping-pong buffers + the h1 region.
+            // Each 128-column chunk is committed to its own barrier so the epilogue can accumulate the
+            // LayerNorm statistics of chunk c while chunk c+1 is computed.
+            acc_acquire(0); acc_acquire(1);
+            tcgen05_fence_after();
+            const bool first = type == J_QL1;
+            const int nkb = first ? m.nkb1 : 8;
+            for (int c = 0; c < 4; ++c) {
+              for (int kb = 0; kb < nkb; ++kb) {
+                if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+                const uint32_t wt = tile_wait();
+                if (leader)
+                  kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
+                            first ? min(4, ks1_total - kb * 4) : 4, kb == 0);
+                tile_release();
+              }
+              if (leader) umma_commit(&q_full[c]);
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
-      }
+    }
   } else {
-    // ============================== epilogue: thread = trajectory ==============================
+    // ============================== epilogue: two warpgroups, thread = trajectory ==============================
+    // Group g (warps 4-7: g=0, warps 8-11: g=1) owns accumulator buffer g: jobs alternate buffers, so
+    // the two groups drain consecutive 128-column chunks concurrently (two warps per SM sub-partition
+    // hide each other's TMEM / L1 / MUFU latencies).  Row-wise reductions that span chunks (reward
+    // dot product, LayerNorm statistics, Q dot product) are combined through `xch` in shared memory.
+    setmaxnreg_inc<REGS_EPI>();
+    const int grp = (warp - 4) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
-    uint32_t fcnt[2] = {0, 0}, nbuf = 0, q_phase = 0;
+    uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
+    float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
+    float* x_ssq = xch + (1 * 2 + (grp ^ 1)) * 128;
+    float* x_dot = xch + (2 * 2 + (grp ^ 1)) * 128;
+    float* m_sum = xch + (0 * 2 + grp) * 128;            // my slots (write side)
+    float* m_ssq = xch + (1 * 2 + grp) * 128;
+    float* m_dot = xch + (2 * 2 + grp) * 128;
 
-    auto acc_wait = [&](int b) {
-      mbar_wait(&acc_full[b], fcnt[b] & 1, 7);
-      ++fcnt[b];
+    auto acc_wait = [&]() {
+      mbar_wait(&acc_full[grp], fcnt & 1, 7);
+      ++fcnt;
+    };
+    auto load8 = [&](const float* ptr, int idx, float4 (&x)[8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = ldg4(ptr, idx * 8 + i);
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -285,8 +310,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       float* pi_row = p.pi_actions ? p.pi_actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
       float G = 0.0f, rlast = 0.0f, dot = 0.0f, q1v = 0.0f;
 
-      // initial [z0, a0, 0...] row
-      {
+      // initial [z0, a0, 0...] row (group 0)
+      if (grp == 0) {
         const float* zr = p.z0 + (size_t)pb * L;
         for (int k0 = 0; k0 < m.nkb1 * 64; k0 += 8) {
           float v[8];
@@ -311,199 +336,237 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, t = (job >> 8) & 31, flags = job >> 13;
         const TcChain& ch = m.chain[chain];
 
-        if (type == J_L1) {
-          // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
+        if (type <= J_L3) {
           const int b = nbuf; nbuf ^= 1;
-          acc_wait(b);
-          tcgen05_fence_after();
-          const float* bias = ch.b1 + chunk * 128;
-          const uint32_t dst = tlane + TM_A + chunk * 64;
-          tmem_stream(tlane + TM_ACC + b * 128, 4, [&](int s, uint32_t (&v)[32]) {
-            uint32_t o[16];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = ldg4(bias, s * 8 + i);
-              o[2 * i] = pack_bf16x2(elu_fast(__uint_as_float(v[4 * i]) + f.x), elu_fast(__uint_as_float(v[4 * i + 1]) + f.y));
-              o[2 * i + 1] = pack_bf16x2(elu_fast(__uint_as_float(v[4 * i + 2]) + f.z), elu_fast(__uint_as_float(v[4 * i + 3]) + f.w));
-            }
-            tmem_st16(dst + s * 16, o);
-          });
-          tmem_wait_st();
-          tcgen05_fence_before();
-          mbar_arrive(&h1_full[chunk]);
-          mbar_arrive(&acc_empty[b]);
-        } else if (type == J_L2) {
-          const int b = nbuf; nbuf ^= 1;
-          acc_wait(b);
-          tcgen05_fence_after();
-          const bool to_xs = chain != CH_REW;
-          const float* bias = ch.b2 + chunk * 128;
-          if (to_xs) {
-            tmem_stream(tlane + TM_ACC + b * 128, 4, [&](int s, uint32_t (&v)[32]) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 f0 = ldg4(bias, s * 8 + 2 * i), f1 = ldg4(bias, s * 8 + 2 * i + 1);
-                float h[8];
-                h[0] = elu_fast(__uint_as_float(v[8 * i]) + f0.x); h[1] = elu_fast(__uint_as_float(v[8 * i + 1]) + f0.y);
-                h[2] = elu_fast(__uint_as_float(v[8 * i + 2]) + f0.z); h[3] = elu_fast(__uint_as_float(v[8 * i + 3]) + f0.w);
-                h[4] = elu_fast(__uint_as_float(v[8 * i + 4]) + f1.x); h[5] = elu_fast(__uint_as_float(v[8 * i + 5]) + f1.y);
-                h[6] = elu_fast(__uint_as_float(v[8 * i + 6]) + f1.z); h[7] = elu_fast(__uint_as_float(v[8 * i + 7]) + f1.w);
-                sw_store8(xs, row, chunk * 128 + s * 32 + i * 8, h);
-              }
-            });
-            fence_proxy_async_smem();
-            mbar_arrive(&xs_full[chunk]);
-          } else {
-            // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
-            const float* w3 = ch.w3 + chunk * 128;
-            tmem_stream(tlane + TM_ACC + b * 128, 4, [&](int s, uint32_t (&v)[32]) {
+          const bool mine = b == grp;
+          if (type == J_L1) {
+            if (!mine) continue;
+            // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
+            const float* bias = ch.b1 + chunk * 128;
+            const uint32_t dst = tlane + TM_A + chunk * 64;
+            float4 x0[8];
+            load8(bias, 0, x0);
+            acc_wait();
+            tcgen05_fence_after();
+            tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
+              uint32_t o[16];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 f = ldg4(bias, s * 8 + i), w = ldg4(w3, s * 8 + i);
-                dot = fmaf(elu_fast(__uint_as_float(v[4 * i]) + f.x), w.x, dot);
-                dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 1]) + f.y), w.y, dot);
-                dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 2]) + f.z), w.z, dot);
-                dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 3]) + f.w), w.w, dot);
+                o[2 * i] = pack_bf16x2(elu_fast(__uint_as_float(v[4 * i]) + x[i].x), elu_fast(__uint_as_float(v[4 * i + 1]) + x[i].y));
+                o[2 * i + 1] = pack_bf16x2(elu_fast(__uint_as_float(v[4 * i + 2]) + x[i].z), elu_fast(__uint_as_float(v[4 * i + 3]) + x[i].w));
               }
+              tmem_st16(dst + s * 16, o);
             });
-            if (chunk == 3) {
-              const float r = dot + __ldg(ch.b3);
-              G = __fadd_rn(G, __fmul_rn(p.disc[t], r));   // G += discount * reward (tdmpc.py:89): mul, then add, as torch does
-              rlast = r;
-              dot = 0.0f;
-            }
-          }
-          tcgen05_fence_before();
-          mbar_arrive(&acc_empty[b]);
-        } else if (type == J_L3) {
-          const int b = nbuf; nbuf ^= 1;
-          acc_wait(b);
-          tcgen05_fence_after();
-          if (chain == CH_DYN) {
-            // z' = acc + b3 -> [z', a_{t+1}, 0...] row of the next step
-            const bool next_act = p.mode == MODE_VALUE && !(flags & F_LAST_STEP);
-            // columns >= L+A of the row are zero padding written once per tile and never touched again
-            for (int k0 = 0; k0 < L + A; k0 += 32) {
-              uint32_t v[32];
+            tmem_wait_st();
+            tcgen05_fence_before();
+            mbar_arrive(&h1_full[chunk]);
+            mbar_arrive(&acc_empty[b]);
+          } else if (type == J_L2) {
+            const bool to_xs = chain != CH_REW;
+            if (mine) {
+              const float* bias = ch.b2 + chunk * 128;
+              float4 x0[8];
+              load8(bias, 0, x0);
+              acc_wait();
+              tcgen05_fence_after();
+              if (to_xs) {
+                tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                                [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 0u;
-              if (k0 < L) { tmem_ld32(tlane + TM_ACC + b * 128 + k0, v); tmem_wait_ld_dep(v); }
-#pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {
-                const int kk = k0 + c8 * 8;
-                if (kk < L + A) {
-                  float o[8];
+                  for (int i = 0; i < 4; ++i) {
+                    float h[8];
+                    h[0] = elu_fast(__uint_as_float(v[8 * i]) + x[2 * i].x); h[1] = elu_fast(__uint_as_float(v[8 * i + 1]) + x[2 * i].y);
+                    h[2] = elu_fast(__uint_as_float(v[8 * i + 2]) + x[2 * i].z); h[3] = elu_fast(__uint_as_float(v[8 * i + 3]) + x[2 * i].w);
+                    h[4] = elu_fast(__uint_as_float(v[8 * i + 4]) + x[2 * i + 1].x); h[5] = elu_fast(__uint_as_float(v[8 * i + 5]) + x[2 * i + 1].y);
+                    h[6] = elu_fast(__uint_as_float(v[8 * i + 6]) + x[2 * i + 1].z); h[7] = elu_fast(__uint_as_float(v[8 * i + 7]) + x[2 * i + 1].w);
+                    sw_store8(xs, row, chunk * 128 + s * 32 + i * 8, h);
+                  }
+                });
+                fence_proxy_async_smem();
+                mbar_arrive(&xs_full[chunk]);
+              } else {
+                // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
+                const float* w3 = ch.w3 + chunk * 128;
+                tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                                [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    const int k = kk + i;
-                    float x = 0.0f;
-                    if (k < L) x = __uint_as_float(v[c8 * 8 + i]) + __ldg(ch.b3 + k);
-                    else if (k < L + A && next_act && valid) x = __ldg(act_row + (size_t)(t + 1) * A + (k - L));
-                    o[i] = x;
+                    const float4 w = ldg4(w3, s * 8 + i);
+                    dot = fmaf(elu_fast(__uint_as_float(v[4 * i]) + x[i].x), w.x, dot);
+                    dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 1]) + x[i].y), w.y, dot);
+                    dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 2]) + x[i].z), w.z, dot);
+                    dot = fmaf(elu_fast(__uint_as_float(v[4 * i + 3]) + x[i].w), w.w, dot);
                   }
-                  if (kk + 8 <= L || next_act) sw_store8(za, row, kk, o);     // pure-z group, or the action is replaced too
-                  else {
-                    // group holds action columns that must survive (policy rollout / last step): z elements only
-                    for (int i = 0; i < 8; ++i) if (kk + i < L) za_store1(za, row, kk + i, o[i]);
-                  }
-                }
+                });
               }
+              tcgen05_fence_before();
+              mbar_arrive(&acc_empty[b]);
+            }
+            if (!to_xs && chunk == 3) {
+              // both groups hold a partial reward dot product of this row: combine in group 0
+              m_dot[row] = dot;
+              epi_bar_sync();
+              if (grp == 0) {
+                const float r = (dot + x_dot[row]) + __ldg(ch.b3);
+                G = __fadd_rn(G, __fmul_rn(p.disc[t], r));   // G += discount * reward (tdmpc.py:89): mul, then add, as torch does
+                rlast = r;
+              }
+              dot = 0.0f;
             }
           } else {
-            // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
-            const bool terminal = (flags & F_TERMINAL) != 0;
-            const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
-            for (int a0 = 0; a0 < A; a0 += 32) {
-              uint32_t v[32];
-              tmem_ld32(tlane + TM_ACC + b * 128 + a0, v);
-              tmem_wait_ld_dep(v);
+            if (!mine) continue;
+            acc_wait();
+            tcgen05_fence_after();
+            if (chain == CH_DYN) {
+              // z' = acc + b3 -> [z', a_{t+1}, 0...] row of the next step.  Columns >= L+A of the row are
+              // zero padding written once per tile and never touched again.
+              const bool next_act = p.mode == MODE_VALUE && !(flags & F_LAST_STEP);
+              for (int k0 = 0; k0 < L + A; k0 += 32) {
+                uint32_t v[32];
+                float4 bz[8];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int a = a0 + i;
-                if (a < A) {
-                  float x = 0.0f;
-                  if (valid) {
-                    const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
-                    x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
-                    if (!terminal) pi_row[(size_t)t * A + a] = x;
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k0 < L) {
+                  tmem_ld32(tlane + TM_ACC + b * 128 + k0, v);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) if (k0 + 4 * i < L) bz[i] = ldg4(ch.b3, (k0 >> 2) + i);    // b3 is zero padded to a multiple of 4
+                  tmem_wait_ld_dep(v);
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                  const int kk = k0 + c8 * 8;
+                  if (kk < L + A) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      const int k = kk + i;
+                      const float4 bb = bz[c8 * 2 + (i >> 2)];
+                      const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
+                      float x = 0.0f;
+                      if (k < L) x = __uint_as_float(v[c8 * 8 + i]) + bv;
+                      else if (k < L + A && next_act && valid) x = __ldg(act_row + (size_t)(t + 1) * A + (k - L));
+                      o[i] = x;
+                    }
+                    if (kk + 8 <= L || next_act) sw_store8(za, row, kk, o);     // pure-z group, or the action is replaced too
+                    else {
+                      // group holds action columns that must survive (policy rollout / last step): z elements only
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) if (kk + i < L) za_store1(za, row, kk + i, o[i]);
+                    }
                   }
-                  if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
+                }
+              }
+            } else {
+              // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
+              const bool terminal = (flags & F_TERMINAL) != 0;
+              const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
+#pragma unroll 1
+              for (int a0 = 0; a0 < A; a0 += 4) {
+                uint32_t v[4];
+                tmem_ld4(tlane + TM_ACC + b * 128 + a0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int a = a0 + i;
+                  if (a < A) {
+                    float x = 0.0f;
+                    if (valid) {
+                      const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
+                      x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
+                      if (!terminal) pi_row[(size_t)t * A + a] = x;
+                    }
+                    if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
+                  }
                 }
               }
             }
-          }
-          tcgen05_fence_before();
-          mbar_arrive(&acc_empty[b]);
-          if (!(chain == CH_PI && (flags & F_LAST_STEP))) {
-            fence_proxy_async_smem();
-            mbar_arrive(za_full);
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[b]);
+            if (!(chain == CH_PI && (flags & F_LAST_STEP))) {
+              fence_proxy_async_smem();
+              mbar_arrive(za_full);
+            }
           }
         } else {
           // Q head layer: x = acc + b over all 512 columns, LayerNorm, then
           //   J_QL1: tanh -> bf16 -> XS        J_QL2: ELU -> dot with w3 -> q
-          // pass 1 (sum, sum of squares) runs chunk by chunk as the MMA warp commits them.
+          // Group g handles chunks g and g+2; statistics are exchanged between the groups.
           const bool first = type == J_QL1;
           const float* bias = first ? ch.b1 : ch.b2;
           const float* lg = ch.ln_g[first ? 0 : 1];
           const float* lb = ch.ln_b[first ? 0 : 1];
           float sum = 0.0f, ssq = 0.0f;
-          for (int c = 0; c < 4; ++c) {
+          for (int c = grp; c < 4; c += 2) {
+            float4 x0[8];
+            load8(bias, c * 4, x0);
             mbar_wait(&q_full[c], q_phase, 8);
             tcgen05_fence_after();
-            tmem_stream(tlane + c * 128, 4, [&](int s, uint32_t (&v)[32]) {
+            tmem_stream_aux(tlane + c * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, c * 4 + s, x); },
+                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 f = ldg4(bias, c * 32 + s * 8 + i);
-                const float x0 = __uint_as_float(v[4 * i]) + f.x, x1 = __uint_as_float(v[4 * i + 1]) + f.y;
-                const float x2 = __uint_as_float(v[4 * i + 2]) + f.z, x3 = __uint_as_float(v[4 * i + 3]) + f.w;
-                sum += (x0 + x1) + (x2 + x3);
-                ssq = fmaf(x0, x0, ssq); ssq = fmaf(x1, x1, ssq); ssq = fmaf(x2, x2, ssq); ssq = fmaf(x3, x3, ssq);
+                const float y0 = __uint_as_float(v[4 * i]) + x[i].x, y1 = __uint_as_float(v[4 * i + 1]) + x[i].y;
+                const float y2 = __uint_as_float(v[4 * i + 2]) + x[i].z, y3 = __uint_as_float(v[4 * i + 3]) + x[i].w;
+                sum += (y0 + y1) + (y2 + y3);
+                ssq = fmaf(y0, y0, ssq); ssq = fmaf(y1, y1, ssq); ssq = fmaf(y2, y2, ssq); ssq = fmaf(y3, y3, ssq);
               }
             });
           }
           q_phase ^= 1;
+          m_sum[row] = sum; m_ssq[row] = ssq;
+          epi_bar_sync();
+          sum += x_sum[row]; ssq += x_ssq[row];
           const float mu = sum * (1.0f / 512.0f);
           const float var = fmaxf(ssq * (1.0f / 512.0f) - mu * mu, 0.0f);      // biased variance, as nn.LayerNorm
           const float rstd = 1.0f / sqrtf(var + 1e-5f);
           float qdot = 0.0f;
-          tmem_stream(tlane, 16, [&](int s, uint32_t (&v)[32]) {
-            float y[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = ldg4(bias, s * 8 + i), gg = ldg4(lg, s * 8 + i), bb = ldg4(lb, s * 8 + i);
-              y[4 * i] = (__uint_as_float(v[4 * i]) + f.x - mu) * rstd * gg.x + bb.x;
-              y[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + f.y - mu) * rstd * gg.y + bb.y;
-              y[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + f.z - mu) * rstd * gg.z + bb.z;
-              y[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + f.w - mu) * rstd * gg.w + bb.w;
-            }
-            if (first) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = tanh_fast(y[i]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) sw_store8(xs, row, s * 32 + i * 8, y + i * 8);
-              if ((s & 3) == 3) { fence_proxy_async_smem(); mbar_arrive(&xs_full[s >> 2]); }
-            } else {
+          for (int c = grp; c < 4; c += 2) {
+            tmem_stream(tlane + c * 128, 4, [&](int s, uint32_t (&v)[32]) {
+              float y[32];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 f = ldg4(ch.w3, s * 8 + i);
-                qdot = fmaf(elu_fast(y[4 * i]), f.x, qdot); qdot = fmaf(elu_fast(y[4 * i + 1]), f.y, qdot);
-                qdot = fmaf(elu_fast(y[4 * i + 2]), f.z, qdot); qdot = fmaf(elu_fast(y[4 * i + 3]), f.w, qdot);
+                const int vi = (c * 4 + s) * 8 + i;
+                const float4 x = ldg4(bias, vi), gg = ldg4(lg, vi), bb = ldg4(lb, vi);
+                y[4 * i] = (__uint_as_float(v[4 * i]) + x.x - mu) * rstd * gg.x + bb.x;
+                y[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + x.y - mu) * rstd * gg.y + bb.y;
+                y[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + x.z - mu) * rstd * gg.z + bb.z;
+                y[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + x.w - mu) * rstd * gg.w + bb.w;
               }
-            }
-          });
+              if (first) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) y[i] = tanh_fast(y[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sw_store8(xs, row, c * 128 + s * 32 + i * 8, y + i * 8);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 f = ldg4(ch.w3, (c * 4 + s) * 8 + i);
+                  qdot = fmaf(elu_fast(y[4 * i]), f.x, qdot); qdot = fmaf(elu_fast(y[4 * i + 1]), f.y, qdot);
+                  qdot = fmaf(elu_fast(y[4 * i + 2]), f.z, qdot); qdot = fmaf(elu_fast(y[4 * i + 3]), f.w, qdot);
+                }
+              }
+            });
+            if (first) { fence_proxy_async_smem(); mbar_arrive(&xs_full[c]); }
+          }
           if (!first) {
-            const float qv = qdot + __ldg(ch.b3);
-            if (chain == CH_Q1) q1v = qv;
-            else if (valid) {
-              // G += discount * min(Q1, Q2); nan_to_num_   (tdmpc.py:91-92)
-              const float val = __fadd_rn(G, __fmul_rn(p.disc[p.H], min_nanprop(q1v, qv)));
-              p.values[pb * p.Tcap + pj] = nan_to_num0(val);
-              if (p.last_reward) p.last_reward[pb * p.Tcap + pj] = rlast;
+            m_dot[row] = qdot;
+            epi_bar_sync();
+            if (grp == 0) {
+              const float qv = (qdot + x_dot[row]) + __ldg(ch.b3);
+              if (chain == CH_Q1) q1v = qv;
+              else if (valid) {
+                // G += discount * min(Q1, Q2); nan_to_num_   (tdmpc.py:91-92)
+                const float val = __fadd_rn(G, __fmul_rn(p.disc[p.H], min_nanprop(q1v, qv)));
+                p.values[pb * p.Tcap + pj] = nan_to_num0(val);
+                if (p.last_reward) p.last_reward[pb * p.Tcap + pj] = rlast;
+              }
             }
           }
           tcgen05_fence_before();
-          mbar_arrive(&acc_empty[0]);
-          mbar_arrive(&acc_empty[1]);
+          mbar_arrive(&acc_empty[grp]);
         }
       }
     }
@@ -678,7 +741,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + MAX_JOBS * 4 + (2 * MAX_STAGES + 17) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + XCH_FLOATS * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 17) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return -1;
