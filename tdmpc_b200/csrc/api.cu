@@ -123,6 +123,12 @@ extern "C" int tdmpc_destroy(tdmpc_handle* h) {
 }
 
 extern "C" const char* tdmpc_last_error(const tdmpc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+void tc_set_trace(unsigned long long* dev_buf);
+int tc_trace_slots();
+// Debug hook (not part of the public header): device buffer of tc_trace_slots() uint64 that receives
+// clock64 stamps [role][job][start,end] of one tile of the tcgen05 rollout kernel; NULL disables.
+extern "C" __attribute__((visibility("default"))) int tdmpc_debug_set_trace(void* dev_buf) { tc_set_trace((unsigned long long*)dev_buf); return tc_trace_slots(); }
+
 extern "C" uint64_t tdmpc_launch_count(const tdmpc_handle* h) { return h ? h->launches : 0; }
 extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;select=bitonic"; }
 

@@ -32,7 +32,7 @@ namespace {
 
 constexpr int TILE_ROWS = 128;
 constexpr int NTHREADS = 384;              // warps 0-3: producer / MMA / 2 idle; warps 4-7, 8-11: epilogue groups 0 and 1
-constexpr int REGS_CTRL = 40, REGS_EPI = 232;   // setmaxnreg: frees (168-40)*128 = takes (232-168)*256 registers, exactly
+constexpr int REGS_CTRL = 56, REGS_EPI = 224;   // setmaxnreg: frees (168-56)*128 = takes (224-168)*256 registers, exactly
 constexpr int XCH_FLOATS = 3 * 2 * 128;   // epilogue-group exchange: {sum, sum-of-squares, dot} x 2 groups x 128 rows
 constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
@@ -48,6 +48,7 @@ struct KParams {
   int njobs;
   int stages;
   int num_tiles;
+  unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -171,14 +172,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
       const int ks1_total = m.K1p / 16;
 
-      auto tile_wait = [&]() -> uint32_t {
-        mbar_wait(&w_full[stage], wphase, 2);
+      // Weight-ring consumer.  The mbarrier probe of the NEXT stage is issued before the MMAs of the
+      // current one, so its ~90-cycle latency overlaps the issue instead of adding to every k-block.
+      uint32_t ready = 0;                    // result of the probe of w_full[stage] (0 = unknown / not yet)
+      auto tile_acquire = [&]() -> uint32_t {   // returns the smem address of the current tile, advances the ring
+        if (!ready) mbar_wait(&w_full[stage], wphase, 2);
         tcgen05_fence_after();
-        return ring_addr + stage * TILE_BYTES;
+        const uint32_t addr = ring_addr + stage * TILE_BYTES;
+        return addr;
       };
-      auto tile_release = [&]() {
+      auto tile_release = [&]() {            // commit -> frees the slot when the MMAs that read it retire
         if (leader) umma_commit(&w_empty[stage]);
         if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
+        ready = mbar_try_wait(&w_full[stage], wphase) ? 1u : 0u;
       };
       auto acc_acquire = [&](int b) {
         mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
@@ -204,6 +210,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         for (int j = 0; j < kp.njobs; ++j) {
           const uint32_t job = sjobs[j];
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
+          const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
+          if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
           if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tcgen05_fence_after();
             const uint32_t d = tmem + TM_ACC + b * 128;
             for (int kb = 0; kb < m.nkb1; ++kb) {
-              const uint32_t wt = tile_wait();
+              const uint32_t wt = tile_acquire();
               if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
               tile_release();
             }
@@ -221,9 +229,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             acc_acquire(b);
             tcgen05_fence_after();
             const uint32_t d = tmem + TM_ACC + b * 128;
+#pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
               if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
-              const uint32_t wt = tile_wait();
+              const uint32_t wt = tile_acquire();
               if (leader) {
                 const uint32_t blo = umma_desc_lo(wt);
                 const uint32_t a = tmem + TM_A + kb * 32;
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             uint32_t wt = 0;
             for (int kb = 0; kb < 8; ++kb) {
               if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-              if (!half || (kb & 1) == 0) wt = tile_wait();
+              if (!half || (kb & 1) == 0) wt = tile_acquire();
               if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
               if (!half || (kb & 1)) tile_release();
             }
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             for (int c = 0; c < 4; ++c) {
               for (int kb = 0; kb < nkb; ++kb) {
                 if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-                const uint32_t wt = tile_wait();
+                const uint32_t wt = tile_acquire();
                 if (leader)
                   kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
                             first ? min(4, ks1_total - kb * 4) : 4, kb == 0);
@@ -268,6 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (leader) umma_commit(&q_full[c]);
             }
           }
+          if (tr) kp.trace[(0 * MAX_JOBS + j) * 2 + 1] = clock64();
           __syncwarp();
         }
     }
@@ -335,10 +345,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         const uint32_t job = sjobs[j];
         const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, t = (job >> 8) & 31, flags = job >> 13;
         const TcChain& ch = m.chain[chain];
+        const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && threadIdx.x % 128 == 0;
+        unsigned long long* trp = kp.trace + ((1 + grp) * MAX_JOBS + j) * 2;
 
         if (type <= J_L3) {
           const int b = nbuf; nbuf ^= 1;
           const bool mine = b == grp;
+          if (tr && (mine || (type == J_L2 && chain == CH_REW && chunk == 3))) trp[0] = clock64();
           if (type == J_L1) {
             if (!mine) continue;
             // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
@@ -362,6 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tcgen05_fence_before();
             mbar_arrive(&h1_full[chunk]);
             mbar_arrive(&acc_empty[b]);
+            if (tr) trp[1] = clock64();
           } else if (type == J_L2) {
             const bool to_xs = chain != CH_REW;
             if (mine) {
@@ -414,6 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
               dot = 0.0f;
             }
+            if (tr && (mine || (!to_xs && chunk == 3))) trp[1] = clock64();
           } else {
             if (!mine) continue;
             acc_wait();
@@ -489,8 +504,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               fence_proxy_async_smem();
               mbar_arrive(za_full);
             }
+            if (tr) trp[1] = clock64();
           }
         } else {
+          if (tr) trp[0] = clock64();
           // Q head layer: x = acc + b over all 512 columns, LayerNorm, then
           //   J_QL1: tanh -> bf16 -> XS        J_QL2: ELU -> dot with w3 -> q
           // Group g handles chunks g and g+2; statistics are exchanged between the groups.
@@ -567,6 +584,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           }
           tcgen05_fence_before();
           mbar_arrive(&acc_empty[grp]);
+          if (tr) trp[1] = clock64();
         }
       }
     }
@@ -752,6 +770,10 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   return launches;
 }
 
+static unsigned long long* g_tc_trace = nullptr;
+void tc_set_trace(unsigned long long* dev_buf) { g_tc_trace = dev_buf; }
+int tc_trace_slots() { return 3 * MAX_JOBS * 2; }
+
 int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st) {
   if (p.H < 1 || p.H > TDMPC_MAX_H) return -1;
   KParams kp;
@@ -761,6 +783,7 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.stages = m.stages;
   const long long total = (long long)p.B * p.T;
   kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
+  kp.trace = g_tc_trace;
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   rollout_tc_kernel<<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   return 1;
