@@ -19,14 +19,15 @@ def broadcast_weights(model, src=0):
     (about 6 MB fp32), then each rank re-packs locally (Planner.sync_weights)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
-    params = [p.data for p in model.parameters()]
-    flat = torch.cat([p.reshape(-1) for p in params])
-    dist.broadcast(flat, src=src)
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.copy_(flat[off:off + n].view_as(p))     # in-place: bumps Tensor._version -> planner re-packs
-        off += n
+    params = list(model.parameters())
+    with torch.no_grad():
+        flat = torch.cat([p.reshape(-1) for p in params])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))     # on the parameter itself (not .data): bumps Tensor._version -> planner re-packs
+            off += n
 
 
 def gather_actions(local_actions, total):
