@@ -287,7 +287,9 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "rollout_tc_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload)
+            t = json.load(open(tp)).get(args.workload)
+            if t:   # measured by ncu on a smaller launch of the same kernel; DRAM traffic is per-trajectory data only
+                traffic = t["dram_bytes_per_launch"] * B / t["batch"]
         roof = {"bound": "tensor", "kernel": "rollout_tc_kernel (value mode)" if args.precision == "bf16" else "rollout_fp32_kernel",
                 "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": traffic,
                 "peak_source": f"{src}: bf16_tflops_sustained (kernel runs back-to-back for >1 s); burst {burst}",

@@ -21,6 +21,7 @@
 // The Q heads need the whole 512-wide pre-LayerNorm row, so their jobs use all 512 columns.
 // All three roles walk the same job list (tc_model.cuh), which keeps the mbarrier phases aligned.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "tc_model.cuh"
@@ -48,6 +49,7 @@ struct KParams {
   int njobs;
   int stages;
   int num_tiles;
+  int debug;                   // experiments only (TDMPC_TC_DEBUG): bit0 = producer skips the weight copies (timing probe, wrong results)
   unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py)
 };
 
@@ -134,7 +136,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  if (*tmem_slot != 0) asm volatile("trap;");   // all 512 columns of the SM are ours: the base is 0, so TMEM addresses are immediates
+  constexpr uint32_t tmem = 0;
   const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < 4) {
@@ -152,8 +155,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
             for (int i = 0; i < nt; ++i) {
               mbar_wait(&w_empty[stage], phase ^ 1, 1);
-              mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
-              bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
+              if (kp.debug & 1) mbar_arrive(&w_full[stage]);
+              else {
+                mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
+                bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
+              }
               if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
             }
           }
@@ -172,19 +178,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
       const int ks1_total = m.K1p / 16;
 
-      // Weight-ring consumer.  The mbarrier probe of the NEXT stage is issued before the MMAs of the
-      // current one, so its ~90-cycle latency overlaps the issue instead of adding to every k-block.
-      uint32_t ready = 0;                    // result of the probe of w_full[stage] (0 = unknown / not yet)
-      auto tile_acquire = [&]() -> uint32_t {   // returns the smem address of the current tile, advances the ring
+      // Weight-ring consumer.  tile_acquire() returns the smem address of the current tile and already
+      // advances the ring and probes the NEXT tile's barrier, so that probe's latency overlaps the MMA
+      // issue; tile_release(slot) commits the slot that was just consumed.
+      uint32_t ready = 0;                    // result of the early probe of w_full[stage]
+      uint32_t cur_stage = 0;
+      auto tile_acquire = [&]() -> uint32_t {
         if (!ready) mbar_wait(&w_full[stage], wphase, 2);
         tcgen05_fence_after();
-        const uint32_t addr = ring_addr + stage * TILE_BYTES;
-        return addr;
-      };
-      auto tile_release = [&]() {            // commit -> frees the slot when the MMAs that read it retire
-        if (leader) umma_commit(&w_empty[stage]);
+        cur_stage = stage;
         if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
         ready = mbar_try_wait(&w_full[stage], wphase) ? 1u : 0u;
+        return ring_addr + cur_stage * TILE_BYTES;
+      };
+      auto tile_release = [&]() {            // commit -> frees the slot when the MMAs that read it retire
+        if (leader) umma_commit(&w_empty[cur_stage]);
       };
       auto acc_acquire = [&](int b) {
         mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
@@ -250,6 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
             const bool half = m.l3rows[chain] == 64;
             uint32_t wt = 0;
+#pragma unroll
             for (int kb = 0; kb < 8; ++kb) {
               if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
               if (!half || (kb & 1) == 0) wt = tile_acquire();
@@ -784,6 +793,7 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   const long long total = (long long)p.B * p.T;
   kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
   kp.trace = g_tc_trace;
+  { const char* e = getenv("TDMPC_TC_DEBUG"); kp.debug = e ? atoi(e) : 0; }
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   rollout_tc_kernel<<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   return 1;
