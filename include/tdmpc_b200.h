@@ -113,6 +113,18 @@ typedef struct {
   int32_t best_a_last;      /* iCEM: sample 0 of the last iteration := mean (:213-214)            */
   int32_t shift_elites;     /* iCEM: iteration-0 reuse = previous step's elites shifted by one (:217-224) */
   int32_t has_prev;         /* 0: prev_mean holds nothing yet (hasattr(self,'_prev_mean') False)  */
+  int32_t elite_horizon;    /* iCEM: horizon the stored elite_actions were planned with (== horizon unless the
+                               plan horizon just grew, `extend_horizon`, tdmpc_icem_similarity_mlp.py:170-173,220-221) */
+  /* iCEM colored action noise for the built-in generator (tdmpc_icem_similarity_mlp.py:126-157).  Ignored where
+   * noise is injected (injected buffers hold final unit-variance noise).  color_len = length of the synthesised
+   * series (cfg.horizon), 0 = white noise only.  color_mats: device [3][color_len][color_len] fp32 synthesis
+   * matrices (colored = S . white along the horizon): [0] second class ("pink"), [1] third class ("brown"),
+   * [2] the tail sampler of the shifted elites (sample_action_sequence, cfg.noise_beta).  Per iteration the first
+   * n_white[i] sampled rows are white, the next n_color1[i] use mats[0], the rest mats[1]. */
+  int32_t color_len;
+  const float* color_mats;
+  int32_t n_white[TDMPC_MAX_ITERS];
+  int32_t n_color1[TDMPC_MAX_ITERS];
 
   const float* obs;         /* device [B, obs_dim]                                                */
   const float* z0;          /* device [B, latent_dim] or NULL; when set the encoder is skipped    */
@@ -128,6 +140,7 @@ typedef struct {
   const float* noise_cem;   /* device [B, I, H, Nmax, A]     torch.randn(H,N,A) of each iteration     */
   const float* noise_term;  /* device [B, I, Tmax, A]        terminal-policy draws in estimate_value  */
   const float* noise_out;   /* device [B, A]                 exploration noise (tdmpc.py:158)         */
+  const float* noise_shift; /* device [B, H, E0, A]          iCEM: tail of the shifted elites (E0 = n_reuse[0]) */
   const double* u_pick;     /* device [B]                    uniform of np.random.choice (:153)       */
 
   float* action;            /* device [B, A] out                                                  */
@@ -185,7 +198,7 @@ TDMPC_API int tdmpc_select_update(tdmpc_handle* h, const float* values, const fl
 TDMPC_API int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* args, void* stream);
 
 /* The built-in noise stream, exposed so tests can feed the SAME draws to the oracle:
- * out[i] = i-th standard normal of stream `stream_id` (0 pi, 1 cem, 2 term, 3 out) for (seed, call);
+ * out[i] = i-th standard normal of stream `stream_id` (0 pi, 1 cem, 2 term, 3 out, 5 shift) for (seed, call);
  * stream 4 writes uniforms in [0,1) as float64 (u_pick). */
 TDMPC_API int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,
                      void* out, void* stream);

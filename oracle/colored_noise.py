@@ -11,7 +11,7 @@ vector exists anywhere in the reference).  Call sites it stands in for:
 Algorithm (published): draw independent Gaussian real/imag Fourier coefficients with
 standard deviation f^(-beta/2) on the rfft grid of the last axis, make the DC and (for
 even n) Nyquist bins real, inverse-rfft, and divide by the analytic standard deviation
-so each sample has unit variance.
+so each sample has (approximately) unit variance.
 
 Because every sample is a fixed linear map of white Gaussians, ``synthesis_matrix``
 below returns that map explicitly; the CUDA sampler multiplies white noise by the same
@@ -57,7 +57,8 @@ def synthesis_matrix(beta, n):
     """[n, n] float64 matrix S with  colored = S @ white  (white ~ N(0, I_n)).
 
     Column order of the white vector: real parts of bins 0..n//2, then the imaginary
-    parts of the bins that keep one (1..ceil(n/2)-1).  S S^T has unit diagonal.
+    parts of the bins that keep one (1..ceil(n/2)-1).  diag(S S^T) is a constant slightly above 1: the
+    package normalises by the analytic std of the non-DC bins only; reproduced as is.
     """
     scale, sigma = _spectrum_scale(beta, n)
     nb = len(scale)

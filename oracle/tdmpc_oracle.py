@@ -368,6 +368,94 @@ def plan_icem_mlp(sd, cfg, obs, *, eval_mode, step, t0, state, noise, quant=Fals
     return a, metrics, taps
 
 
+# ----------------------------------------------------------------------------- iCEM (DRNN / GRU dynamics)
+
+
+def icem_drnn_sizes(cfg, mixture_coef, have_elites, t0):
+    """Per-iteration (N_i, E_i, P_i) of TdICemSimDssm.plan (tdmpc_icem_similarity_drnn.py:203-214): as the MLP
+    variant, but elite reuse is gated on `not t0` in EVERY iteration."""
+    out = []
+    n = cfg.num_samples
+    for i in range(cfg.iterations):
+        if i > 0:
+            n = max(2 * cfg.num_elites, int(n / cfg.factor_decrease_num))
+        p = int(mixture_coef * n)
+        have = (have_elites or i > 0) and not t0
+        e = int(cfg.fraction_elites_reused * cfg.num_elites) if (cfg.fraction_elites_reused > 0 and have) else 0
+        out.append((n, e, p))
+    return out
+
+
+def plan_icem_drnn(sd, cfg, obs, hidden, *, eval_mode, step, t0, state, noise, quant=False):
+    """TdICemSimDssm.plan (tdmpc_icem_similarity_drnn.py:168-272), draws injected.
+    hidden [1, Hd] in; returns (a, hidden' [1, Hd], metrics, taps).  noise as plan_icem_mlp ('cem' already
+    colored with the single cfg.noise_beta of sample_action_sequence, :135-146)."""
+    metrics = {"external_reward_mean": 0.0, "current_std": 0.0}
+    if step < cfg.seed_steps and not eval_mode:
+        return noise["seed_uniform"].clone(), None, metrics, {}
+    A = cfg.action_dim
+    extend_horizon = False
+    horizon = int(min(cfg.horizon, linear_schedule(cfg.horizon_schedule, step)))
+    if horizon != state["plan_horizon"] and t0:
+        state["plan_horizon"] = horizon
+        extend_horizon = True
+    H = state["plan_horizon"]
+    mix = linear_schedule(cfg.regularization_schedule, step)
+    state["mixture_coef"] = mix
+    mean = torch.zeros(H, A)
+    std = 0.5 * torch.ones(H, A)
+    pm = state.get("_prev_mean")
+    if not t0 and pm is not None:
+        mean[:-1] = pm[1:]
+        mean[-1] = pm[-1]
+    N = cfg.num_samples
+    P = int(mix * N)
+    assert P > 0
+    obs = torch.as_tensor(obs, dtype=torch.float32).unsqueeze(0)
+    z = told_h(sd, obs)
+    pi_actions = torch.empty(H, P, A)
+    zs, hs = z.repeat(P, 1), hidden.repeat(P, 1)
+    for t in range(H):
+        pi_actions[t] = told_pi(sd, zs, cfg.min_std, noise["pi"][t], quant)
+        zs, hs, _ = dssm_next(sd, zs, pi_actions[t], hs, quant)
+    taps = {"values": [], "elite_idx": [], "mean": [], "std": [], "sizes": []}
+    for i in range(cfg.iterations):
+        if i > 0:
+            N = max(2 * cfg.num_elites, int(N / cfg.factor_decrease_num))
+            P = int(mix * N)
+        have = state.get("_elite_actions") is not None
+        E = int(cfg.fraction_elites_reused * cfg.num_elites) if (cfg.fraction_elites_reused > 0 and have and not t0) else 0
+        T = N + P + E
+        actions_sampled = torch.clamp(mean.unsqueeze(1) + std.unsqueeze(1) * noise["cem"][i], -1, 1)
+        if i == cfg.iterations - 1:
+            actions_sampled[:, 0] = mean
+        if i == 0 and cfg.shift_elites_over_time and have and not t0:
+            reused = state["_elite_actions"][1:, :E]
+            tail = torch.clamp(mean.unsqueeze(1) + std.unsqueeze(1) * noise["shift"], -1, 1)
+            tail = tail[-2:] if extend_horizon else tail[-1:]
+            reused = torch.cat([reused, tail], dim=0)
+        if i > 0 and cfg.keep_previous_elites:
+            reused = state["_elite_actions"][:, :E]
+        actions = torch.cat([actions_sampled, reused, pi_actions[:, :P]], dim=1) if E > 0 else torch.cat([actions_sampled, pi_actions[:, :P]], dim=1)
+        value, reward_mean = estimate_value(sd, z.repeat(T, 1), actions, H, cfg.discount, cfg.min_std, noise["term"][i], quant,
+                                            hidden=hidden.repeat(T, 1))
+        elite_idxs = topk_desc(value.squeeze(1), cfg.num_elites)
+        elite_value, elite_actions = value[elite_idxs], actions[:, elite_idxs]
+        state["_elite_actions"] = elite_actions
+        mean, std, score = cem_update(elite_value, elite_actions, mean, cfg.temperature, cfg.momentum, state["std"])
+        taps["values"].append(value.squeeze(1).clone()); taps["elite_idx"].append(elite_idxs.clone())
+        taps["mean"].append(mean.clone()); taps["std"].append(std.clone()); taps["sizes"].append((N, E, P))
+    j = categorical_pick(score, noise["u"])
+    state["_prev_mean"] = mean
+    a = elite_actions[0, j].clone()
+    if not eval_mode:
+        a = a + std[0] * noise["out"]
+    _, hidden_next, _ = dssm_next(sd, z[0:1], a.unsqueeze(0), hidden, quant)
+    metrics = {"external_reward_mean": reward_mean, "current_std": std[0].mean().item()}
+    taps["pick"] = j
+    return a, hidden_next, metrics, taps
+
+
 # ----------------------------------------------------------------------------- flop / step accounting (SURVEY 8d)
 
 

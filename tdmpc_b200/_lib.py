@@ -49,10 +49,12 @@ class PlanArgs(C.Structure):
         ("temperature", C.c_float), ("min_std", C.c_float), ("std_floor", C.c_float), ("std_max", C.c_float),
         ("init_std", C.c_float),
         ("eval_mode", C.c_int32), ("t0_all", C.c_int32), ("warm_last", C.c_int32), ("best_a_last", C.c_int32),
-        ("shift_elites", C.c_int32), ("has_prev", C.c_int32),
+        ("shift_elites", C.c_int32), ("has_prev", C.c_int32), ("elite_horizon", C.c_int32),
+        ("color_len", C.c_int32), ("color_mats", _fp),
+        ("n_white", C.c_int32 * TDMPC_MAX_ITERS), ("n_color1", C.c_int32 * TDMPC_MAX_ITERS),
         ("obs", _fp), ("z0", _fp), ("t0", _fp), ("prev_mean", _fp), ("elite_actions", _fp),
         ("seed", C.c_uint64), ("call", C.c_uint64),
-        ("noise_pi", _fp), ("noise_cem", _fp), ("noise_term", _fp), ("noise_out", _fp), ("u_pick", _fp),
+        ("noise_pi", _fp), ("noise_cem", _fp), ("noise_term", _fp), ("noise_out", _fp), ("noise_shift", _fp), ("u_pick", _fp),
         ("action", _fp), ("metrics", _fp),
         ("tap_values", _fp), ("tap_elite_idx", _fp), ("tap_mean", _fp), ("tap_std", _fp), ("tap_z0", _fp),
     ]

@@ -307,7 +307,7 @@ extern "C" int tdmpc_select_update(tdmpc_handle* h, const float* values, const f
 
 extern "C" int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,
                                 void* out, void* stream) {
-  if (!h || !out || stream_id < 0 || stream_id > NS_PICK) return TDMPC_ERR_INVALID;
+  if (!h || !out || stream_id < 0 || stream_id > NS_SHIFT) return TDMPC_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
   launch_fill_noise(stream_id, seed, call, count, out, (cudaStream_t)stream);
   return check_launch(h, "fill_noise");
@@ -360,16 +360,35 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
   }
 
   float* elites = a->elite_actions ? a->elite_actions : h->elites;
+  bool any_reuse = false;
+  for (int i = 0; i < I; ++i) any_reuse = any_reuse || a->n_reuse[i] > 0;
+  if (a->n_reuse[0] > 0 && !a->elite_actions) FAIL(h, TDMPC_ERR_INVALID, "plan: n_reuse[0] > 0 needs elite_actions from the previous step");
+  const int CL = a->color_len;
+  if (CL < 0 || CL > TDMPC_MAX_H || (CL > 0 && (!a->color_mats || CL < H))) FAIL(h, TDMPC_ERR_INVALID, "plan: bad colored-noise spec");
+  const int eh = a->elite_horizon > 0 ? a->elite_horizon : H;
+  if (eh > H || eh < 1) FAIL(h, TDMPC_ERR_INVALID, "plan: elite_horizon %d out of range", eh);
+  // time rows of the cem noise stream: injected buffers are [.., H, Nmax, A]; the built-in colored
+  // generator needs color_len white rows per trajectory
+  const int Trows = (a->noise_cem || CL == 0) ? H : CL;
   const NoiseSrc cem{a->noise_cem, a->seed, a->call, NS_CEM};
-  const uint64_t cem_bstride = (uint64_t)I * H * Nmax * A;
+  const uint64_t cem_bstride = (uint64_t)I * Trows * Nmax * A;
+  auto spec = [&](int i) {
+    SampleSpec sp{};
+    sp.N = a->n_samples[i]; sp.E = a->n_reuse[i]; sp.P = a->n_pi[i];
+    sp.best_a = (a->best_a_last && i == I - 1) ? 1 : 0;
+    sp.cem = cem; sp.cem_base = (uint64_t)i * Trows * Nmax * A; sp.cem_bstride = cem_bstride; sp.cem_rows = Nmax;
+    sp.color_mats = a->color_mats; sp.color_len = CL;
+    sp.n_white = CL > 0 ? a->n_white[i] : sp.N; sp.n_pink = CL > 0 ? a->n_color1[i] : 0;
+    return sp;
+  };
 
   InitParams ip{};
-  ip.B = B; ip.H = H; ip.A = A; ip.N = a->n_samples[0]; ip.E = a->n_reuse[0]; ip.P = a->n_pi[0]; ip.Tcap = Tmax;
+  ip.B = B; ip.H = H; ip.A = A; ip.Tcap = Tmax; ip.first = spec(0);
   ip.init_std = a->init_std; ip.t0_all = a->t0_all; ip.t0 = a->t0; ip.has_prev = a->has_prev; ip.warm_last = a->warm_last;
   ip.prev_mean = a->prev_mean; ip.mean = h->mean; ip.std = h->std; ip.actions = h->actions;
-  ip.pi_actions = h->pi_actions; ip.P0 = P0; ip.elite_actions = elites; ip.K = K; ip.shift_elites = a->shift_elites;
-  ip.cem = cem; ip.cem_base = 0; ip.cem_bstride = cem_bstride; ip.cem_rows = Nmax;
-  ip.best_a = (a->best_a_last && I == 1) ? 1 : 0;
+  ip.pi_actions = h->pi_actions; ip.P0 = P0; ip.elite_actions = elites; ip.K = K; ip.shift_elites = a->shift_elites; ip.elite_h = eh;
+  ip.shift = NoiseSrc{a->noise_shift, a->seed, a->call, NS_SHIFT};
+  ip.shift_mat = (CL > 0 && !a->noise_shift) ? a->color_mats + 2 * (size_t)CL * CL : nullptr;
   launch_init(ip, st);
   if (int r = check_launch(h, "init")) return r;
 
@@ -389,14 +408,12 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     sp.temperature = a->temperature; sp.momentum = (float)a->momentum; sp.one_minus_momentum = (float)(1.0 - a->momentum);
     sp.std_floor = a->std_floor; sp.std_max = a->std_max;
     sp.elite_idx = h->elite_idx; sp.score = h->score;
-    sp.elite_actions = (a->elite_actions || a->n_reuse[i + 1 < I ? i + 1 : i] > 0) ? elites : nullptr;
+    sp.elite_actions = (a->elite_actions || any_reuse) ? elites : nullptr;
     const bool last = i == I - 1;
     sp.do_sample = !last; sp.do_output = last;
     if (!last) {
-      sp.next_N = a->n_samples[i + 1]; sp.next_E = a->n_reuse[i + 1]; sp.next_P = a->n_pi[i + 1];
-      sp.best_a = (a->best_a_last && i + 1 == I - 1) ? 1 : 0;
+      sp.next = spec(i + 1);
       sp.pi_actions = h->pi_actions; sp.P0 = P0;
-      sp.cem = cem; sp.cem_base = (uint64_t)(i + 1) * H * Nmax * A; sp.cem_bstride = cem_bstride; sp.cem_rows = Nmax;
     }
     sp.eval_mode = a->eval_mode;
     sp.out_noise = NoiseSrc{a->noise_out, a->seed, a->call, NS_OUT};

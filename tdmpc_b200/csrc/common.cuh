@@ -30,7 +30,7 @@ struct ModelFp32 {
 // ------------------------------------------------------------------------------------------
 // Noise source: injected buffer (parity tests) or Philox4x32-10 keyed by (seed, call, stream).
 // Both are addressed by the same flat element index, see include/tdmpc_b200.h for the layouts.
-enum NoiseStream { NS_PI = 0, NS_CEM = 1, NS_TERM = 2, NS_OUT = 3, NS_PICK = 4 };
+enum NoiseStream { NS_PI = 0, NS_CEM = 1, NS_TERM = 2, NS_OUT = 3, NS_PICK = 4, NS_SHIFT = 5 };
 
 struct NoiseSrc {
   const float* inj;      // nullptr -> Philox
@@ -130,6 +130,19 @@ struct RolloutParams {
   float disc[TDMPC_MAX_H + 1];   // (float)gamma^t, gamma^t accumulated in double like the reference
 };
 
+// Sampling of one iteration's action rows, in the reference's concatenation order
+// [sampled | reused elites | pi]  (tdmpc.py:130-134; tdmpc_icem_similarity_mlp.py:139-157,200-233).
+struct SampleSpec {
+  int N, E, P;               // rows of the iteration
+  int best_a;                // iCEM best-a: sample 0 := mean (tdmpc_icem_similarity_mlp.py:213-214)
+  NoiseSrc cem;              // unit-variance noise [.., Trows, cem_rows, A]; injected buffers are used as they are
+  uint64_t cem_base, cem_bstride; int cem_rows;
+  // colored noise for the built-in generator (ignored when cem.inj is set): rows [0,n_white) white,
+  // [n_white, n_white+n_pink) mats[0], the rest mats[1]; mats are [color_len][color_len] synthesis
+  // matrices (colored = S * white along the horizon axis)
+  const float* color_mats; int color_len; int n_white, n_pink;
+};
+
 // Selection / distribution update / next-iteration sampling.
 struct SelectParams {
   int B, T, H, A, K;
@@ -144,12 +157,10 @@ struct SelectParams {
   int* elite_idx;            // [B, K] scratch/out
   float* score;              // [B, K] scratch/out
   float* elite_actions;      // [B, K, H, A] out (iCEM carry-over) or nullptr
-  // next-iteration sampling (ignored on the last iteration)
-  int next_N, next_E, next_P; // rows of the next iteration
-  int best_a;                 // next iteration is the last and best-a overwrite is on
+  // next-iteration sampling (do_sample)
+  SampleSpec next;
   const float* pi_actions;    // [B, P0, H, A]
   int P0;
-  NoiseSrc cem;  uint64_t cem_base, cem_bstride; int cem_rows;   // [.., H, Nmax, A]
   // final outputs (last iteration)
   int eval_mode;
   NoiseSrc out_noise; NoiseSrc pick;
@@ -161,16 +172,18 @@ struct SelectParams {
 
 struct InitParams {
   int B, H, A;
-  int N, E, P, Tcap;          // rows of iteration 0
+  int Tcap;
+  SampleSpec first;           // rows of iteration 0
   float init_std;
   int t0_all; const uint8_t* t0; int has_prev; int warm_last;
   const float* prev_mean;     // [B,H,A]
   float* mean; float* std;
   float* actions;
   const float* pi_actions; int P0;
-  const float* elite_actions; int K; int shift_elites;   // iCEM step-shifted reuse
-  NoiseSrc cem; uint64_t cem_base, cem_bstride; int cem_rows;
-  int best_a;
+  // iCEM: iteration-0 reuse = previous step's elites shifted by one step, tail re-sampled
+  // (tdmpc_icem_similarity_mlp.py:217-224).  elite_h = horizon the stored elites were planned with.
+  float* elite_actions; int K; int shift_elites; int elite_h;
+  NoiseSrc shift; const float* shift_mat;     // tail noise [B, Trows, E, A]; synthesis matrix or nullptr
 };
 
 // kernels implemented in the .cu files -----------------------------------------------------

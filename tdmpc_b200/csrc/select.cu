@@ -77,27 +77,40 @@ __device__ void bitonic_sort_desc(float* key, int* idx, int n) {
   }
 }
 
+// Unit-variance noise of trajectory n at step t, action a.  Built-in generator: white rows read one
+// Philox normal; colored rows (iCEM) are S[t][:] . white[:, n, a] with S the power-law synthesis
+// matrix along the horizon axis (restates colorednoise.powerlaw_psd_gaussian as a linear map).
+__device__ __forceinline__ float sample_noise(const SampleSpec& sp, int b, int t, int n, int a, int A) {
+  const uint64_t row0 = sp.cem_base + (uint64_t)b * sp.cem_bstride;
+  if (sp.cem.inj || sp.color_len == 0 || n < sp.n_white)
+    return noise_at(sp.cem, row0 + ((uint64_t)t * sp.cem_rows + n) * A + a);
+  const float* S = sp.color_mats + (n < sp.n_white + sp.n_pink ? 0 : sp.color_len * sp.color_len) + t * sp.color_len;
+  float acc = 0.0f;
+  for (int j = 0; j < sp.color_len; ++j)
+    acc = fmaf(__ldg(S + j), philox_normal(sp.cem, row0 + ((uint64_t)j * sp.cem_rows + n) * A + a), acc);
+  return acc;
+}
+
 // Rows of one iteration, in the reference's concatenation order [sampled | reused elites | pi]
-// (tdmpc.py:130-134; tdmpc_icem_similarity_mlp.py:230-233).
-__device__ void sample_rows(int b, int N, int E, int P, int Tcap, int H, int A, const float* mean_s, const float* std_s,
-                            const NoiseSrc& cem, uint64_t cem_base, uint64_t cem_bstride, int cem_rows,
-                            float* actions, const float* pi_actions, int P0, const float* reuse, int reuse_rows,
-                            int best_a) {
+// (tdmpc.py:130-134; tdmpc_icem_similarity_mlp.py:230-233).  `reuse` rows must already be in place
+// (init_kernel writes the shifted elites itself) unless reuse != nullptr.
+__device__ void sample_rows(int b, const SampleSpec& sp, int Tcap, int H, int A, const float* mean_s, const float* std_s,
+                            float* actions, const float* pi_actions, int P0, const float* reuse, int reuse_rows) {
   const int HA = H * A;
   float* out = actions + (size_t)b * Tcap * HA;
-  for (int e = threadIdx.x; e < N * HA; e += NT) {
+  for (int e = threadIdx.x; e < sp.N * HA; e += NT) {
     const int n = e / HA, ta = e - n * HA;
     const int t = ta / A, a = ta - t * A;
-    const float xi = noise_at(cem, cem_base + (uint64_t)b * cem_bstride + ((uint64_t)t * cem_rows + n) * A + a);
-    float v = mean_s[ta] + std_s[ta] * xi;          // mean + std * randn, then clamp(-1, 1)  (tdmpc.py:130-132)
+    float v = mean_s[ta] + std_s[ta] * sample_noise(sp, b, t, n, a, A);   // mean + std * noise, clamp(-1, 1)  (tdmpc.py:130-132)
     v = fminf(fmaxf(v, -1.0f), 1.0f);
-    if (best_a && n == 0) v = mean_s[ta];           // iCEM best-a (tdmpc_icem_similarity_mlp.py:213-214)
+    if (sp.best_a && n == 0) v = mean_s[ta];        // iCEM best-a (tdmpc_icem_similarity_mlp.py:213-214)
     out[e] = v;
   }
-  for (int e = threadIdx.x; e < E * HA; e += NT)
-    out[(size_t)N * HA + e] = reuse[(size_t)b * reuse_rows * HA + e];
-  for (int e = threadIdx.x; e < P * HA; e += NT)
-    out[(size_t)(N + E) * HA + e] = pi_actions[(size_t)b * P0 * HA + e];
+  if (reuse)
+    for (int e = threadIdx.x; e < sp.E * HA; e += NT)
+      out[(size_t)sp.N * HA + e] = reuse[(size_t)b * reuse_rows * HA + e];
+  for (int e = threadIdx.x; e < sp.P * HA; e += NT)
+    out[(size_t)(sp.N + sp.E) * HA + e] = pi_actions[(size_t)b * P0 * HA + e];
 }
 
 __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
@@ -162,8 +175,7 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
   __syncthreads();
 
   if (p.do_sample) {
-    sample_rows(b, p.next_N, p.next_E, p.next_P, p.Tcap, H, A, mean_s, std_s, p.cem, p.cem_base, p.cem_bstride,
-                p.cem_rows, p.actions, p.pi_actions, p.P0, p.elite_actions, K, p.best_a);
+    sample_rows(b, p.next, p.Tcap, H, A, mean_s, std_s, p.actions, p.pi_actions, p.P0, p.elite_actions, K);
     return;
   }
   if (!p.do_output) return;
@@ -215,8 +227,32 @@ __global__ void __launch_bounds__(NT) init_kernel(InitParams p) {
     p.mean[(size_t)b * HA + e] = m; p.std[(size_t)b * HA + e] = p.init_std;
   }
   __syncthreads();
-  sample_rows(b, p.N, p.E, p.P, p.Tcap, H, A, mean_s, std_s, p.cem, p.cem_base, p.cem_bstride, p.cem_rows, p.actions,
-              p.pi_actions, p.P0, p.elite_actions, p.K, p.best_a);
+  // iteration-0 reused rows: previous step's elites advanced by one step; the tail that runs past
+  // the stored horizon is sampled afresh from (mean, std) with its own noise stream
+  const SampleSpec& sp = p.first;
+  if (sp.E > 0) {
+    float* out = p.actions + ((size_t)b * p.Tcap + sp.N) * HA;
+    for (int e = threadIdx.x; e < sp.E * HA; e += NT) {
+      const int k = e / HA, ta = e - k * HA;
+      const int t = ta / A, a = ta - t * A;
+      float v;
+      if (!p.shift_elites) v = p.elite_actions[((size_t)b * p.K + k) * HA + ta];
+      else if (t < p.elite_h - 1) v = p.elite_actions[((size_t)b * p.K + k) * (size_t)p.elite_h * A + (size_t)(t + 1) * A + a];
+      else {
+        const uint64_t row0 = (uint64_t)b * H * sp.E * A;
+        float xi;
+        if (p.shift.inj || !p.shift_mat) xi = noise_at(p.shift, row0 + ((uint64_t)t * sp.E + k) * A + a);
+        else {
+          xi = 0.0f;
+          for (int j = 0; j < sp.color_len; ++j)
+            xi = fmaf(__ldg(p.shift_mat + t * sp.color_len + j), philox_normal(p.shift, row0 + ((uint64_t)j * sp.E + k) * A + a), xi);
+        }
+        v = fminf(fmaxf(mean_s[ta] + std_s[ta] * xi, -1.0f), 1.0f);
+      }
+      out[e] = v;
+    }
+  }
+  sample_rows(b, sp, p.Tcap, H, A, mean_s, std_s, p.actions, p.pi_actions, p.P0, nullptr, 0);
 }
 
 __global__ void fill_noise_kernel(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out) {

@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .told import TOLD, linear_schedule
+from .colored import color_matrices, mix_split
+from .told import DSSM, TOLD, linear_schedule
 
 _PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
 
@@ -177,7 +178,8 @@ class Planner:
     def plan(self, obs=None, *, z0=None, horizon, num_samples, num_pi_trajs, num_elites, iterations, discount,
              temperature, momentum, min_std, std_floor, std_max=2.0, init_std=2.0, eval_mode=False, t0=True,
              prev_mean=None, has_prev=None, noise=None, taps=False, seed=None, call=None,
-             n_samples=None, n_reuse=None, n_pi=None, out=None):
+             n_samples=None, n_reuse=None, n_pi=None, out=None, elite_actions=None, elite_horizon=0,
+             warm_last=False, best_a_last=False, shift_elites=False, color=None):
         """TDMPC.plan (tdmpc.py:94-163) for a batch of independent problems.
 
         obs [B,D] (or z0 [B,L]) on the device.  prev_mean [B,H,A] is read (warm start) and
@@ -212,6 +214,15 @@ class Planner:
         else:
             a.t0_all = int(bool(t0))
         a.has_prev = int(bool(has_prev))
+        a.warm_last, a.best_a_last, a.shift_elites = int(bool(warm_last)), int(bool(best_a_last)), int(bool(shift_elites))
+        a.elite_horizon = int(elite_horizon)
+        if elite_actions is not None:       # [B, K, H, A] in/out (iCEM agent._elite_actions)
+            assert elite_actions.is_contiguous() and elite_actions.dtype == torch.float32 and elite_actions.numel() >= B * K * H * A
+            a.elite_actions = elite_actions.data_ptr()
+        if color is not None:               # dict(len=, mats=[3,len,len] device fp32, n_white=[I], n_color1=[I])
+            a.color_len = int(color["len"]); keep.append(color["mats"]); a.color_mats = color["mats"].data_ptr()
+            for i in range(I):
+                a.n_white[i], a.n_color1[i] = int(color["n_white"][i]), int(color["n_color1"][i])
         if z0 is None:
             obs = _f32(obs, self.device); keep.append(obs); a.obs = obs.data_ptr()
         else:
@@ -224,8 +235,10 @@ class Planner:
             call = self.call
         a.call = call
         if noise is not None:
-            exp = {"pi": (B, H, int(num_pi_trajs), A), "cem": (B, I, H, Nmax, A), "term": (B, I, Tmax, A), "out": (B, A)}
-            for k, fld in (("pi", "noise_pi"), ("cem", "noise_cem"), ("term", "noise_term"), ("out", "noise_out")):
+            exp = {"pi": (B, H, int(num_pi_trajs), A), "cem": (B, I, H, Nmax, A), "term": (B, I, Tmax, A), "out": (B, A),
+                   "shift": (B, H, nr[0], A)}
+            for k, fld in (("pi", "noise_pi"), ("cem", "noise_cem"), ("term", "noise_term"), ("out", "noise_out"),
+                           ("shift", "noise_shift")):
                 if noise.get(k) is not None:
                     t = _f32(noise[k], self.device)
                     assert tuple(t.shape) == exp[k], (k, tuple(t.shape), exp[k])
@@ -286,6 +299,79 @@ def _fast_plan(self, obs, eval_mode=False, step=None, t0=True):
     return res["action"][0], plan_metrics
 
 
+def icem_sizes(cfg, mixture_coef, have_elites):
+    """Per-iteration (sampled, reused, pi) row counts of TdICemSimMlp.plan
+    (tdmpc_icem_similarity_mlp.py:182-210): sample-count decay, elite carry-over."""
+    out, n = [], cfg.num_samples
+    for i in range(cfg.iterations):
+        if i > 0:
+            n = max(2 * cfg.num_elites, int(n / cfg.factor_decrease_num))
+        p = int(mixture_coef * n)
+        if p <= 0:
+            raise AssertionError("num_pi_trajs must be > 0")            # the reference asserts the same (:184,:203)
+        reuse = cfg.fraction_elites_reused > 0 and (have_elites or i > 0)
+        out.append((n, int(cfg.fraction_elites_reused * cfg.num_elites) if reuse else 0, p))
+    return out
+
+
+def _fast_plan_icem(self, obs, eval_mode=False, step=None, t0=True):
+    """Drop-in for TdICemSimMlp.plan (src/algorithm/tdmpc_icem_similarity_mlp.py:159-265): colored-noise
+    sampling, sample-count decay, elite carry-over across steps (shifted) and iterations, best-a, warm
+    start with repeated last mean.  Same arguments / return / side effects (plan_horizon, mixture_coef,
+    _prev_mean, _elite_actions)."""
+    cfg = self.cfg
+    plan_metrics = {"external_reward_mean": 0.0, "current_std": 0.0}
+    if step < cfg.seed_steps and not eval_mode:
+        return torch.empty(cfg.action_dim, dtype=torch.float32, device=self.device).uniform_(-1, 1), plan_metrics
+    pl = self._planner
+    pl.sync_weights(self.model)
+    horizon = int(min(cfg.horizon, linear_schedule(cfg.horizon_schedule, step)))
+    extend = False
+    if horizon != self.plan_horizon and t0:
+        self.plan_horizon = horizon
+        extend = True
+    H, A, K, I = self.plan_horizon, cfg.action_dim, cfg.num_elites, cfg.iterations
+    self.mixture_coef = linear_schedule(cfg.regularization_schedule, step)
+    prev_elites = getattr(self, "_elite_actions", None)            # reference layout [H_e, K, A]
+    have = prev_elites is not None
+    sizes = icem_sizes(cfg, self.mixture_coef, have)
+    shift = bool(cfg.shift_elites_over_time) and have
+    if have and not shift and sizes[0][1] > 0:
+        raise RuntimeError("fraction_elites_reused > 0 without shift_elites_over_time leaves `reused_actions` "
+                           "undefined in the reference (tdmpc_icem_similarity_mlp.py:217-231)")
+    ebuf = torch.zeros(1, K, H, A, device=self.device)
+    eh = H
+    if have:
+        eh = prev_elites.shape[0]
+        if eh not in (H, H - 1) or (eh == H - 1 and not extend):
+            raise RuntimeError(f"shape mismatch: _elite_actions has horizon {eh}, plan horizon is {H}")
+        ebuf.view(-1)[: K * eh * A] = prev_elites.permute(1, 0, 2).reshape(-1)      # [K][eh][A] at the buffer start
+    prev = getattr(self, "_prev_mean", None)
+    has_prev = prev is not None and not t0
+    if has_prev and prev.shape[0] != H:
+        raise RuntimeError(f"shape mismatch: _prev_mean has horizon {prev.shape[0]}, plan horizon is {H}")
+    buf = prev.reshape(1, H, A).contiguous().clone() if has_prev else None
+    obs_t = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.device, non_blocking=True).reshape(1, -1)
+    splits = [mix_split(n) for n, _, _ in sizes]
+    key = (cfg.horizon, H, float(cfg.noise_beta))
+    if getattr(self, "_color_key", None) != key:
+        self._color_mats = torch.from_numpy(color_matrices(cfg.horizon, H, cfg.noise_beta)).to(self.device)
+        self._color_key = key
+    color = {"len": cfg.horizon, "mats": self._color_mats, "n_white": [s[0] for s in splits], "n_color1": [s[1] for s in splits]}
+    res = pl.plan(obs_t, horizon=H, num_samples=cfg.num_samples, num_pi_trajs=sizes[0][2], num_elites=K, iterations=I,
+                  discount=cfg.discount, temperature=cfg.temperature, momentum=cfg.momentum, min_std=cfg.min_std,
+                  std_floor=self.std, init_std=0.5, eval_mode=eval_mode, t0=bool(t0), prev_mean=buf, has_prev=has_prev,
+                  noise=getattr(self, "_inject_noise", None), taps=getattr(self, "_want_taps", False),
+                  n_samples=[s[0] for s in sizes], n_reuse=[s[1] for s in sizes], n_pi=[s[2] for s in sizes],
+                  elite_actions=ebuf, elite_horizon=eh, warm_last=True, best_a_last=True, shift_elites=shift, color=color)
+    self._prev_mean = res["prev_mean"][0]
+    self._elite_actions = ebuf[0].permute(1, 0, 2)                 # [H, K, A] like the reference
+    self._last_taps = res["taps"]
+    m = res["metrics"][0].tolist()
+    plan_metrics.update({"external_reward_mean": m[0], "current_std": m[1]})
+    return res["action"][0], plan_metrics
+
+
 def accelerate(agent, precision="bf16"):
     """Give an existing reference-style agent (attributes cfg, model, std, device) the CUDA `plan`.
     The agent's nn.Module keeps owning the parameters; they are re-packed whenever they change."""
@@ -293,7 +379,8 @@ def accelerate(agent, precision="bf16"):
     sd = agent.model.state_dict()
     agent._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
                              enc_layernorm="_encoder.3.weight" in sd, precision=precision, device=agent.device)
-    agent.plan = types.MethodType(_fast_plan, agent)
+    icem = hasattr(agent, "plan_horizon") and hasattr(cfg, "factor_decrease_num") and not hasattr(agent.model._dynamics, "gru_cell")
+    agent.plan = types.MethodType(_fast_plan_icem if icem else _fast_plan, agent)
     return agent
 
 
@@ -338,3 +425,25 @@ class TDMPC:
     def update(self, replay_buffer, step):
         raise NotImplementedError("training stays in the reference's PyTorch code; use tdmpc_b200.accelerate(agent) "
                                   "on a reference TDMPC to keep update() and gain the CUDA plan()")
+
+
+class TdICemSimMlp(TDMPC):
+    """Planning half of the reference's iCEM agent with MLP dynamics
+    (src/algorithm/tdmpc_icem_similarity_mlp.py:77-265) on the B200 planner."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        dev = getattr(cfg, "device", "cuda")
+        self.device = torch.device(dev if dev != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        self.std = linear_schedule(cfg.std_schedule, 0)
+        self.mixture_coef = linear_schedule(cfg.regularization_schedule, 0)
+        self.model = DSSM(cfg).to(self.device)
+        self.model_target = deepcopy(self.model)
+        self.model.eval()
+        self.model_target.eval()
+        self.plan_horizon = 1
+        self._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
+                                enc_layernorm=bool(cfg.normalize), precision=getattr(cfg, "precision", "bf16"),
+                                device=self.device)
+
+    plan = _fast_plan_icem

@@ -91,3 +91,36 @@ class TOLD(nn.Module):
     def Q(self, z, a):
         x = torch.cat([z, a], dim=-1)
         return self._Q1(x), self._Q2(x)
+
+
+class DSSM(TOLD):
+    """Model of the iCEM agents (src/algorithm/tdmpc_icem_similarity_mlp.py:14-74): TOLD plus a `_predictor`
+    head (training only) and, when cfg.normalize, the LayerNorm state encoder (helper.dmlab_enc_norm).
+    Same state_dict keys as the reference."""
+
+    def __init__(self, cfg):
+        nn.Module.__init__(self)
+        self.cfg = cfg
+        L, A, M, E, D = cfg.latent_dim, cfg.action_dim, cfg.mlp_dim, cfg.enc_dim, cfg.obs_shape[0]
+        if getattr(cfg, "modality", "state") != "state":
+            raise NotImplementedError("tdmpc_b200 covers the state-observation encoder only")
+        self._dynamics = _mlp(L + A, M, L)
+        self._reward = _mlp(L + A, M, 1)
+        self._pi = _mlp(L, M, A)
+        self._Q1, self._Q2 = _q(L + A, M), _q(L + A, M)
+        if cfg.normalize:
+            self._encoder = nn.Sequential(nn.Linear(D, E), nn.LayerNorm(E), nn.ELU(), nn.Linear(E, L))
+            self._predictor = nn.Sequential(nn.Linear(L, M), nn.BatchNorm1d(M), nn.ELU(), nn.Linear(M, L))
+        else:
+            self._encoder = nn.Sequential(nn.Linear(D, E), nn.ELU(), nn.Linear(E, L))
+            self._predictor = _mlp(L, M, L)
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
+                nn.init.orthogonal_(mod.weight.data)
+                nn.init.zeros_(mod.bias)
+        for mod in (self._reward, self._Q1, self._Q2):
+            mod[-1].weight.data.fill_(0)
+            mod[-1].bias.data.fill_(0)
+
+    def pred_z(self, z):
+        return self._predictor(z)

@@ -131,6 +131,178 @@ def run_case(name, cfg_name, steps=3, eval_mode=True, seed=0, std_floor=None, **
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def run_icem_case(name, cfg_name, steps=3, seed=0):
+    """TdICemSimMlp.plan (tdmpc_icem_similarity_mlp.py:159-265), the unmodified reference class."""
+    import colorednoise
+    from src.algorithm.tdmpc_icem_similarity_mlp import TdICemSimMlp
+    import src.algorithm.helper as ref_h2          # the iCEM file imports helper under this name
+    cfg = synth.make_cfg(cfg_name)
+    torch.manual_seed(0)
+    agent = TdICemSimMlp(cfg)
+    agent.device = torch.device("cpu")
+    sd = synth.make_told_weights(cfg, seed, enc_ln=bool(cfg.normalize))
+    missing = agent.model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("_predictor") for k in missing.missing_keys) and not missing.unexpected_keys
+    agent.std = cfg.min_std
+    step = 10 ** 6
+    out = {}
+    state = {"plan_horizon": 1, "std": agent.std}
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        t0 = s == 0
+        horizon = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, step)))
+        H = horizon if t0 else agent.plan_horizon
+        mix = O.linear_schedule(cfg.regularization_schedule, step)
+        have = hasattr(agent, "_elite_actions")
+        sizes = O.icem_sizes(cfg, mix, have)
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have)
+        inj = Injector()
+        for t in range(H):
+            inj.stdn_q.append(nz["pi"][t])
+        colored_q = []
+        for i in range(cfg.iterations):
+            inj.randn_q.append(nz["white"][i])
+            colored_q += [nz["pink"][i], nz["brown"][i]]
+            if i == 0 and "shift_raw" in nz:
+                colored_q.append(nz["shift_raw"])
+            inj.stdn_q.append(nz["term"][i])
+        inj.randn_q.append(nz["out"])
+        inj.u = nz["u"]
+
+        def fake_powerlaw(exponent, size, **kw):
+            x = colored_q.pop(0)
+            assert tuple(x.shape) == tuple(size), (x.shape, size)
+            return x.copy()
+
+        real_pl = colorednoise.powerlaw_psd_gaussian
+        colorednoise.powerlaw_psd_gaussian = fake_powerlaw
+        ev = agent.estimate_value
+
+        def ev_logged(z, actions, _ev=ev, _inj=inj):
+            v, r = _ev(z, actions)
+            _inj.value_log.append(v.squeeze(1).clone())
+            return v, r
+
+        agent.estimate_value = ev_logged
+        ref_std = ref_h2._standard_normal
+        with inj:
+            ref_h2._standard_normal = ref_h._standard_normal      # same patched queue for both import names
+            a, metrics = agent.plan(obs, eval_mode=True, step=step, t0=t0)
+        ref_h2._standard_normal = ref_std
+        agent.estimate_value = ev
+        colorednoise.powerlaw_psd_gaussian = real_pl
+        assert not colored_q and not inj.stdn_q
+        Tm = max(v.shape[0] for v in inj.value_log)
+        vals = np.zeros((cfg.iterations, Tm), dtype=np.float32)
+        for i, v in enumerate(inj.value_log):
+            vals[i, :v.shape[0]] = v.numpy()
+        out[f"s{s}_action"] = a.numpy().copy()
+        out[f"s{s}_prev_mean"] = agent._prev_mean.numpy().copy()
+        out[f"s{s}_values"] = vals
+        out[f"s{s}_elite_idx"] = torch.stack(inj.topk_log).numpy().astype(np.int32)
+        out[f"s{s}_elite_actions"] = agent._elite_actions.numpy().copy()
+        out[f"s{s}_sizes"] = np.array(sizes, dtype=np.int32)
+        out[f"s{s}_metrics"] = np.array([metrics["external_reward_mean"], metrics["current_std"]], dtype=np.float64)
+
+        a_o, m_o, taps = O.plan_icem_mlp(sd, cfg, obs, eval_mode=True, step=step, t0=t0, state=state, noise=nz)
+        dv = max((taps["values"][i] - inj.value_log[i]).abs().max().item() for i in range(cfg.iterations))
+        da = (a_o - a).abs().max().item()
+        dm = (state["_prev_mean"] - agent._prev_mean).abs().max().item()
+        de = (state["_elite_actions"] - agent._elite_actions).abs().max().item()
+        print(f"[{name}] step {s}: sizes {sizes[0]}..{sizes[-1]} |dvalue|={dv:.3e} |daction|={da:.3e} |dmean|={dm:.3e} |delite|={de:.3e}")
+        assert dv < 1e-5 and da < 1e-5 and dm < 1e-5 and de < 1e-5
+    out["meta"] = np.array([seed, steps, 1], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
+def run_drnn_case(name, cfg_name, steps=3, seed=0):
+    """TdICemSimDssm.plan (tdmpc_icem_similarity_drnn.py:168-272), the unmodified reference class
+    (NormGRUCell + BatchNorm prior MLP dynamics, reward from the hidden state)."""
+    import colorednoise
+    from src.algorithm.tdmpc_icem_similarity_drnn import TdICemSimDssm
+    import src.algorithm.helper as ref_h2
+    cfg = synth.make_cfg(cfg_name)
+    torch.manual_seed(0)
+    agent = TdICemSimDssm(cfg)
+    agent.device = torch.device("cpu")
+    sd = synth.make_drnn_weights(cfg, seed)
+    missing = agent.model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("_predictor") or k.endswith("num_batches_tracked") for k in missing.missing_keys) and not missing.unexpected_keys, missing
+    agent.model.eval()
+    agent.std = cfg.min_std
+    step = 10 ** 6
+    out = {}
+    state = {"plan_horizon": 1, "std": agent.std}
+    hidden = torch.zeros(1, cfg.hidden_dim)
+    hidden_o = hidden.clone()
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        t0 = s == 0
+        horizon = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, step)))
+        H = horizon if t0 else agent.plan_horizon
+        mix = O.linear_schedule(cfg.regularization_schedule, step)
+        have = hasattr(agent, "_elite_actions")
+        sizes = O.icem_drnn_sizes(cfg, mix, have, t0)
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have and not t0, single_beta=True)
+        inj = Injector()
+        for t in range(H):
+            inj.stdn_q.append(nz["pi"][t])
+        colored_q = []
+        for i in range(cfg.iterations):
+            colored_q.append(nz["pink"][i])
+            if i == 0 and "shift_raw" in nz:
+                colored_q.append(nz["shift_raw"])
+            inj.stdn_q.append(nz["term"][i])
+        inj.randn_q.append(nz["out"])
+        inj.u = nz["u"]
+
+        def fake_powerlaw(exponent, size, **kw):
+            x = colored_q.pop(0)
+            assert tuple(x.shape) == tuple(size), (x.shape, size)
+            return x.copy()
+
+        real_pl = colorednoise.powerlaw_psd_gaussian
+        colorednoise.powerlaw_psd_gaussian = fake_powerlaw
+        ev = agent.estimate_value
+
+        def ev_logged(z, actions, hid, _ev=ev, _inj=inj):
+            v, r = _ev(z, actions, hid)
+            _inj.value_log.append(v.squeeze(1).clone())
+            return v, r
+
+        agent.estimate_value = ev_logged
+        ref_std = ref_h2._standard_normal
+        with inj:
+            ref_h2._standard_normal = ref_h._standard_normal
+            a, hidden, metrics = agent.plan(obs, hidden, eval_mode=True, step=step, t0=t0)
+        ref_h2._standard_normal = ref_std
+        agent.estimate_value = ev
+        colorednoise.powerlaw_psd_gaussian = real_pl
+        assert not colored_q and not inj.stdn_q
+        Tm = max(v.shape[0] for v in inj.value_log)
+        vals = np.zeros((cfg.iterations, Tm), dtype=np.float32)
+        for i, v in enumerate(inj.value_log):
+            vals[i, :v.shape[0]] = v.numpy()
+        out[f"s{s}_action"] = a.numpy().copy()
+        out[f"s{s}_hidden"] = hidden.numpy().copy()
+        out[f"s{s}_prev_mean"] = agent._prev_mean.numpy().copy()
+        out[f"s{s}_values"] = vals
+        out[f"s{s}_elite_idx"] = torch.stack(inj.topk_log).numpy().astype(np.int32)
+        out[f"s{s}_elite_actions"] = agent._elite_actions.numpy().copy()
+        out[f"s{s}_sizes"] = np.array(sizes, dtype=np.int32)
+        out[f"s{s}_metrics"] = np.array([metrics["external_reward_mean"], metrics["current_std"]], dtype=np.float64)
+
+        a_o, hidden_o, m_o, taps = O.plan_icem_drnn(sd, cfg, obs, hidden_o, eval_mode=True, step=step, t0=t0, state=state, noise=nz)
+        dv = max((taps["values"][i] - inj.value_log[i]).abs().max().item() for i in range(cfg.iterations))
+        da = (a_o - a).abs().max().item()
+        dh = (hidden_o - hidden).abs().max().item()
+        dm = (state["_prev_mean"] - agent._prev_mean).abs().max().item()
+        print(f"[{name}] step {s}: sizes {sizes[0]}..{sizes[-1]} |dvalue|={dv:.3e} |daction|={da:.3e} |dhidden|={dh:.3e} |dmean|={dm:.3e}")
+        assert dv < 1e-5 and da < 1e-5 and dm < 1e-5 and dh < 1e-5
+    out["meta"] = np.array([seed, steps, 1], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
 if __name__ == "__main__":
     check_choice_replica()
     run_case("tdmpc_tiny", "tiny", steps=3)
@@ -138,4 +310,8 @@ if __name__ == "__main__":
     run_case("tdmpc_cfg1", "cfg1", steps=3)
     run_case("tdmpc_cfg3", "cfg3", steps=2, seed=1)
     run_case("tdmpc_cfg2s", "cfg2s", steps=2, seed=2)
+    run_icem_case("icem_tiny", "tiny_icem", steps=3, seed=4)
+    run_icem_case("icem_cfg4", "cfg4", steps=2, seed=5)
+    run_drnn_case("drnn_tiny", "tiny_drnn", steps=3, seed=6)
+    run_drnn_case("drnn_cfg5", "cfg5", steps=2, seed=7)
     print("golden fixtures written to", HERE)

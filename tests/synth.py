@@ -23,7 +23,7 @@ def make_cfg(name="cfg1", **over):
         regularization_schedule="linear(0.05, 0.5, 1, 5000)", lr=1e-3,
         factor_decrease_num=1.25, shift_elites_over_time=True, fraction_elites_reused=0.25,
         keep_previous_elites=True, noise_beta=2.5, normalize=False, norm_type="ln", norm_cell=True,
-        img_size=84, frame_stack=1, num_channels=32,
+        img_size=84, frame_stack=1, num_channels=32, train_steps=500000, episode_length=1000, optim_id="adamw", pi_lr=1e-3,
     )
     dims = {
         "cfg1": dict(obs_shape=(5,), action_dim=1),                       # cartpole-swingup
@@ -34,6 +34,12 @@ def make_cfg(name="cfg1", **over):
                      mixture_coef=0.5, horizon_schedule="linear(2, 10, 25000, 0)", normalize=True),
         "tiny": dict(obs_shape=(7,), action_dim=3, latent_dim=24, horizon=3, num_samples=96,
                      num_elites=16, iterations=3, mixture_coef=0.25, horizon_schedule="3"),
+        "tiny_drnn": dict(obs_shape=(7,), action_dim=3, latent_dim=24, horizon=4, num_samples=120, hidden_dim=128,
+                          num_elites=16, iterations=3, mixture_coef=0.5, horizon_schedule="4", normalize=True),
+        "cfg5": dict(obs_shape=(18,), action_dim=4, horizon=10, num_samples=1024, num_elites=32, hidden_dim=128,
+                     mixture_coef=0.5, horizon_schedule="linear(2, 10, 25000, 0)", normalize=True),
+        "tiny_icem": dict(obs_shape=(7,), action_dim=3, latent_dim=24, horizon=4, num_samples=120,
+                          num_elites=16, iterations=3, mixture_coef=0.5, horizon_schedule="4", normalize=True),
     }[name]
     base.update(dims)
     base.update(over)
@@ -63,6 +69,42 @@ def make_told_weights(cfg, seed=0, enc_ln=False):
     for name, out in (("_dynamics", L), ("_reward", 1), ("_pi", A)):
         inp = L if name == "_pi" else L + A
         lin(name + ".0", M, inp, gain=1.4); lin(name + ".2", M, M, gain=1.4); lin(name + ".4", out, M)
+    for name in ("_Q1", "_Q2"):
+        lin(name + ".0", M, L + A); ln(name + ".1", M)
+        lin(name + ".3", M, M); ln(name + ".4", M)
+        lin(name + ".6", 1, M, gain=2.0)
+    return sd
+
+
+def make_drnn_weights(cfg, seed=0):
+    """Random DSSM (GRU latent dynamics) parameters keyed like the reference state_dict
+    (tdmpc_icem_similarity_drnn.py:14-36, models/gru_dyna.py:11-23, models/rnns.py:8-17).  LayerNorm / BatchNorm
+    affine parameters and running statistics are perturbed so folding bugs show."""
+    rs = np.random.RandomState(7000 + seed)
+    D, A, L, M, E, Hd = cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, cfg.hidden_dim
+    sd = {}
+
+    def lin(key, out, inp, gain=1.0, bias=True, bias_std=0.05):
+        sd[key + ".weight"] = _t(rs.standard_normal((out, inp)) * (gain / np.sqrt(inp)))
+        if bias:
+            sd[key + ".bias"] = _t(rs.standard_normal(out) * bias_std)
+
+    def ln(key, n):
+        sd[key + ".weight"] = _t(1.0 + 0.1 * rs.standard_normal(n))
+        sd[key + ".bias"] = _t(0.1 * rs.standard_normal(n))
+
+    lin("_encoder.0", E, D); ln("_encoder.1", E); lin("_encoder.3", L, E)
+    lin("_dynamics.gru_cell.weight_ih", 3 * Hd, L + A, bias=False)
+    lin("_dynamics.gru_cell.weight_hh", 3 * Hd, Hd, bias=False)
+    for g in ("reset", "update", "newval"):
+        ln(f"_dynamics.gru_cell.ln_{g}", Hd)
+    lin("_dynamics.prior_mlp.0", M, Hd, gain=1.2)
+    ln("_dynamics.prior_mlp.1", M)
+    sd["_dynamics.prior_mlp.1.running_mean"] = _t(0.2 * rs.standard_normal(M))
+    sd["_dynamics.prior_mlp.1.running_var"] = _t(np.exp(0.3 * rs.standard_normal(M)))
+    lin("_dynamics.prior_mlp.3", L, M)
+    lin("_reward.0", M, Hd, gain=1.4); lin("_reward.2", M, M, gain=1.4); lin("_reward.4", 1, M)
+    lin("_pi.0", M, L, gain=1.4); lin("_pi.2", M, M, gain=1.4); lin("_pi.4", A, M)
     for name in ("_Q1", "_Q2"):
         lin(name + ".0", M, L + A); ln(name + ".1", M)
         lin(name + ".3", M, M); ln(name + ".4", M)
@@ -100,3 +142,53 @@ def make_noise(cfg, seed=0, step=10 ** 6, batch=None):
     u = rs.random_sample(lead if lead else None)
     n["u"] = float(u) if batch is None else np.asarray(u, dtype=np.float64)
     return n
+
+
+def make_icem_noise(cfg, seed, sizes, H, have_elites, single_beta=False):
+    """Draws of one TdICemSimMlp.plan call in consumption order (tdmpc_icem_similarity_mlp.py:139-157,
+    188-239): per iteration white randn + two colored blocks (series of length cfg.horizon, truncated to
+    the plan horizon), the tail noise of the shifted elites, policy / terminal draws, pick, output noise.
+    Returns the raw pieces (for injecting into the reference) and the assembled unit noise (oracle / ABI)."""
+    from oracle.colored_noise import powerlaw_psd_gaussian
+    from tdmpc_b200.colored import mix_split
+    rs = np.random.RandomState(3000 + seed)
+    A = cfg.action_dim
+    P0 = sizes[0][2]
+    n = {"pi": _t(rs.standard_normal((H, P0, A))), "white": [], "pink": [], "brown": [], "cem": [], "term": []}
+    for (N, E, P) in sizes:
+        if single_beta:      # DRNN agent: sample_action_sequence, one beta, series of length plan horizon
+            c = powerlaw_psd_gaussian(cfg.noise_beta, (N, A, H), random_state=rs)
+            n["pink"].append(c)
+            n["cem"].append(torch.from_numpy(c).float().permute(2, 0, 1))
+        else:
+            nw, npk, nb = mix_split(N)
+            w = _t(rs.standard_normal((H, nw, A)))
+            pk = powerlaw_psd_gaussian(1.0, (npk, A, cfg.horizon), random_state=rs)
+            br = powerlaw_psd_gaussian(2.5, (nb, A, cfg.horizon), random_state=rs)
+            n["white"].append(w); n["pink"].append(pk); n["brown"].append(br)
+            n["cem"].append(torch.cat([w, torch.from_numpy(pk).float().permute(2, 0, 1)[:H],
+                                       torch.from_numpy(br).float().permute(2, 0, 1)[:H]], dim=1))
+        n["term"].append(_t(rs.standard_normal((N + E + P, A))))
+    E0 = sizes[0][1]
+    if have_elites and E0 > 0:
+        sh = powerlaw_psd_gaussian(cfg.noise_beta, (E0, A, H), random_state=rs) if cfg.noise_beta > 0 else rs.standard_normal((E0, A, H))
+        n["shift_raw"] = sh
+        n["shift"] = torch.from_numpy(sh).float().permute(2, 0, 1)
+    n["out"] = _t(rs.standard_normal(A))
+    n["seed_uniform"] = _t(rs.uniform(-1, 1, A))
+    n["u"] = float(rs.random_sample())
+    return n
+
+
+def icem_noise_abi(n, sizes, H, A):
+    """Pack make_icem_noise output into the C-ABI layouts (B = 1): cem [1,I,H,Nmax,A], term [1,I,Tmax,A] ..."""
+    I = len(sizes)
+    Nmax = max(s[0] for s in sizes); Tmax = max(sum(s) for s in sizes)
+    cem = torch.zeros(1, I, H, Nmax, A); term = torch.zeros(1, I, Tmax, A)
+    for i, (N, E, P) in enumerate(sizes):
+        cem[0, i, :, :N] = n["cem"][i]
+        term[0, i, :N + E + P] = n["term"][i]
+    out = {"pi": n["pi"].unsqueeze(0), "cem": cem, "term": term, "out": n["out"].unsqueeze(0), "u": np.array([n["u"]])}
+    if "shift" in n:
+        out["shift"] = n["shift"].unsqueeze(0).contiguous()
+    return out

@@ -422,3 +422,128 @@ def test_dropin_agent_surface():
     a, m = agent.plan(obs, eval_mode=True, step=10 ** 6, t0=True)
     _, m_o, _, _ = gu.oracle_plan(sd2, cfg, obs, nz, t0=True, prev_mean=None)
     assert abs(m["external_reward_mean"] - m_o["external_reward_mean"]) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------- iCEM
+def _icem_agent(cfg, sd, precision):
+    from tdmpc_b200 import TdICemSimMlp
+    cfg.device, cfg.precision = "cuda", precision
+    agent = TdICemSimMlp(cfg)
+    missing = agent.model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("_predictor") for k in missing.missing_keys)
+    agent.std = cfg.min_std
+    return agent
+
+
+@pytest.mark.parametrize("name,cfg_name", [("icem_tiny", "tiny_icem"), ("icem_cfg4", "cfg4")])
+def test_icem_fp32_matches_oracle_and_reference_golden(golden_dir, name, cfg_name):
+    """TdICemSimMlp drop-in (fp32 mode), multi-step: sample decay, shifted + carried elites, best-a, repeated-last
+    warm start, LayerNorm encoder -- against the oracle and the real reference's outputs."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, steps, _ = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed, enc_ln=True)
+    agent = _icem_agent(cfg, sd, "fp32")
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    K, A = cfg.num_elites, cfg.action_dim
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_sizes(cfg, O.linear_schedule(cfg.regularization_schedule, 10 ** 6), have)
+        H = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, 10 ** 6)))
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have)
+        a_o, m_o, taps_o = O.plan_icem_mlp(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(s == 0), state=state, noise=nz)
+        agent._inject_noise = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.icem_noise_abi(nz, sizes, H, A).items()}
+        agent._want_taps = True
+        a, m = agent.plan(obs, eval_mode=True, step=10 ** 6, t0=(s == 0))
+        torch.cuda.synchronize()
+        taps = agent._last_taps
+        scale = max(v.abs().max().item() for v in taps_o["values"])
+        ok = True
+        for i in range(cfg.iterations):
+            v_o = taps_o["values"][i]
+            v_g = taps["values"][i, 0, :v_o.shape[0]].cpu()
+            assert (v_g - v_o).abs().max().item() <= TOL_FP32 * scale, (s, i)
+            ref_v = g[f"s{s}_values"][i, :v_o.shape[0]]
+            assert np.abs(v_g.numpy() - ref_v).max() <= 2e-5 * scale, (s, i)
+            if taps["elite_idx"][i, 0].cpu().tolist() != taps_o["elite_idx"][i].tolist():
+                srt = np.sort(v_o.numpy())[::-1]
+                assert srt[K - 1] - srt[K] <= 1e-4 * scale      # only an unresolvable tie may differ
+                ok = False
+                break
+        assert ok, "elite lists diverged"
+        np.testing.assert_allclose(agent._prev_mean.cpu().numpy(), g[f"s{s}_prev_mean"], atol=1e-4)
+        np.testing.assert_allclose(agent._elite_actions.cpu().numpy(), g[f"s{s}_elite_actions"], atol=1e-4)
+        np.testing.assert_allclose(a.cpu().numpy(), g[f"s{s}_action"], atol=1e-4)
+        assert abs(m["external_reward_mean"] - g[f"s{s}_metrics"][0]) <= 1e-3 and abs(m["current_std"] - g[f"s{s}_metrics"][1]) <= 1e-4
+        assert agent.plan_horizon == H and abs(agent.mixture_coef - 0.5) < 1e-12
+
+
+def test_icem_bf16_first_iteration_and_sanity():
+    cfg = synth.make_cfg("cfg4")
+    sd = synth.make_told_weights(cfg, 5, enc_ln=True)
+    agent = _icem_agent(cfg, sd, "bf16")
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    for s in range(2):
+        obs = synth.make_obs(cfg, 500 + s)
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_sizes(cfg, 0.5, have)
+        nz = synth.make_icem_noise(cfg, 500 + s, sizes, cfg.horizon, have)
+        # teacher-force the carried state so both sides see the same inputs at every step
+        if have:
+            agent._elite_actions = state["_elite_actions"].cuda()
+            agent._prev_mean = state["_prev_mean"].cuda()
+        a_o, m_o, taps_o = O.plan_icem_mlp(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(s == 0), state=state, noise=nz, quant=True)
+        agent._inject_noise = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.icem_noise_abi(nz, sizes, cfg.horizon, cfg.action_dim).items()}
+        agent._want_taps = True
+        a, m = agent.plan(obs, eval_mode=True, step=10 ** 6, t0=(s == 0))
+        torch.cuda.synchronize()
+        v_o = taps_o["values"][0]
+        v_g = agent._last_taps["values"][0, 0, :v_o.shape[0]].cpu()
+        err = (v_g - v_o).abs() / v_o.abs().max()
+        ov = len(set(taps_o["elite_idx"][0].tolist()) & set(agent._last_taps["elite_idx"][0, 0].cpu().tolist()))
+        print(f"icem bf16 step {s}: it0 value err median {err.median().item():.2e} max {err.max().item():.2e}, elite overlap {ov}/{cfg.num_elites}")
+        assert err.median().item() <= TOL_BF16 and ov >= int(0.85 * cfg.num_elites)
+        assert torch.isfinite(a).all() and a.abs().max() <= 1.0
+
+
+def test_icem_builtin_colored_sampler_statistics():
+    """The built-in (Philox) iCEM sampler: action noise classes are white / pink / brown along the horizon with the
+    covariance of the synthesis matrices (colorednoise restated), independent across trajectories."""
+    from tdmpc_b200.colored import synthesis_matrix, mix_split
+    cfg = synth.make_cfg("cfg4", num_samples=3000, iterations=1, num_elites=256, mixture_coef=0.02)   # K > P: elites include sampled rows of every class
+    sd = synth.make_told_weights(cfg, 1, enc_ln=True)
+    agent = _icem_agent(cfg, sd, "fp32")
+    agent.std = 0.05
+    obs = synth.make_obs(cfg, 0)
+    # iteration 0 samples clamp(0 + 0.5 * noise): recover the noise from the action rows of the elites buffer is
+    # not possible, so read the sampled rows through the taps of a 1-iteration plan: values are irrelevant here.
+    pl = agent._planner
+    pl.sync_weights(agent.model)
+    H, A, N = cfg.horizon, cfg.action_dim, cfg.num_samples
+    from tdmpc_b200.colored import color_matrices
+    mats = torch.from_numpy(color_matrices(cfg.horizon, H, cfg.noise_beta)).cuda()
+    nw, npk, nb = mix_split(N)
+    P = int(0.02 * N)
+    ebuf = torch.zeros(1, cfg.num_elites, H, A, device="cuda")
+    res = pl.plan(torch.from_numpy(obs).cuda().unsqueeze(0), horizon=H, num_samples=N, num_pi_trajs=P, num_elites=cfg.num_elites,
+                  iterations=1, discount=0.99, temperature=0.5, momentum=0.1, min_std=0.05, std_floor=0.05, init_std=0.1,
+                  eval_mode=True, t0=True, n_samples=[N], n_reuse=[0], n_pi=[P], elite_actions=ebuf, seed=7, call=3,
+                  color={"len": cfg.horizon, "mats": mats, "n_white": [nw], "n_color1": [npk]}, taps=True)
+    torch.cuda.synchronize()
+    # the planner's scratch is private; re-derive the sampled noise from the Philox stream instead and check the
+    # device coloring against S @ white on the host for the elite rows (their actions = clamp(0.1 * noise))
+    white = pl.fill_noise(1, cfg.horizon * N * A, 7, 3).view(cfg.horizon, N, A).cpu().double().numpy()
+    idx = res["taps"]["elite_idx"][0, 0].cpu().numpy()
+    elites = ebuf[0].cpu().double().numpy()                      # [K, H, A] sorted like idx
+    S1, S2 = synthesis_matrix(1.0, cfg.horizon), synthesis_matrix(2.5, cfg.horizon)
+    checked = 0
+    for k, n in enumerate(idx):
+        if n >= N:
+            continue                                              # a policy trajectory
+        w = white[:, n, :]                                        # [Hc, A]
+        col = w if n < nw else (S1 @ w if n < nw + npk else S2 @ w)
+        expect = np.clip(0.1 * col[:H], -1, 1)
+        np.testing.assert_allclose(elites[k], expect, atol=2e-6)
+        checked += 1
+    assert checked >= 150 and (idx[idx < N] >= nw).any() and (idx[idx < N] >= nw + npk).any()

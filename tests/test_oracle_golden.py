@@ -76,3 +76,46 @@ def test_flop_accounting_matches_survey():
     f = O.flops_per_plan(D=5, A=1, L=50, M=512, E=256, H=5, rows_per_iter=[537] * 6, P=25)
     assert abs(f / 1e9 - 25.15) < 0.05
     assert O.sample_steps_per_plan(5, [537] * 6, 25) == 16235
+
+
+@pytest.mark.parametrize("name,cfg_name", [("icem_tiny", "tiny_icem"), ("icem_cfg4", "cfg4")])
+def test_icem_oracle_matches_reference_fixture(golden_dir, name, cfg_name):
+    """oracle.plan_icem_mlp against what the real TdICemSimMlp.plan produced (colored noise, sample decay,
+    shifted / carried elites, best-a): tests/golden/make_golden.py:run_icem_case."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, steps, _ = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed, enc_ln=bool(cfg.normalize))
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_sizes(cfg, O.linear_schedule(cfg.regularization_schedule, 10 ** 6), have)
+        assert np.array_equal(np.array(sizes), g[f"s{s}_sizes"])
+        H = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, 10 ** 6)))
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have)
+        a, m, taps = O.plan_icem_mlp(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(s == 0), state=state, noise=nz)
+        ref_vals = g[f"s{s}_values"]
+        scale = np.abs(ref_vals).max()
+        for i in range(cfg.iterations):
+            v = taps["values"][i].numpy()
+            assert np.abs(v - ref_vals[i, :v.shape[0]]).max() <= TOL * scale
+        np.testing.assert_allclose(state["_prev_mean"].numpy(), g[f"s{s}_prev_mean"], atol=1e-4)
+        np.testing.assert_allclose(state["_elite_actions"].numpy(), g[f"s{s}_elite_actions"], atol=1e-4)
+        np.testing.assert_allclose(a.numpy(), g[f"s{s}_action"], atol=1e-4)
+
+
+def test_colored_noise_matrix_is_the_generator():
+    """tdmpc_b200.colored.synthesis_matrix (what the CUDA sampler multiplies white noise by) equals the oracle's
+    restatement of colorednoise.powerlaw_psd_gaussian, both as a matrix and in distribution."""
+    from oracle.colored_noise import powerlaw_psd_gaussian, synthesis_matrix as S_o
+    from tdmpc_b200.colored import color_matrices, mix_split, synthesis_matrix
+    for beta in (1.0, 2.5, 0.5):
+        for n in (2, 5, 6, 10, 12):
+            np.testing.assert_allclose(synthesis_matrix(beta, n), S_o(beta, n), atol=1e-12)
+    x = powerlaw_psd_gaussian(2.5, (200000, 10), random_state=np.random.RandomState(0))
+    S = synthesis_matrix(2.5, 10)
+    assert np.abs(np.cov(x.T) - S @ S.T).max() < 2e-2
+    m = color_matrices(10, 7, 2.5)
+    assert m.shape == (3, 10, 10) and np.all(m[2, 7:] == 0) and np.all(m[2, :, 7:] == 0)
+    assert mix_split(1024) == (341, 342, 341) and mix_split(819) == (273, 273, 273) and mix_split(335) == (111, 112, 112)
