@@ -86,6 +86,15 @@ typedef struct {
   const float* q_b[2][3];
   const float* q_ln_g[2][2];  /* _Q{1,2}.{1,4}.weight [M]                                          */
   const float* q_ln_b[2][2];
+  /* TDMPC_DYN_DRNN only (tdmpc_icem_similarity_drnn.py:14-36, models/gru_dyna.py:11-23, models/rnns.py:8-17).
+   * dyn_w / dyn_b are unused; rew_w[0] is [M, hidden_dim] (the reward reads the GRU state). */
+  const float* gru_w_ih;      /* _dynamics.gru_cell.weight_ih.weight [3*Hd, L+A] (no bias); chunks reset, update, newval */
+  const float* gru_w_hh;      /* _dynamics.gru_cell.weight_hh.weight [3*Hd, Hd]  (no bias)         */
+  const float* gru_ln_g[3];   /* _dynamics.gru_cell.ln_{reset,update,newval}.weight [Hd] (eps 1e-3) */
+  const float* gru_ln_b[3];
+  const float* prior_w[2];    /* _dynamics.prior_mlp.{0,3}.weight [M,Hd] [L,M]                     */
+  const float* prior_b[2];
+  const float* prior_bn[4];   /* _dynamics.prior_mlp.1.{weight, bias, running_mean, running_var} [M] (BatchNorm1d, eval) */
 } tdmpc_weights;
 
 /* One call of TDMPC.plan (algorithm/tdmpc.py:94-163) for `batch` independent problems. */
@@ -131,6 +140,8 @@ typedef struct {
   const uint8_t* t0;        /* device [B] or NULL (t0_all != -1)                                  */
   float* prev_mean;         /* device [B, H, A] in/out: agent._prev_mean (tdmpc.py:125,154)       */
   float* elite_actions;     /* device [B, K, H, A] in/out or NULL: iCEM agent._elite_actions      */
+  const float* hidden;      /* DRNN: device [B, hidden_dim] GRU state in (NULL = zeros)  tdmpc_icem_similarity_drnn.py:168 */
+  float* hidden_out;        /* DRNN: device [B, hidden_dim] state after stepping the model with the returned action (:267) */
 
   /* randomness: either injected draws (parity tests; consumption order = SURVEY Appendix B)
    * or, where a pointer is NULL, the built-in Philox4x32-10 stream keyed by (seed, call).        */
@@ -205,6 +216,11 @@ TDMPC_API int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed
 
 /* Number of kernels of THIS library launched by the handle so far (bench.py's gpu_launches). */
 TDMPC_API uint64_t tdmpc_launch_count(const tdmpc_handle* h);
+
+/* Layout self-check for FFI bindings: writes up to n of {sizeof(tdmpc_model_cfg), sizeof(tdmpc_weights),
+ * sizeof(tdmpc_plan_args), offsetof(plan_args, obs), offsetof(.., seed), offsetof(.., action), offsetof(.., tap_z0)}
+ * and returns how many values exist. */
+TDMPC_API int32_t tdmpc_abi_sizes(int32_t* out, int32_t n);
 
 /* Build information: "sm_100a;tcgen05=1;..." */
 TDMPC_API const char* tdmpc_build_info(void);

@@ -18,7 +18,7 @@ DYN_MLP, DYN_DRNN = 0, 1
 EXPORTS = [
     "tdmpc_create", "tdmpc_destroy", "tdmpc_last_error", "tdmpc_reserve", "tdmpc_set_weights",
     "tdmpc_encode", "tdmpc_estimate_value", "tdmpc_pi_rollout", "tdmpc_select_update", "tdmpc_plan",
-    "tdmpc_fill_noise", "tdmpc_launch_count", "tdmpc_build_info",
+    "tdmpc_fill_noise", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes",
 ]
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -36,6 +36,8 @@ class Weights(C.Structure):
         ("dyn_w", _fp * 3), ("dyn_b", _fp * 3), ("rew_w", _fp * 3), ("rew_b", _fp * 3),
         ("pi_w", _fp * 3), ("pi_b", _fp * 3),
         ("q_w", (_fp * 3) * 2), ("q_b", (_fp * 3) * 2), ("q_ln_g", (_fp * 2) * 2), ("q_ln_b", (_fp * 2) * 2),
+        ("gru_w_ih", _fp), ("gru_w_hh", _fp), ("gru_ln_g", _fp * 3), ("gru_ln_b", _fp * 3),
+        ("prior_w", _fp * 2), ("prior_b", _fp * 2), ("prior_bn", _fp * 4),
     ]
 
 
@@ -53,6 +55,7 @@ class PlanArgs(C.Structure):
         ("color_len", C.c_int32), ("color_mats", _fp),
         ("n_white", C.c_int32 * TDMPC_MAX_ITERS), ("n_color1", C.c_int32 * TDMPC_MAX_ITERS),
         ("obs", _fp), ("z0", _fp), ("t0", _fp), ("prev_mean", _fp), ("elite_actions", _fp),
+        ("hidden", _fp), ("hidden_out", _fp),
         ("seed", C.c_uint64), ("call", C.c_uint64),
         ("noise_pi", _fp), ("noise_cem", _fp), ("noise_term", _fp), ("noise_out", _fp), ("noise_shift", _fp), ("u_pick", _fp),
         ("action", _fp), ("metrics", _fp),
@@ -98,8 +101,15 @@ def load():
     lib.tdmpc_fill_noise.argtypes = [H, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, _fp, C.c_void_p]
     lib.tdmpc_launch_count.argtypes = [H]; lib.tdmpc_launch_count.restype = C.c_uint64
     lib.tdmpc_build_info.argtypes = []; lib.tdmpc_build_info.restype = C.c_char_p
+    lib.tdmpc_abi_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]; lib.tdmpc_abi_sizes.restype = C.c_int32
+    got = (C.c_int32 * 7)()
+    lib.tdmpc_abi_sizes(got, 7)
+    want = [C.sizeof(ModelCfg), C.sizeof(Weights), C.sizeof(PlanArgs), PlanArgs.obs.offset, PlanArgs.seed.offset,
+            PlanArgs.action.offset, PlanArgs.tap_z0.offset]
+    if list(got) != want:
+        raise RuntimeError(f"libtdmpc_b200.so ABI mismatch: library {list(got)} vs binding {want} (stale build?)")
     for name in EXPORTS:
-        if name not in ("tdmpc_last_error", "tdmpc_launch_count", "tdmpc_build_info"):
+        if name not in ("tdmpc_last_error", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

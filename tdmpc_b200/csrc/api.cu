@@ -1,6 +1,7 @@
 // C-ABI entry points of libtdmpc_b200.so (declared in include/tdmpc_b200.h): handle management,
 // weight packing, scratch reservation and the host-side orchestration of one TDMPC.plan call
 // (algorithm/tdmpc.py:94-163) as a fixed sequence of stream-ordered kernel launches.
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -12,6 +13,7 @@
 int select_max_rows();
 int select_max_elites();
 int select_max_ha();
+void launch_bn_affine(const float* g, const float* b, const float* rm, const float* rv, float eps, int n, float* scale, float* shift, cudaStream_t st);
 
 struct tdmpc_handle {
   tdmpc_model_cfg cfg;
@@ -62,6 +64,12 @@ static size_t arena32_size(const tdmpc_model_cfg& c) {
   n += lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(1, M);        // rew
   n += lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(A, M);        // pi (K padded to L+A)
   n += 2 * (lin_floats(M, L + A) + lin_floats(M, M) + lin_floats(1, M) + 4 * (size_t)M);
+  if (c.dynamics == TDMPC_DYN_DRNN) {
+    const int Hd = c.hidden_dim;
+    n += lin_floats(3 * Hd, L + A) + lin_floats(3 * Hd, Hd) + 6 * (size_t)Hd;     // GRU gates + 3 LayerNorms
+    n += lin_floats(M, Hd) + lin_floats(L, M) + 2 * (size_t)M;                      // prior MLP + BN scale/shift
+    n += lin_floats(M, Hd);                                                         // reward layer 1 reads the GRU state
+  }
   return n + 64;
 }
 
@@ -86,7 +94,12 @@ extern "C" int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out) {
     g_create_err = "model dims must be positive"; return TDMPC_ERR_INVALID;
   }
   if (cfg->action_dim > 64) { g_create_err = "action_dim > 64 unsupported"; return TDMPC_ERR_INVALID; }
-  if (cfg->dynamics != TDMPC_DYN_MLP) { g_create_err = "only MLP dynamics are implemented in this build"; return TDMPC_ERR_INVALID; }
+  if (cfg->dynamics != TDMPC_DYN_MLP && cfg->dynamics != TDMPC_DYN_DRNN) { g_create_err = "unknown dynamics type"; return TDMPC_ERR_INVALID; }
+  if (cfg->dynamics == TDMPC_DYN_DRNN) {
+    if (cfg->hidden_dim <= 0 || cfg->hidden_dim > 128 || cfg->hidden_dim % 4) { g_create_err = "DRNN: hidden_dim must be a multiple of 4 in (0, 128]"; return TDMPC_ERR_INVALID; }
+    if (3 * cfg->hidden_dim > cfg->mlp_dim) { g_create_err = "DRNN: 3*hidden_dim must not exceed mlp_dim"; return TDMPC_ERR_INVALID; }
+    if (cfg->precision != TDMPC_PREC_FP32) { g_create_err = "DRNN (GRU) dynamics are implemented in the fp32 mode only in this build"; return TDMPC_ERR_INVALID; }
+  }
   if (cfg->precision == TDMPC_PREC_BF16) {
     const char* why = tc_supported(*cfg);
     if (why) { g_create_err = std::string("bf16 tcgen05 path: ") + why; return TDMPC_ERR_INVALID; }
@@ -129,6 +142,14 @@ int tc_trace_slots();
 // clock64 stamps [role][job][start,end] of one tile of the tcgen05 rollout kernel; NULL disables.
 extern "C" __attribute__((visibility("default"))) int tdmpc_debug_set_trace(void* dev_buf) { tc_set_trace((unsigned long long*)dev_buf); return tc_trace_slots(); }
 
+extern "C" int32_t tdmpc_abi_sizes(int32_t* out, int32_t n) {
+  const int32_t v[] = {(int32_t)sizeof(tdmpc_model_cfg), (int32_t)sizeof(tdmpc_weights), (int32_t)sizeof(tdmpc_plan_args),
+                       (int32_t)offsetof(tdmpc_plan_args, obs), (int32_t)offsetof(tdmpc_plan_args, seed),
+                       (int32_t)offsetof(tdmpc_plan_args, action), (int32_t)offsetof(tdmpc_plan_args, tap_z0)};
+  const int32_t m = (int32_t)(sizeof(v) / sizeof(v[0]));
+  for (int32_t i = 0; i < n && i < m; ++i) out[i] = v[i];
+  return m;
+}
 extern "C" uint64_t tdmpc_launch_count(const tdmpc_handle* h) { return h ? h->launches : 0; }
 extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;select=bitonic"; }
 
@@ -173,6 +194,7 @@ static int pack_linear(tdmpc_handle* h, ArenaCursor& c, const float* w, const fl
   if (int r = check_launch(h, "transpose_pack")) return r;
   if (b) CUDA_OK(h, cudaMemcpyAsync(bp, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
   out->wt = wt; out->b = b ? bp : nullptr; out->K = Kfull; out->Kp = Kp; out->N = N;
+  out->post_scale = nullptr; out->post_shift = nullptr;
   return 0;
 }
 
@@ -201,10 +223,29 @@ extern "C" int tdmpc_set_weights(tdmpc_handle* h, const tdmpc_weights* w, void* 
   PL(w->enc_w[1], w->enc_b[1], L, E, E, &m.enc[1]);
   m.enc_has_ln = c.enc_layernorm;
   if (c.enc_layernorm) { if ((r = pack_ln(h, cur, w->enc_ln_g, w->enc_ln_b, E, &m.enc_ln, st))) return r; }
-  PL(w->dyn_w[0], w->dyn_b[0], M, L + A, L + A, &m.dyn[0]);
-  PL(w->dyn_w[1], w->dyn_b[1], M, M, M, &m.dyn[1]);
-  PL(w->dyn_w[2], w->dyn_b[2], L, M, M, &m.dyn[2]);
-  PL(w->rew_w[0], w->rew_b[0], M, L + A, L + A, &m.rew[0]);
+  m.drnn = c.dynamics == TDMPC_DYN_DRNN;
+  m.Hd = c.hidden_dim;
+  if (!m.drnn) {
+    PL(w->dyn_w[0], w->dyn_b[0], M, L + A, L + A, &m.dyn[0]);
+    PL(w->dyn_w[1], w->dyn_b[1], M, M, M, &m.dyn[1]);
+    PL(w->dyn_w[2], w->dyn_b[2], L, M, M, &m.dyn[2]);
+    PL(w->rew_w[0], w->rew_b[0], M, L + A, L + A, &m.rew[0]);
+  } else {
+    const int Hd = c.hidden_dim;
+    PL(w->gru_w_ih, nullptr, 3 * Hd, L + A, L + A, &m.gru_ih);
+    PL(w->gru_w_hh, nullptr, 3 * Hd, Hd, Hd, &m.gru_hh);
+    for (int g = 0; g < 3; ++g)
+      if ((r = pack_ln(h, cur, w->gru_ln_g[g], w->gru_ln_b[g], Hd, &m.gru_ln[g], st))) return r;
+    PL(w->prior_w[0], w->prior_b[0], M, Hd, Hd, &m.prior[0]);
+    PL(w->prior_w[1], w->prior_b[1], L, M, M, &m.prior[1]);
+    for (int i = 0; i < 4; ++i) if (!w->prior_bn[i]) FAIL(h, TDMPC_ERR_INVALID, "set_weights: a BatchNorm pointer is NULL");
+    float* sc = cur.base + cur.off; cur.off += M;
+    float* sh = cur.base + cur.off; cur.off += M;
+    launch_bn_affine(w->prior_bn[0], w->prior_bn[1], w->prior_bn[2], w->prior_bn[3], 1e-5f, M, sc, sh, st);
+    if ((r = check_launch(h, "bn_affine"))) return r;
+    m.prior[0].post_scale = sc; m.prior[0].post_shift = sh;
+    PL(w->rew_w[0], w->rew_b[0], M, Hd, Hd, &m.rew[0]);
+  }
   PL(w->rew_w[1], w->rew_b[1], M, M, M, &m.rew[1]);
   PL(w->rew_w[2], w->rew_b[2], 1, M, M, &m.rew[2]);
   PL(w->pi_w[0], w->pi_b[0], M, L, L + A, &m.pi[0]);     // action rows stay zero
@@ -348,6 +389,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
 
   RolloutParams rp{};
   rp.B = B; rp.H = H; rp.L = L; rp.A = A; rp.M = h->cfg.mlp_dim; rp.z0 = z0; rp.min_std = a->min_std;
+  rp.hidden0 = h->cfg.dynamics == TDMPC_DYN_DRNN ? a->hidden : nullptr;
   fill_disc(a->discount, H, rp.disc);
 
   // policy trajectories (tdmpc.py:113-118)
@@ -423,6 +465,12 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     sp.tap_elite_idx = a->tap_elite_idx; sp.tap_mean = a->tap_mean; sp.tap_std = a->tap_std;
     launch_select(sp, st);
     if (int r = check_launch(h, "select")) return r;
+  }
+  if (h->cfg.dynamics == TDMPC_DYN_DRNN && a->hidden_out) {
+    // step the model with the chosen action to get the next GRU state (tdmpc_icem_similarity_drnn.py:267)
+    RolloutParams sp = rp;
+    sp.mode = MODE_STEP; sp.T = 1; sp.Tcap = 1; sp.H = 1; sp.actions = a->action; sp.hidden_out = a->hidden_out;
+    if (int r = run_rollout(h, sp, st)) return r;
   }
   return TDMPC_OK;
 }

@@ -15,6 +15,8 @@ struct LinearT {
   const float* wt;   // [Kp][N]
   const float* b;    // [N] or nullptr
   int K, Kp, N;
+  const float* post_scale;   // optional per-output affine applied after the bias (eval-mode BatchNorm1d)
+  const float* post_shift;
 };
 struct LayerNormP { const float* g; const float* b; };
 
@@ -25,6 +27,11 @@ struct ModelFp32 {
   LinearT pi[3];          // pi[0] is padded to K = L+A with zero rows for the action inputs
   LinearT q[2][3];
   LayerNormP q_ln[2][2];
+  // DRNN dynamics (models/gru_dyna.py:11-29): NormGRUCell + BatchNorm prior MLP; reward reads the GRU state
+  int drnn, Hd;
+  LinearT gru_ih, gru_hh;        // [L+A -> 3Hd], [Hd -> 3Hd], no bias
+  LayerNormP gru_ln[3];          // reset, update, newval (eps 1e-3)
+  LinearT prior[2];              // Hd -> M (with BN affine) -> L
 };
 
 // ------------------------------------------------------------------------------------------
@@ -110,7 +117,7 @@ __device__ __forceinline__ float policy_sample(float mu, float std, float eps) {
 
 // ------------------------------------------------------------------------------------------
 // Trajectory-rollout launch parameters, shared by the fp32 and tcgen05 kernels.
-enum RolloutMode { MODE_VALUE = 0, MODE_PI = 1 };
+enum RolloutMode { MODE_VALUE = 0, MODE_PI = 1, MODE_STEP = 2 };   // MODE_STEP: one DRNN transition with given actions -> hidden_out
 
 struct RolloutParams {
   int mode;
@@ -118,6 +125,8 @@ struct RolloutParams {
   int Tcap;                // row pitch (per problem) of actions / pi_actions / values / last_reward
   int L, A, M;
   const float* z0;         // [B, L]
+  const float* hidden0;    // DRNN: [B, Hd] initial GRU state (nullptr = zeros)
+  float* hidden_out;       // MODE_STEP: [B*T, Hd]
   const float* actions;    // MODE_VALUE: [B, Tcap, H, A] read
   float* pi_actions;       // MODE_PI:    [B, Tcap, H, A] written
   float* values;           // [B, Tcap]

@@ -272,7 +272,21 @@ __global__ void transpose_pack_kernel(const float* __restrict__ w, int N, int K,
   }
 }
 
+// eval-mode BatchNorm1d as y = x * scale + shift  (helper.py:179-184, 657-659; eps 1e-5)
+__global__ void bn_affine_kernel(const float* g, const float* b, const float* rm, const float* rv, float eps, int n, float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float s = g[i] / sqrtf(rv[i] + eps);
+    scale[i] = s;
+    shift[i] = b[i] - rm[i] * s;
+  }
+}
+
 }  // namespace
+
+void launch_bn_affine(const float* g, const float* b, const float* rm, const float* rv, float eps, int n, float* scale, float* shift, cudaStream_t st) {
+  bn_affine_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, b, rm, rv, eps, n, scale, shift);
+}
 
 void launch_select(const SelectParams& p, cudaStream_t st) {
   int n2 = 64;

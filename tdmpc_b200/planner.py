@@ -17,8 +17,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .colored import color_matrices, mix_split
-from .told import DSSM, TOLD, linear_schedule
+from .colored import color_matrices, mix_split, synthesis_matrix
+from .told import DSSM, DSSMRnn, TOLD, linear_schedule
 
 _PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
 
@@ -35,7 +35,7 @@ class Planner:
     """One handle = one model on one GPU.  Not thread-safe; stream-ordered on torch's current stream."""
 
     def __init__(self, obs_dim, action_dim, latent_dim, mlp_dim=512, enc_dim=256, enc_layernorm=False,
-                 precision="bf16", device=None):
+                 precision="bf16", device=None, dynamics="mlp", hidden_dim=0):
         self.lib = _lib.load()          # raises if libtdmpc_b200.so is missing: there is no fallback
         if not torch.cuda.is_available():
             raise RuntimeError("tdmpc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -44,8 +44,10 @@ class Planner:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.D, self.A, self.L, self.M, self.E = obs_dim, action_dim, latent_dim, mlp_dim, enc_dim
         self.precision = precision
-        cfg = _lib.ModelCfg(obs_dim, action_dim, latent_dim, mlp_dim, enc_dim, 0, int(bool(enc_layernorm)),
-                            _lib.DYN_MLP, _PREC[precision], self.device.index)
+        self.drnn = dynamics == "drnn"
+        self.Hd = int(hidden_dim) if self.drnn else 0
+        cfg = _lib.ModelCfg(obs_dim, action_dim, latent_dim, mlp_dim, enc_dim, self.Hd, int(bool(enc_layernorm)),
+                            {"mlp": _lib.DYN_MLP, "drnn": _lib.DYN_DRNN}[dynamics], _PREC[precision], self.device.index)
         self._h = C.c_void_p()
         rc = self.lib.tdmpc_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
@@ -90,11 +92,18 @@ class Planner:
         sd = model_or_sd if isinstance(model_or_sd, dict) else dict(model_or_sd.state_dict(keep_vars=True))
         ln = "_encoder.3.weight" in sd
         last = "_encoder.3" if ln else "_encoder.2"
-        names = ["_encoder.0", last] + [f"{m}.{i}" for m in ("_dynamics", "_reward", "_pi") for i in (0, 2, 4)] + \
+        mlps = ("_reward", "_pi") if self.drnn else ("_dynamics", "_reward", "_pi")
+        names = ["_encoder.0", last] + [f"{m}.{i}" for m in mlps for i in (0, 2, 4)] + \
                 [f"{m}.{i}" for m in ("_Q1", "_Q2") for i in (0, 3, 6)]
         keys = [n + s for n in names for s in (".weight", ".bias")] + \
                [f"{m}.{i}{s}" for m in ("_Q1", "_Q2") for i in (1, 4) for s in (".weight", ".bias")] + \
                (["_encoder.1.weight", "_encoder.1.bias"] if ln else [])
+        if self.drnn:       # models/gru_dyna.py:11-23, models/rnns.py:8-17
+            g = "_dynamics.gru_cell."
+            pm = "_dynamics.prior_mlp."
+            keys += [g + "weight_ih.weight", g + "weight_hh.weight"] + \
+                    [f"{g}ln_{n}{s}" for n in ("reset", "update", "newval") for s in (".weight", ".bias")] + \
+                    [pm + k for k in ("0.weight", "0.bias", "3.weight", "3.bias", "1.weight", "1.bias", "1.running_mean", "1.running_var")]
         ver = tuple((sd[k].data_ptr(), sd[k]._version) for k in keys)
         if not force and ver == self._wver:
             return False
@@ -109,16 +118,29 @@ class Planner:
         if ln:
             w.enc_ln_g, w.enc_ln_b = P("_encoder.1.weight"), P("_encoder.1.bias")
         for dst_w, dst_b, mod in ((w.dyn_w, w.dyn_b, "_dynamics"), (w.rew_w, w.rew_b, "_reward"), (w.pi_w, w.pi_b, "_pi")):
+            if mod == "_dynamics" and self.drnn:
+                continue
             for j, i in enumerate((0, 2, 4)):
                 dst_w[j], dst_b[j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
+        if self.drnn:
+            w.gru_w_ih, w.gru_w_hh = P(g + "weight_ih.weight"), P(g + "weight_hh.weight")
+            for j, n in enumerate(("reset", "update", "newval")):
+                w.gru_ln_g[j], w.gru_ln_b[j] = P(f"{g}ln_{n}.weight"), P(f"{g}ln_{n}.bias")
+            w.prior_w[0], w.prior_b[0], w.prior_w[1], w.prior_b[1] = P(pm + "0.weight"), P(pm + "0.bias"), P(pm + "3.weight"), P(pm + "3.bias")
+            for j, n in enumerate(("weight", "bias", "running_mean", "running_var")):
+                w.prior_bn[j] = P(pm + "1." + n)
         for qi, mod in enumerate(("_Q1", "_Q2")):
             for j, i in enumerate((0, 3, 6)):
                 w.q_w[qi][j], w.q_b[qi][j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
             for j, i in enumerate((1, 4)):
                 w.q_ln_g[qi][j], w.q_ln_b[qi][j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
         shapes = {"_encoder.0.weight": (self.E, self.D), last + ".weight": (self.L, self.E),
-                  "_dynamics.0.weight": (self.M, self.L + self.A), "_dynamics.4.weight": (self.L, self.M),
                   "_pi.0.weight": (self.M, self.L), "_pi.4.weight": (self.A, self.M), "_Q1.6.weight": (1, self.M)}
+        if self.drnn:
+            shapes.update({g + "weight_ih.weight": (3 * self.Hd, self.L + self.A), g + "weight_hh.weight": (3 * self.Hd, self.Hd),
+                           pm + "0.weight": (self.M, self.Hd), pm + "3.weight": (self.L, self.M), "_reward.0.weight": (self.M, self.Hd)})
+        else:
+            shapes.update({"_dynamics.0.weight": (self.M, self.L + self.A), "_dynamics.4.weight": (self.L, self.M)})
         for k, s in shapes.items():
             if tuple(t[k].shape) != s:
                 raise RuntimeError(f"sync_weights: {k} has shape {tuple(t[k].shape)}, expected {s}")
@@ -179,7 +201,7 @@ class Planner:
              temperature, momentum, min_std, std_floor, std_max=2.0, init_std=2.0, eval_mode=False, t0=True,
              prev_mean=None, has_prev=None, noise=None, taps=False, seed=None, call=None,
              n_samples=None, n_reuse=None, n_pi=None, out=None, elite_actions=None, elite_horizon=0,
-             warm_last=False, best_a_last=False, shift_elites=False, color=None):
+             warm_last=False, best_a_last=False, shift_elites=False, color=None, hidden=None, hidden_out=None):
         """TDMPC.plan (tdmpc.py:94-163) for a batch of independent problems.
 
         obs [B,D] (or z0 [B,L]) on the device.  prev_mean [B,H,A] is read (warm start) and
@@ -227,6 +249,13 @@ class Planner:
             obs = _f32(obs, self.device); keep.append(obs); a.obs = obs.data_ptr()
         else:
             z0 = _f32(z0, self.device); keep.append(z0); a.z0 = z0.data_ptr()
+        if self.drnn:                       # GRU state in / state after stepping with the returned action out
+            if hidden is not None:
+                hidden = _f32(hidden, self.device); keep.append(hidden); a.hidden = hidden.data_ptr()
+                assert tuple(hidden.shape) == (B, self.Hd)
+            if hidden_out is not None:
+                assert hidden_out.is_contiguous() and hidden_out.dtype == torch.float32 and tuple(hidden_out.shape) == (B, self.Hd)
+                a.hidden_out = hidden_out.data_ptr()
         assert prev_mean.is_contiguous() and prev_mean.dtype == torch.float32 and tuple(prev_mean.shape) == (B, H, A)
         a.prev_mean = prev_mean.data_ptr()
         a.seed = self.seed if seed is None else seed
@@ -259,7 +288,7 @@ class Planner:
             a.tap_mean, a.tap_std, a.tap_z0 = tp["mean"].data_ptr(), tp["std"].data_ptr(), tp["z0"].data_ptr()
         self._check(self.lib.tdmpc_plan(self._h, C.byref(a), self._stream()), "tdmpc_plan")
         self._keep_call = keep          # inputs must outlive the enqueued kernels
-        return {"action": out["action"], "metrics": out["metrics"], "prev_mean": prev_mean, "taps": tp}
+        return {"action": out["action"], "metrics": out["metrics"], "prev_mean": prev_mean, "taps": tp, "hidden": hidden_out}
 
 
 # ======================================================================================= drop-in
@@ -372,15 +401,96 @@ def _fast_plan_icem(self, obs, eval_mode=False, step=None, t0=True):
     return res["action"][0], plan_metrics
 
 
+def _fast_plan_icem_drnn(self, obs, hidden, eval_mode=False, step=None, t0=True):
+    """Drop-in for TdICemSimDssm.plan (src/algorithm/tdmpc_icem_similarity_drnn.py:168-272): the iCEM loop over the
+    GRU latent dynamics.  Same arguments and return `(action [A], hidden' [1, Hd], metrics)`; `hidden'` is the GRU
+    state after stepping the model with the returned action (:267).  Differences from the MLP agent that are
+    reproduced: single-beta colored noise of length plan_horizon (sample_action_sequence, :135-146) and elite
+    reuse gated on `not t0` in every iteration (:203-214)."""
+    cfg = self.cfg
+    plan_metrics = {"external_reward_mean": 0.0, "current_std": 0.0}
+    if step < cfg.seed_steps and not eval_mode:
+        return torch.empty(cfg.action_dim, dtype=torch.float32, device=self.device).uniform_(-1, 1), None, plan_metrics
+    if cfg.fraction_elites_reused > 0 and not cfg.keep_previous_elites:
+        raise NotImplementedError("fraction_elites_reused > 0 needs keep_previous_elites (the reference reuses a stale tensor otherwise)")
+    pl = self._planner
+    pl.sync_weights(self.model)
+    horizon = int(min(cfg.horizon, linear_schedule(cfg.horizon_schedule, step)))
+    extend = False
+    if horizon != self.plan_horizon and t0:
+        self.plan_horizon = horizon
+        extend = True
+    H, A, K, I = self.plan_horizon, cfg.action_dim, cfg.num_elites, cfg.iterations
+    self.mixture_coef = linear_schedule(cfg.regularization_schedule, step)
+    prev_elites = getattr(self, "_elite_actions", None)            # reference layout [H_e, K, A]
+    have = prev_elites is not None and not t0
+    sizes = []
+    n = cfg.num_samples
+    for i in range(I):
+        if i > 0:
+            n = max(2 * K, int(n / cfg.factor_decrease_num))
+        p = int(self.mixture_coef * n)
+        if p <= 0:
+            raise AssertionError("num_pi_trajs must be > 0")
+        # `hasattr(self, '_elite_actions')` turns true after iteration 0 of this very call; `not t0` gates every iteration
+        reuse = cfg.fraction_elites_reused > 0 and not t0 and (prev_elites is not None or i > 0)
+        sizes.append((n, int(cfg.fraction_elites_reused * K) if reuse else 0, p))
+    shift = bool(cfg.shift_elites_over_time) and have
+    if have and not shift and sizes[0][1] > 0:
+        raise RuntimeError("fraction_elites_reused > 0 without shift_elites_over_time leaves `reused_actions` undefined "
+                           "in the reference (tdmpc_icem_similarity_drnn.py:221-232)")
+    ebuf = torch.zeros(1, K, H, A, device=self.device)
+    eh = H
+    if have:
+        eh = prev_elites.shape[0]
+        if eh != H:                     # extend_horizon needs t0, and t0 disables reuse: lengths must agree here
+            raise RuntimeError(f"shape mismatch: _elite_actions has horizon {eh}, plan horizon is {H}")
+        ebuf.view(-1)[: K * eh * A] = prev_elites.permute(1, 0, 2).reshape(-1)
+    prev = getattr(self, "_prev_mean", None)
+    has_prev = prev is not None and not t0
+    if has_prev and prev.shape[0] != H:
+        raise RuntimeError(f"shape mismatch: _prev_mean has horizon {prev.shape[0]}, plan horizon is {H}")
+    buf = prev.reshape(1, H, A).contiguous().clone() if has_prev else None
+    obs_t = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.device, non_blocking=True).reshape(1, -1)
+    color = None
+    if cfg.noise_beta > 0:
+        key = (H, float(cfg.noise_beta))
+        if getattr(self, "_color_key", None) != key:
+            m = np.zeros((3, H, H), dtype=np.float32)
+            m[0] = m[1] = m[2] = synthesis_matrix(cfg.noise_beta, H)
+            self._color_mats = torch.from_numpy(m).to(self.device)
+            self._color_key = key
+        color = {"len": H, "mats": self._color_mats, "n_white": [0] * I, "n_color1": [s[0] for s in sizes]}
+    hid = torch.as_tensor(hidden, dtype=torch.float32, device=self.device).reshape(1, -1)
+    hid_out = torch.empty(1, cfg.hidden_dim, device=self.device)
+    res = pl.plan(obs_t, horizon=H, num_samples=cfg.num_samples, num_pi_trajs=sizes[0][2], num_elites=K, iterations=I,
+                  discount=cfg.discount, temperature=cfg.temperature, momentum=cfg.momentum, min_std=cfg.min_std,
+                  std_floor=self.std, init_std=0.5, eval_mode=eval_mode, t0=bool(t0), prev_mean=buf, has_prev=has_prev,
+                  noise=getattr(self, "_inject_noise", None), taps=getattr(self, "_want_taps", False),
+                  n_samples=[s[0] for s in sizes], n_reuse=[s[1] for s in sizes], n_pi=[s[2] for s in sizes],
+                  elite_actions=ebuf, elite_horizon=eh, warm_last=True, best_a_last=True, shift_elites=shift, color=color,
+                  hidden=hid, hidden_out=hid_out)
+    self._prev_mean = res["prev_mean"][0]
+    self._elite_actions = ebuf[0].permute(1, 0, 2)                 # [H, K, A] like the reference
+    self._last_taps = res["taps"]
+    m = res["metrics"][0].tolist()
+    plan_metrics.update({"external_reward_mean": m[0], "current_std": m[1]})
+    return res["action"][0], hid_out, plan_metrics
+
+
 def accelerate(agent, precision="bf16"):
     """Give an existing reference-style agent (attributes cfg, model, std, device) the CUDA `plan`.
     The agent's nn.Module keeps owning the parameters; they are re-packed whenever they change."""
     cfg = agent.cfg
     sd = agent.model.state_dict()
+    drnn = hasattr(agent.model._dynamics, "gru_cell")
+    if drnn and precision != "fp32":
+        raise RuntimeError("the GRU (DRNN) dynamics are available in the fp32 mode only")
     agent._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
-                             enc_layernorm="_encoder.3.weight" in sd, precision=precision, device=agent.device)
-    icem = hasattr(agent, "plan_horizon") and hasattr(cfg, "factor_decrease_num") and not hasattr(agent.model._dynamics, "gru_cell")
-    agent.plan = types.MethodType(_fast_plan_icem if icem else _fast_plan, agent)
+                             enc_layernorm="_encoder.3.weight" in sd, precision=precision, device=agent.device,
+                             dynamics="drnn" if drnn else "mlp", hidden_dim=cfg.hidden_dim if drnn else 0)
+    icem = hasattr(agent, "plan_horizon") and hasattr(cfg, "factor_decrease_num")
+    agent.plan = types.MethodType(_fast_plan_icem_drnn if drnn else _fast_plan_icem if icem else _fast_plan, agent)
     return agent
 
 
@@ -447,3 +557,30 @@ class TdICemSimMlp(TDMPC):
                                 device=self.device)
 
     plan = _fast_plan_icem
+
+
+class TdICemSimDssm(TDMPC):
+    """Planning half of the reference's iCEM agent with GRU latent dynamics
+    (src/algorithm/tdmpc_icem_similarity_drnn.py:80-272) on the B200 planner: `plan(obs, hidden, eval_mode, step, t0)`
+    -> `(action, hidden', metrics)`."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        dev = getattr(cfg, "device", "cuda")
+        self.device = torch.device(dev if dev != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        self.std = linear_schedule(cfg.std_schedule, 0)
+        self.mixture_coef = linear_schedule(cfg.regularization_schedule, 0)
+        self.model = DSSMRnn(cfg).to(self.device)
+        self.model_target = deepcopy(self.model)
+        self.model.eval()
+        self.model_target.eval()
+        self.plan_horizon = 1
+        self.explore_coef = 0
+        self._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
+                                enc_layernorm=bool(cfg.normalize), precision=getattr(cfg, "precision", "fp32"),
+                                device=self.device, dynamics="drnn", hidden_dim=cfg.hidden_dim)
+
+    plan = _fast_plan_icem_drnn
+
+    def estimate_value(self, z, actions, hidden):
+        raise NotImplementedError("use Planner.plan / TdICemSimDssm.plan; the stage-level DRNN value call is not exposed")

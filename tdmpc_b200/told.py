@@ -124,3 +124,86 @@ class DSSM(TOLD):
 
     def pred_z(self, z):
         return self._predictor(z)
+
+
+class NormGRUCell(nn.Module):
+    """Bias-free GRU cell with one LayerNorm (eps 1e-3) per gate (src/models/rnns.py:8-29).  Gate chunks along
+    3*hidden are reset, update, newval and h' = update * newval + (1 - update) * h."""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.weight_ih = nn.Linear(input_size, 3 * hidden_size, bias=False)
+        self.weight_hh = nn.Linear(hidden_size, 3 * hidden_size, bias=False)
+        self.ln_reset = nn.LayerNorm(hidden_size, eps=1e-3)
+        self.ln_update = nn.LayerNorm(hidden_size, eps=1e-3)
+        self.ln_newval = nn.LayerNorm(hidden_size, eps=1e-3)
+
+    def forward(self, x, state):
+        ri, ui, ni = self.weight_ih(x).chunk(3, 1)
+        rh, uh, nh = self.weight_hh(state).chunk(3, 1)
+        reset = torch.sigmoid(self.ln_reset(ri + rh))
+        update = torch.sigmoid(self.ln_update(ui + uh))
+        newval = torch.tanh(self.ln_newval(ni + reset * nh))
+        return update * newval + (1 - update) * state
+
+
+class DGruDyna(nn.Module):
+    """Recurrent latent dynamics (src/models/gru_dyna.py:11-29): NormGRUCell([z,a], h) -> prior MLP with
+    BatchNorm1d (helper.mlp_norm's default norm_type, helper.py:179-184)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        L, A, M, Hd = cfg.latent_dim, cfg.action_dim, cfg.mlp_dim, cfg.hidden_dim
+        self.prior_mlp = nn.Sequential(nn.Linear(Hd, M), nn.BatchNorm1d(M), nn.ELU(), nn.Linear(M, L))
+        if not getattr(cfg, "norm_cell", True):
+            raise NotImplementedError("tdmpc_b200 covers the NormGRUCell dynamics (cfg.norm_cell=True) only")
+        self.gru_cell = NormGRUCell(L + A, Hd)
+
+    def init_hidden_state(self, batch_size, device):
+        return torch.zeros((batch_size, self.cfg.hidden_dim), device=device)
+
+    def forward(self, obs_embed, action, h_prev):
+        h = self.gru_cell(torch.cat([obs_embed, action], dim=-1), h_prev)
+        return self.prior_mlp(h), h
+
+
+class DSSMRnn(TOLD):
+    """Model of the DRNN iCEM agent (src/algorithm/tdmpc_icem_similarity_drnn.py:14-77): GRU latent dynamics,
+    reward read from the GRU state, `next(z, a, h_prev) -> (z', h', r)`.  Same state_dict keys as the reference."""
+
+    def __init__(self, cfg):
+        nn.Module.__init__(self)
+        self.cfg = cfg
+        L, A, M, E, D, Hd = cfg.latent_dim, cfg.action_dim, cfg.mlp_dim, cfg.enc_dim, cfg.obs_shape[0], cfg.hidden_dim
+        if getattr(cfg, "modality", "state") != "state":
+            raise NotImplementedError("tdmpc_b200 covers the state-observation encoder only")
+        self._dynamics = DGruDyna(cfg)
+        self._reward = _mlp(Hd, M, 1)
+        self._pi = _mlp(L, M, A)
+        self._Q1, self._Q2 = _q(L + A, M), _q(L + A, M)
+        if cfg.normalize:
+            self._encoder = nn.Sequential(nn.Linear(D, E), nn.LayerNorm(E), nn.ELU(), nn.Linear(E, L))
+            self._predictor = nn.Sequential(nn.Linear(L, M), nn.BatchNorm1d(M), nn.ELU(), nn.Linear(M, L))
+        else:
+            self._encoder = nn.Sequential(nn.Linear(D, E), nn.ELU(), nn.Linear(E, L))
+            self._predictor = _mlp(L, M, L)
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
+                nn.init.orthogonal_(mod.weight.data)
+                if mod.bias is not None:
+                    nn.init.zeros_(mod.bias)
+        for mod in (self._reward, self._Q1, self._Q2):
+            mod[-1].weight.data.fill_(0)
+            mod[-1].bias.data.fill_(0)
+
+    def next(self, z, a, h_prev):
+        z, hidden = self._dynamics(z, a, h_prev)
+        return z, hidden, self._reward(hidden)
+
+    def init_hidden_state(self, batch_size, device):
+        return self._dynamics.init_hidden_state(batch_size, device)
+
+    def pred_z(self, z):
+        return self._predictor(z)

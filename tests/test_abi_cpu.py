@@ -15,7 +15,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "tdmpc_b200.h")).read()
     declared = re.findall(r"TDMPC_API\s+[\w\s\*]+?\b(tdmpc_\w+)\s*\(", hdr)
-    assert len(declared) >= 13 and set(declared) == set(_lib.EXPORTS)
+    assert len(declared) >= 14 and set(declared) == set(_lib.EXPORTS)
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
@@ -25,7 +25,12 @@ def test_header_symbols_are_exported():
 def test_struct_layouts_match_header_sizes():
     # pointer-heavy structs: sizes must be multiples of 8 and the iteration arrays 16 long
     assert C.sizeof(_lib.ModelCfg) == 40
-    assert C.sizeof(_lib.Weights) == 8 * (2 + 2 + 2 + 3 * 6 + 6 + 6 + 4 + 4)
+    assert C.sizeof(_lib.Weights) == 8 * (2 + 2 + 2 + 3 * 6 + 6 + 6 + 4 + 4 + 2 + 6 + 4 + 4)
+    # the library reports its own sizeof/offsetof values; load() compares them with the ctypes mirror
+    got = (C.c_int32 * 7)()
+    assert _lib.load().tdmpc_abi_sizes(got, 7) == 7
+    assert list(got)[:3] == [C.sizeof(_lib.ModelCfg), C.sizeof(_lib.Weights), C.sizeof(_lib.PlanArgs)]
+    assert got[6] == _lib.PlanArgs.tap_z0.offset
     assert _lib.PlanArgs.n_samples.size == 4 * _lib.TDMPC_MAX_ITERS
     assert C.sizeof(_lib.PlanArgs) % 8 == 0
 

@@ -105,6 +105,56 @@ def test_icem_oracle_matches_reference_fixture(golden_dir, name, cfg_name):
         np.testing.assert_allclose(a.numpy(), g[f"s{s}_action"], atol=1e-4)
 
 
+@pytest.mark.parametrize("name,cfg_name", [("drnn_tiny", "tiny_drnn"), ("drnn_cfg5", "cfg5")])
+def test_drnn_oracle_matches_reference_fixture(golden_dir, name, cfg_name):
+    """oracle.plan_icem_drnn against what the real TdICemSimDssm.plan produced (NormGRUCell + BatchNorm prior MLP
+    dynamics, reward from the GRU state, hidden-state threading): tests/golden/make_golden.py:run_drnn_case."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, steps, _ = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_drnn_weights(cfg, seed)
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    hidden = torch.zeros(1, cfg.hidden_dim)
+    for s in range(steps):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        t0 = s == 0
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_drnn_sizes(cfg, O.linear_schedule(cfg.regularization_schedule, 10 ** 6), have, t0)
+        assert np.array_equal(np.array(sizes), g[f"s{s}_sizes"])
+        H = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, 10 ** 6)))
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have and not t0, single_beta=True)
+        a, hidden, m, taps = O.plan_icem_drnn(sd, cfg, obs, hidden, eval_mode=True, step=10 ** 6, t0=t0, state=state, noise=nz)
+        ref_vals = g[f"s{s}_values"]
+        scale = np.abs(ref_vals).max()
+        for i in range(cfg.iterations):
+            v = taps["values"][i].numpy()
+            assert np.abs(v - ref_vals[i, :v.shape[0]]).max() <= TOL * scale
+        np.testing.assert_allclose(state["_prev_mean"].numpy(), g[f"s{s}_prev_mean"], atol=1e-4)
+        np.testing.assert_allclose(state["_elite_actions"].numpy(), g[f"s{s}_elite_actions"], atol=1e-4)
+        np.testing.assert_allclose(a.numpy(), g[f"s{s}_action"], atol=1e-4)
+        np.testing.assert_allclose(hidden.numpy(), g[f"s{s}_hidden"], atol=1e-4)
+
+
+def test_drnn_model_mirror_matches_oracle_step():
+    """tdmpc_b200.DSSMRnn (the nn.Module mirror of the reference DSSM with GRU dynamics) has the reference's
+    state_dict keys and its next() equals the oracle's dssm_next."""
+    from tdmpc_b200 import DSSMRnn
+    cfg = synth.make_cfg("tiny_drnn")
+    sd = synth.make_drnn_weights(cfg, 1)
+    m = DSSMRnn(cfg).eval()
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    assert all(k.startswith("_predictor") or k.endswith("num_batches_tracked") for k in missing.missing_keys)
+    rs = np.random.RandomState(0)
+    z = torch.from_numpy(rs.standard_normal((9, cfg.latent_dim)).astype(np.float32))
+    a = torch.from_numpy(rs.uniform(-1, 1, (9, cfg.action_dim)).astype(np.float32))
+    h = torch.from_numpy(rs.standard_normal((9, cfg.hidden_dim)).astype(np.float32))
+    with torch.no_grad():
+        z1, h1, r1 = m.next(z, a, h)
+    z2, h2, r2 = O.dssm_next(sd, z, a, h)
+    assert torch.allclose(z1, z2, atol=1e-6) and torch.allclose(h1, h2, atol=1e-6) and torch.allclose(r1, r2, atol=1e-6)
+
+
 def test_colored_noise_matrix_is_the_generator():
     """tdmpc_b200.colored.synthesis_matrix (what the CUDA sampler multiplies white noise by) equals the oracle's
     restatement of colorednoise.powerlaw_psd_gaussian, both as a matrix and in distribution."""
