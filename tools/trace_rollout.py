@@ -19,39 +19,19 @@ pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, 
 lib.tdmpc_debug_set_trace(C.c_void_p(buf.data_ptr()))
 pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
 torch.cuda.synchronize(); lib.tdmpc_debug_set_trace(None)
-tr = buf.cpu().numpy().reshape(3, -1, 3)
-names = {0: "L1", 1: "L2", 2: "L3"}; chains = ["dyn", "rew", "pi", "q1", "q2"]
-epis = ["H1", "XR", "XS", "DOT", "Z", "PI", "STAT", "QN", "QDOT"]
-# rebuild the job list exactly as build_jobs(MODE_VALUE, H, xr=True) does (rollout_tc.cu)
+tr = buf.cpu().numpy().reshape(3, -1, 2)
+names = {0: "L1", 1: "L2", 2: "L3", 3: "QL1", 4: "QL2"}; chains = ["dyn", "rew", "pi", "q1", "q2"]
+# rebuild the job list exactly as build_jobs(MODE_VALUE, H) does
 jobs = []
-def l1(ch, t, e): jobs.extend((0, e, ch, c, t) for c in range(4))
-def l2(ch, t, e): jobs.extend((1, e, ch, c, t) for c in range(4))
-if os.environ.get("TDMPC_TC_XR", "1") != "0":
-    l1(0, 0, 0)
-    for t in range(H):
-        last = t == H - 1
-        for c in range(4):
-            jobs += [(1, 2, 0, c, t), (0, 1, 1, c, t)]
-        jobs.append((2, 4, 0, 0, t))
-        nxt = 2 if last else 0
-        tn = 0 if last else t + 1
-        jobs.append((1, 3, 1, 0, t))
-        for c in (1, 2, 3):
-            jobs += [(1, 3, 1, c, t), (0, 0, nxt, c - 1, tn)]
-        jobs.append((0, 0, nxt, 3, tn))
-else:
-    for t in range(H):
-        l1(0, t, 0); l2(0, t, 2); l1(1, t, 0); jobs.append((2, 4, 0, 0, t)); l2(1, t, 3)
-    l1(2, 0, 0)
-l2(2, 0, 2); jobs.append((2, 5, 2, 0, 0))
-for qh in (3, 4):
-    l1(qh, 0, 6); l1(qh, 0, 7); l2(qh, 0, 6); l2(qh, 0, 8)
+for t in range(H):
+    jobs += [(0, 0, c, t) for c in range(4)] + [(1, 0, c, t) for c in range(4)] + [(0, 1, c, t) for c in range(4)] + [(2, 0, 0, t)] + [(1, 1, c, t) for c in range(4)]
+jobs += [(0, 2, c, 0) for c in range(4)] + [(1, 2, c, 0) for c in range(4)] + [(2, 2, 0, 0), (3, 3, 0, 0), (4, 3, 0, 0), (3, 4, 0, 0), (4, 4, 0, 0)]
 t0 = tr[0, 0, 0]
-print(f"{'job':>4} {'what':20} | {'mma start':>9} {'wait':>6} {'issue':>6} | {'epi0 start':>10} {'wait':>6} {'work':>6} | {'epi1 start':>10} {'wait':>6} {'work':>6}")
-for j, (ty, ep, chn, c, t) in enumerate(jobs):
-    row = [f"{j:4d} {names[ty] + ' ' + chains[chn] + ' c' + str(c) + ' t' + str(t) + ' ' + epis[ep]:20}"]
+print(f"{'job':>4} {'what':14} | {'mma start':>9} {'mma end':>9} {'dur':>6} | {'epi0 start':>10} {'end':>8} {'dur':>6} | {'epi1 start':>10} {'end':>8} {'dur':>6}")
+for j, (ty, chn, c, t) in enumerate(jobs):
+    row = [f"{j:4d} {names[ty] + ' ' + chains[chn] + ' c' + str(c) + ' t' + str(t):14}"]
     for r in range(3):
-        s, w, e = tr[r, j]
-        row.append(f"{(s - t0) if s else 0:>10} {(w - s) if s and w else 0:>6} {(e - w) if w and e else 0:>6}")
+        s, e = tr[r, j]
+        row.append(f"{(s - t0) if s else 0:>10} {(e - t0) if e else 0:>8} {(e - s) if s and e else 0:>6}")
     print(" | ".join(row))
-print("tile total cycles:", tr[:, :len(jobs), 2].max() - t0)
+print("tile total cycles:", tr[:, :len(jobs), 1].max() - t0)
