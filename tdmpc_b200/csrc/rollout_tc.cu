@@ -35,6 +35,7 @@ constexpr int TILE_ROWS = 128;
 constexpr int NTHREADS = 384;              // warps 0-3: producer / MMA / 2 idle; warps 4-7, 8-11: epilogue groups 0 and 1
 constexpr int REGS_CTRL = 56, REGS_EPI = 224;   // setmaxnreg: frees (168-56)*128 = takes (224-168)*256 registers, exactly
 constexpr int XCH_FLOATS = 3 * 2 * 128;   // epilogue-group exchange: {sum, sum-of-squares, dot} x 2 groups x 128 rows
+constexpr int QC_FLOATS = 4 * 512;         // per-column constants of the current Q-head layer: bias, LN gamma, LN beta, w3
 constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
 constexpr int MAX_JOBS = 17 * TDMPC_MAX_H + 16;
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint8_t* za = xs + XS_BYTES;
   uint8_t* wring = za + m.nkb1 * TILE_BYTES;
   float* xch = reinterpret_cast<float*>(wring + S * TILE_BYTES);     // [3][2 groups][128 rows] epilogue-group exchange
-  uint32_t* sjobs = reinterpret_cast<uint32_t*>(xch + XCH_FLOATS);
+  float* qcs = xch + XCH_FLOATS;                                       // [4][512] Q-head layer constants (16-byte aligned)
+  uint32_t* sjobs = reinterpret_cast<uint32_t*>(qcs + QC_FLOATS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sjobs + ((kp.njobs + 3) & ~3));
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + MAX_STAGES;
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const uint32_t idesc128 = umma_idesc_bf16(128, 128);
       const uint32_t za_addr = smem_u32(za), xs_addr = smem_u32(xs), ring_addr = smem_u32(wring);
       const int ks1_total = m.K1p / 16;
+      const uint32_t ring_lo[4] = {umma_desc_lo(ring_addr), umma_desc_lo(ring_addr + TILE_BYTES), umma_desc_lo(ring_addr + 2 * TILE_BYTES),
+                                   umma_desc_lo(ring_addr + 3 * TILE_BYTES)};
 
       // Weight-ring consumer.  tile_acquire() returns the smem address of the current tile and already
       // advances the ring and probes the NEXT tile's barrier, so that probe's latency overlaps the MMA
@@ -247,17 +251,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             acc_acquire(b);
             tcgen05_fence_after();
             const uint32_t d = tmem + TM_ACC + b * 128;
+            if (S == 4 && stage == 0) {
+              // Static fast path.  With a 4-slot ring every layer consumes a multiple of 4 tiles, so a layer-2 job
+              // always starts at slot 0 and its 8 tiles are two full turns of the ring: slot, barrier and
+              // descriptor of every k-block are compile-time choices among 4 precomputed values, which keeps the
+              // single issuing thread's instruction stream short enough to stay ahead of the tensor pipe.
 #pragma unroll
-            for (int kb = 0; kb < 8; ++kb) {
-              if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
-              const uint32_t wt = tile_acquire();
-              if (leader) {
-                const uint32_t blo = umma_desc_lo(wt);
-                const uint32_t a = tmem + TM_A + kb * 32;
+              for (int kb = 0; kb < 8; ++kb) {
+                const int st = kb & 3;
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
+                tcgen05_fence_after();
+                if (leader) {
+                  const uint32_t blo = ring_lo[st];
+                  const uint32_t a = tmem + TM_A + kb * 32;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+                  for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+                  umma_commit(&w_empty[st]);
+                }
               }
-              tile_release();
+              ready = 0;                       // slot 0 again, same parity: the early probe must be redone
+            } else {
+#pragma unroll
+              for (int kb = 0; kb < 8; ++kb) {
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                const uint32_t wt = tile_acquire();
+                if (leader) {
+                  const uint32_t blo = umma_desc_lo(wt);
+                  const uint32_t a = tmem + TM_A + kb * 32;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+                }
+                tile_release();
+              }
             }
             if (leader) umma_commit(&acc_full[b]);
           } else if (type == J_L3) {
@@ -267,13 +293,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint32_t d = tmem + TM_ACC + b * 128;
             const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
             const bool half = m.l3rows[chain] == 64;
-            uint32_t wt = 0;
+            if (half && S == 4 && stage == 0) {
+              // static fast path: 4 tiles (two k-blocks of 64 weight rows each) = one full turn of the ring
 #pragma unroll
-            for (int kb = 0; kb < 8; ++kb) {
-              if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-              if (!half || (kb & 1) == 0) wt = tile_acquire();
-              if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
-              if (!half || (kb & 1)) tile_release();
+              for (int kb = 0; kb < 8; ++kb) {
+                const int st = kb >> 1;
+                if ((kb & 1) == 0) {
+                  xs_wait(kb >> 1); tcgen05_fence_after();
+                  mbar_wait(&w_full[st], wphase, 2);
+                  tcgen05_fence_after();
+                }
+                if (leader) {
+                  const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES), blo = ring_lo[st] + ((kb & 1) ? (8192u >> 4) : 0u);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_ss(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u);
+                  if (kb & 1) umma_commit(&w_empty[st]);
+                }
+              }
+              wphase ^= 1;                     // one full turn
+              ready = 0;
+            } else {
+              uint32_t wt = 0;
+#pragma unroll
+              for (int kb = 0; kb < 8; ++kb) {
+                if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+                if (!half || (kb & 1) == 0) wt = tile_acquire();
+                if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
+                if (!half || (kb & 1)) tile_release();
+              }
             }
             if (leader) umma_commit(&acc_full[b]);
           } else {
@@ -284,6 +332,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tcgen05_fence_after();
             const bool first = type == J_QL1;
             const int nkb = first ? m.nkb1 : 8;
+            if (!first && S == 4 && stage == 0) {
+              // static fast path (see layer 2): 4 chunks x 8 tiles = 8 full turns of the ring
+              for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) {
+                  const int st = kb & 3;
+                  if (c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+                  mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
+                  tcgen05_fence_after();
+                  if (leader) {
+                    const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES), blo = ring_lo[st];
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      umma_ss(tmem + c * 128, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+                    umma_commit(&w_empty[st]);
+                  }
+                }
+                if (leader) umma_commit(&q_full[c]);
+              }
+              ready = 0;
+            } else
             for (int c = 0; c < 4; ++c) {
               for (int kb = 0; kb < nkb; ++kb) {
                 if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
@@ -531,16 +600,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           //   J_QL1: tanh -> bf16 -> XS        J_QL2: ELU -> dot with w3 -> q
           // Group g handles chunks g and g+2; statistics are exchanged between the groups.
           const bool first = type == J_QL1;
-          const float* bias = first ? ch.b1 : ch.b2;
-          const float* lg = ch.ln_g[first ? 0 : 1];
-          const float* lb = ch.ln_b[first ? 0 : 1];
+          // Stage the layer's per-column constants in shared memory: every thread needs all of them, and with 227 KB of
+          // the SM given to shared memory the L1 is too small to keep the 8 KB vectors of all chains resident.
+          const float4* qb = reinterpret_cast<const float4*>(qcs);            // bias
+          const float4* qg = qb + 128;                                         // LayerNorm gamma
+          const float4* qe = qb + 256;                                         // LayerNorm beta
+          const float4* qw = qb + 384;                                         // head weights w3
+          epi_bar_sync();                                                      // the previous layer's readers are done
+          {
+            const float* srcs[4] = {first ? ch.b1 : ch.b2, ch.ln_g[first ? 0 : 1], ch.ln_b[first ? 0 : 1], ch.w3};
+            float4* dstc = reinterpret_cast<float4*>(qcs);
+            const int te = (int)threadIdx.x - 128;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int idx = te + k * 256;
+              dstc[idx] = ldg4(srcs[idx >> 7], idx & 127);
+            }
+          }
+          epi_bar_sync();
           float sum = 0.0f, ssq = 0.0f;
           for (int c = grp; c < 4; c += 2) {
             float4 x0[8];
-            load8(bias, c * 4, x0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x0[i] = qb[c * 32 + i];
             mbar_wait(&q_full[c], q_phase, 8);
             tcgen05_fence_after();
-            tmem_stream_aux(tlane + c * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, c * 4 + s, x); },
+            tmem_stream_aux(tlane + c * 128, 4, x0, [&](int s, float4 (&x)[8]) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = qb[(c * 4 + s) * 8 + i];
+            },
                             [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -565,7 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int vi = (c * 4 + s) * 8 + i;
-                const float4 x = ldg4(bias, vi), gg = ldg4(lg, vi), bb = ldg4(lb, vi);
+                const float4 x = qb[vi], gg = qg[vi], bb = qe[vi];
                 y[4 * i] = (__uint_as_float(v[4 * i]) + x.x - mu) * rstd * gg.x + bb.x;
                 y[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + x.y - mu) * rstd * gg.y + bb.y;
                 y[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + x.z - mu) * rstd * gg.z + bb.z;
@@ -579,7 +667,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float4 f = ldg4(ch.w3, (c * 4 + s) * 8 + i);
+                  const float4 f = qw[(c * 4 + s) * 8 + i];
                   qdot = fmaf(elu_fast(y[4 * i]), f.x, qdot); qdot = fmaf(elu_fast(y[4 * i + 1]), f.y, qdot);
                   qdot = fmaf(elu_fast(y[4 * i + 2]), f.z, qdot); qdot = fmaf(elu_fast(y[4 * i + 3]), f.w, qdot);
                 }
@@ -778,7 +866,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + XCH_FLOATS * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 17) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 17) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
