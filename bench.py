@@ -319,6 +319,35 @@ def main():
                 ms1 = e0.elapsed_time(e1) / 20
                 extra[wn + "_b1"] = {"workload": WORKLOADS[wn][2], "ms_per_plan": ms1, "plans_per_sec": 1e3 / ms1,
                                      "sample_steps_per_sec": 1e3 / ms1 * s2}
+            # iCEM planners through the drop-in agent classes, B = 1 (BASELINE.json configs[3], configs[4] dims), built-in
+            # Philox / colored-noise sampler: TdICemSimMlp on the tcgen05 path, TdICemSimDssm (GRU dynamics) on the fp32 path
+            from tdmpc_b200 import TdICemSimDssm, TdICemSimMlp
+            for wn, cls, prec, mk in (("cfg4", TdICemSimMlp, args.precision, lambda c: synth.make_told_weights(c, 0, enc_ln=True)),
+                                      ("cfg5", TdICemSimDssm, "fp32", lambda c: synth.make_drnn_weights(c, 0))):
+                c2 = synth.make_cfg(wn, device=str(dev), precision=prec)
+                ag = cls(c2)
+                ag.model.load_state_dict(mk(c2), strict=False)
+                ag.model.eval()
+                ag.std = c2.min_std
+                o1 = synth.make_obs(c2, 3)
+                hid = torch.zeros(1, c2.hidden_dim, device=dev)
+
+                def one(i, ag=ag, o1=o1, drnn=(wn == "cfg5")):
+                    nonlocal hid
+                    if drnn:
+                        _, hid, _ = ag.plan(o1, hid, eval_mode=True, step=10 ** 6, t0=i == 0)
+                    else:
+                        ag.plan(o1, eval_mode=True, step=10 ** 6, t0=i == 0)
+                for i in range(4):
+                    one(i)
+                torch.cuda.synchronize()
+                t_0 = time.perf_counter()
+                for i in range(10):
+                    one(i + 4)
+                torch.cuda.synchronize()
+                ms1 = (time.perf_counter() - t_0) * 1e3 / 10
+                extra[wn + "_b1"] = {"workload": f"{cls.__name__} (iCEM, {'GRU' if wn == 'cfg5' else 'MLP'} dynamics): obs 18, act 4, H=10, N=1024, K=32, "
+                                                 f"mixture 0.5, I=6, precision {prec}", "ms_per_plan_wall": ms1, "plans_per_sec": 1e3 / ms1}
 
     if rank == 0:
         cpu_rate, n_cpu, med = cpu_plan_rate(cfg, sd, args.cpu_budget) if world == 1 else (None, 0, None)

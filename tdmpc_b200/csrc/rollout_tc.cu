@@ -61,8 +61,12 @@ __device__ __forceinline__ float elu_fast(float x) {
   return x > 0.0f ? x : e;
 }
 __device__ __forceinline__ float tanh_fast(float x) {
+#ifdef TDMPC_TANH_APPROX
+  float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
   const float e = ex2_approx(x * 2.8853900817779268f);       // exp(2x)
   return 1.0f - __fdividef(2.0f, 1.0f + e);
+#endif
 }
 __device__ __forceinline__ float4 ldg4(const float* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
 
