@@ -631,3 +631,58 @@ def test_drnn_batched_hidden_states_are_per_problem():
         torch.cuda.synchronize()
         assert torch.equal(one["taps"]["values"][:, 0], res["taps"]["values"][:, b]), b
         assert torch.equal(one["action"][0], res["action"][b]) and torch.equal(one_h[0], hout[b])
+
+
+# ------------------------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("over", [dict(mixture_coef=0.0), dict(horizon=1, horizon_schedule="1"), dict(num_elites=120, mixture_coef=0.25),
+                                  dict(iterations=1), dict(horizon_schedule="linear(1, 3, 100, 0)", seed_steps=0)])
+def test_fp32_plan_edge_cases(over):
+    """No policy trajectories (tdmpc.py:113 `if num_pi_trajs > 0`), horizon 1, every trajectory an elite (K == T), a single
+    iteration, and a horizon still growing on its schedule (step 40 -> H = 1)."""
+    gu = _gu()
+    cfg = synth.make_cfg("tiny", **over)
+    step = 40 if "linear" in cfg.horizon_schedule else 10 ** 6
+    sd = synth.make_told_weights(cfg, 3)
+    pl = gu.make_planner(cfg, sd, "fp32")
+    prev_o, prev_g = None, None
+    for s in range(2):
+        obs = synth.make_obs(cfg, 40 + s)
+        nz = synth.make_noise(cfg, 40 + s, step)
+        out_o = gu.oracle_plan(sd, cfg, obs, nz, t0=(s == 0), prev_mean=prev_o, eval_mode=False, step=step)
+        res = pl.plan(torch.from_numpy(obs).cuda().unsqueeze(0), **gu.plan_kwargs(cfg, step), eval_mode=False, t0=(s == 0),
+                      prev_mean=prev_g, noise=gu.batch_noise([nz]), taps=True)
+        torch.cuda.synchronize()
+        ok = gu.compare_plan(res, 0, out_o, cfg, TOL_FP32, f"edge {over} step {s}")
+        prev_o = out_o[2]
+        prev_g = res["prev_mean"] if ok else prev_o.cuda().unsqueeze(0).contiguous()
+
+
+def test_plan_is_cuda_graph_capturable():
+    """tdmpc_plan allocates nothing and never synchronises (include/tdmpc_b200.h): a captured plan replays to the same
+    result as the eager call, in both precision modes."""
+    gu = _gu()
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 2)
+    B = 3
+    obs = torch.from_numpy(np.stack([synth.make_obs(cfg, 60 + b) for b in range(B)])).cuda()
+    for prec in ("fp32", "bf16"):
+        pl = gu.make_planner(cfg, sd, prec)
+        kw = gu.plan_kwargs(cfg)
+        H, A = kw["horizon"], cfg.action_dim
+        out = {"action": torch.zeros(B, A, device="cuda"), "metrics": torch.zeros(B, 2, device="cuda")}
+        prev = torch.zeros(B, H, A, device="cuda")
+        eager = pl.plan(obs, **kw, eval_mode=False, t0=True, seed=5, call=9)          # also reserves the scratch
+        torch.cuda.synchronize()
+        a_eager, p_eager = eager["action"].clone(), eager["prev_mean"].clone()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                pl.plan(obs, **kw, eval_mode=False, t0=True, seed=5, call=9, prev_mean=prev, has_prev=False, out=out)
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(2):
+            out["action"].zero_(); prev.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out["action"], a_eager) and torch.equal(prev, p_eager), prec
