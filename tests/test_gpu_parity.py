@@ -686,3 +686,41 @@ def test_plan_is_cuda_graph_capturable():
             g.replay()
             torch.cuda.synchronize()
             assert torch.equal(out["action"], a_eager) and torch.equal(prev, p_eager), prec
+
+
+# ------------------------------------------------------------------------------------------------- full size
+def test_full_size_properties_cfg3():
+    """BASELINE.json's batched configuration (4096 quadrotor environments x 537 trajectories x H=5) through properties that
+    need no CPU oracle at that size: (1) the value of a trajectory depends on its problem's latent and its own actions
+    only -- the same (z0, actions) replicated over all 4096 problems gives 4096 identical value rows, equal to the B=1
+    launch bit for bit (tiles straddle problem boundaries: 537 is not a multiple of 128) and within 1e-3 (median) of the
+    quantised oracle; (2) a whole plan over 4096 different observations is deterministic (same seed / call -> same bits),
+    finite, inside the action box, and problems with equal observations but different noise streams differ."""
+    gu = _gu()
+    cfg = synth.make_cfg("cfg3")
+    sd = synth.make_told_weights(cfg, 0)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    H, N, P, T = synth.plan_dims(cfg)
+    B, A = 4096, cfg.action_dim
+    rs = np.random.RandomState(0)
+    z1 = torch.from_numpy(rs.standard_normal((1, cfg.latent_dim)).astype(np.float32)).cuda()
+    a1 = torch.from_numpy(rs.uniform(-1, 1, (1, T, H, A)).astype(np.float32)).cuda()
+    v1, r1 = pl.estimate_value(z1, a1, discount=cfg.discount, min_std=0.0)
+    vB, rB = pl.estimate_value(z1.expand(B, -1).contiguous(), a1.expand(B, -1, -1, -1).contiguous(), discount=cfg.discount, min_std=0.0)
+    torch.cuda.synchronize()
+    assert torch.equal(vB, v1.expand(B, -1)) and torch.equal(rB, r1.expand(B, -1))
+    v_o, _ = O.estimate_value(sd, z1.cpu().repeat(T, 1), a1[0].permute(1, 0, 2).cpu(), H, cfg.discount, 0.0, None, quant=True)
+    err = (v1[0].cpu() - v_o.squeeze(1)).abs() / v_o.abs().max()
+    assert err.median().item() <= TOL_BF16
+    # whole plans
+    obs = torch.from_numpy(synth.make_obs(cfg, 5, batch=B)).cuda()
+    obs[1] = obs[0]                                           # same observation, different Philox sub-stream
+    kw = gu.plan_kwargs(cfg)
+    r_a = pl.plan(obs, **kw, eval_mode=True, t0=True, seed=3, call=11)
+    a_a, m_a, p_a = r_a["action"].clone(), r_a["metrics"].clone(), r_a["prev_mean"].clone()
+    r_b = pl.plan(obs, **kw, eval_mode=True, t0=True, seed=3, call=11)
+    torch.cuda.synchronize()
+    assert torch.equal(a_a, r_b["action"]) and torch.equal(m_a, r_b["metrics"]) and torch.equal(p_a, r_b["prev_mean"])
+    assert torch.isfinite(a_a).all() and a_a.abs().max() <= 1.0 and torch.isfinite(m_a).all()
+    assert (m_a[:, 1] >= cfg.min_std - 1e-6).all() and (m_a[:, 1] <= 2.0).all()        # current_std inside its clamp
+    assert not torch.equal(a_a[0], a_a[1])
