@@ -320,10 +320,10 @@ def main():
                 extra[wn + "_b1"] = {"workload": WORKLOADS[wn][2], "ms_per_plan": ms1, "plans_per_sec": 1e3 / ms1,
                                      "sample_steps_per_sec": 1e3 / ms1 * s2}
             # iCEM planners through the drop-in agent classes, B = 1 (BASELINE.json configs[3], configs[4] dims), built-in
-            # Philox / colored-noise sampler: TdICemSimMlp on the tcgen05 path, TdICemSimDssm (GRU dynamics) on the fp32 path
+            # Philox / colored-noise sampler: both on the tcgen05 path in bf16 mode (GRU: value rollouts; its policy rollout stays fp32)
             from tdmpc_b200 import TdICemSimDssm, TdICemSimMlp
             for wn, cls, prec, mk in (("cfg4", TdICemSimMlp, args.precision, lambda c: synth.make_told_weights(c, 0, enc_ln=True)),
-                                      ("cfg5", TdICemSimDssm, "fp32", lambda c: synth.make_drnn_weights(c, 0))):
+                                      ("cfg5", TdICemSimDssm, args.precision, lambda c: synth.make_drnn_weights(c, 0))):
                 c2 = synth.make_cfg(wn, device=str(dev), precision=prec)
                 ag = cls(c2)
                 ag.model.load_state_dict(mk(c2), strict=False)

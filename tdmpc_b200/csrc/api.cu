@@ -98,7 +98,6 @@ extern "C" int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out) {
   if (cfg->dynamics == TDMPC_DYN_DRNN) {
     if (cfg->hidden_dim <= 0 || cfg->hidden_dim > 128 || cfg->hidden_dim % 4) { g_create_err = "DRNN: hidden_dim must be a multiple of 4 in (0, 128]"; return TDMPC_ERR_INVALID; }
     if (3 * cfg->hidden_dim > cfg->mlp_dim) { g_create_err = "DRNN: 3*hidden_dim must not exceed mlp_dim"; return TDMPC_ERR_INVALID; }
-    if (cfg->precision != TDMPC_PREC_FP32) { g_create_err = "DRNN (GRU) dynamics are implemented in the fp32 mode only in this build"; return TDMPC_ERR_INVALID; }
   }
   if (cfg->precision == TDMPC_PREC_BF16) {
     const char* why = tc_supported(*cfg);
@@ -277,7 +276,10 @@ static void fill_disc(double gamma, int H, float* disc) {
 
 static int run_rollout(tdmpc_handle* h, const RolloutParams& p, cudaStream_t st) {
   if ((long long)p.B * p.T <= 0) return 0;
-  if (h->cfg.precision == TDMPC_PREC_BF16) {
+  // DRNN in bf16 mode: the value rollouts (all the work) run on tcgen05; the policy rollout (P rows) and the single
+  // post-plan transition keep the fp32 kernel
+  const bool tc = h->cfg.precision == TDMPC_PREC_BF16 && !(h->cfg.dynamics == TDMPC_DYN_DRNN && p.mode != MODE_VALUE);
+  if (tc) {
     int n = launch_rollout_tc(h->tc, p, h->num_sms, st);
     if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "tcgen05 rollout launch failed");
     return check_launch(h, "rollout_tc", n);

@@ -40,6 +40,7 @@ constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
 constexpr int MAX_JOBS = 17 * TDMPC_MAX_H + 16;
 constexpr uint32_t TM_ACC = 0, TM_A = 256;
+constexpr uint32_t TM_X = 256;             // DRNN: n-gate accumulator, inside the (then idle) h1 region
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 232448;
 
@@ -68,12 +69,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return 1.0f - __fdividef(2.0f, 1.0f + e);
 #endif
 }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float4 ldg4(const float* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
 
 __device__ __forceinline__ int job_tiles(const TcModel& m, uint32_t job) {
   const int type = job & 7, chain = (job >> 3) & 7;
   switch (type) {
-    case J_L1: return m.nkb1;
+    case J_L1: return ((job >> 13) & F_A_HS) ? 2 : m.nkb1;
+    case J_G: return m.nkb1 + 2;
+    case J_GH: return 2;
+    case J_GI: return m.nkb1 + m.gi_pad;
     case J_L2: return 8;
     case J_L3: return m.l3rows[chain] == 128 ? 8 : 4;
     case J_QL1: return 4 * m.nkb1;
@@ -84,7 +89,10 @@ __device__ __forceinline__ uint32_t job_first_tile(const TcModel& m, uint32_t jo
   const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3;
   const TcChain& c = m.chain[chain];
   switch (type) {
-    case J_L1: return c.l1_tile + chunk * m.nkb1;
+    case J_L1: return c.l1_tile + chunk * (((job >> 13) & F_A_HS) ? 2 : m.nkb1);
+    case J_G: return m.g_tile[chunk];
+    case J_GH: return m.gh_tile;
+    case J_GI: return m.gi_tile;
     case J_L2: return c.l2_tile + chunk * 8;
     case J_L3: return c.l3_tile;
     case J_QL1: return c.l1_tile;
@@ -103,6 +111,7 @@ __device__ __forceinline__ void sw_store8(uint8_t* base, int row, int k0, const 
   *reinterpret_cast<uint4*>(base + (k0 >> 6) * TILE_BYTES + sw128_offset(row, k0 & 63)) = u;
 }
 
+template <bool DRNN>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcModel& m = kp.m;
@@ -126,7 +135,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint64_t* xs_full = h1_full + 4;       // XS chunk c written to smem  (layer-2 / QL1 epilogue -> layer-3 / QL2 MMAs)
   uint64_t* za_full = xs_full + 4;
   uint64_t* q_full = za_full + 1;        // Q-head accumulator chunk c complete (one barrier per chunk: never two phases ahead)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 4);
+  // DRNN only: hidden-state operand written / n-gate accumulator X complete / X scaled by the reset gate / update gate stored
+  uint64_t* hs_full = q_full + 4;
+  uint64_t* x_full = hs_full + 1;
+  uint64_t* x_scaled = x_full + 1;
+  uint64_t* u_ready = x_scaled + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_ready + 1);
+  // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
+  // holds the GRU state: fp32 [column][row] (conflict-free for thread = row) and the bf16 K-major operand HS (2 k-blocks).
+  float* hf = reinterpret_cast<float*>(xs);
+  uint8_t* hs = xs + 128 * 128 * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -137,6 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) { mbar_init(&h1_full[i], 128); mbar_init(&xs_full[i], 128); }
     mbar_init(za_full, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
+    mbar_init(hs_full, 128); mbar_init(x_full, 1); mbar_init(x_scaled, 128); mbar_init(u_ready, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -224,6 +243,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
         xs_phase ^= 1u << c;
       };
+      uint32_t hs_phase = 0, xsc_phase = 0;
+      const uint32_t hs_addr = smem_u32(hs);
       // one k-block (<= 4 k-steps of 16) with both operands in shared memory
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
         const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
@@ -239,7 +260,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
           if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
+          if (DRNN && (flags & F_WAIT_HS)) { mbar_wait(hs_full, hs_phase, 10); hs_phase ^= 1; tcgen05_fence_after(); }
           if (type == J_L1) {
+            const int b = nbuf; nbuf ^= 1;
+            acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            if (DRNN && (flags & F_A_HS)) {
+              // prior / reward layer 1 of the DRNN model: A = the hidden state h' (K = 128)
+              for (int kb = 0; kb < 2; ++kb) {
+                const uint32_t wt = tile_acquire();
+                if (leader) kblock_ss(d, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
+                tile_release();
+              }
+            } else {
+              for (int kb = 0; kb < m.nkb1; ++kb) {
+                const uint32_t wt = tile_acquire();
+                if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+                tile_release();
+              }
+            }
+            if (leader) umma_commit(&acc_full[b]);
+          } else if (DRNN && type == J_G) {
+            // gate pre-activation: [z,a] W_ih[g]^T + h W_hh[g]^T accumulated into one buffer (no biases, rnns.py:13-14)
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
             tcgen05_fence_after();
@@ -249,7 +292,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
               tile_release();
             }
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint32_t wt = tile_acquire();
+              if (leader) kblock_ss(d, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, false);
+              tile_release();
+            }
             if (leader) umma_commit(&acc_full[b]);
+          } else if (DRNN && type == J_GH) {
+            // gh_n = h W_hh[newval]^T parked in X; the reset-gate epilogue scales it in place
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint32_t wt = tile_acquire();
+              if (leader) kblock_ss(tmem + TM_X, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
+              tile_release();
+            }
+            if (leader) umma_commit(x_full);
+          } else if (DRNN && type == J_GI) {
+            // X = r * gh_n (written by the epilogue) ; X += [z,a] W_ih[newval]^T
+            mbar_wait(x_scaled, xsc_phase, 11); xsc_phase ^= 1;
+            tcgen05_fence_after();
+            for (int kb = 0; kb < m.nkb1; ++kb) {
+              const uint32_t wt = tile_acquire();
+              if (leader) kblock_ss(tmem + TM_X, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), false);
+              tile_release();
+            }
+            for (int i = 0; i < m.gi_pad; ++i) { tile_acquire(); tile_release(); }     // padding tiles keep the ring aligned
+            if (leader) umma_commit(x_full);
           } else if (type == J_L2) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
@@ -297,7 +364,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint32_t d = tmem + TM_ACC + b * 128;
             const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
             const bool half = m.l3rows[chain] == 64;
-            if (half && S == 4 && stage == 0) {
+            if (DRNN && (flags & F_A_TMEM)) {
+              // second (last) Linear of the DRNN prior MLP: A = h1 in TMEM
+              uint32_t wt = 0;
+#pragma unroll
+              for (int kb = 0; kb < 8; ++kb) {
+                if ((kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                if (!half || (kb & 1) == 0) wt = tile_acquire();
+                if (leader) {
+                  const uint32_t blo = umma_desc_lo(wt + ((half && (kb & 1)) ? 8192u : 0u));
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma_ts(d, tmem + TM_A + kb * 32 + ks * 8, umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u);
+                }
+                if (!half || (kb & 1)) tile_release();
+              }
+            } else if (half && S == 4 && stage == 0) {
               // static fast path: 4 tiles (two k-blocks of 64 weight rows each) = one full turn of the ring
 #pragma unroll
               for (int kb = 0; kb < 8; ++kb) {
@@ -387,6 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
     uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
+    uint32_t x_phase = 0, u_phase = 0, ga = 0;     // DRNN: phases of x_full / u_ready, group that owns the reset gate of this step
     float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
     float* x_ssq = xch + (1 * 2 + (grp ^ 1)) * 128;
     float* x_dot = xch + (2 * 2 + (grp ^ 1)) * 128;
@@ -411,6 +493,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const float* act_row = p.actions ? p.actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
       float* pi_row = p.pi_actions ? p.pi_actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
       float G = 0.0f, rlast = 0.0f, dot = 0.0f, q1v = 0.0f;
+
+      if (DRNN && grp == 1) {
+        // initial GRU state of the problem (tdmpc_icem_similarity_drnn.py:202): fp32 copy + bf16 operand.  XS was last
+        // read by the previous tile's Q-head MMAs, which this group has seen complete.
+        const float* h0 = p.hidden0 ? p.hidden0 + (size_t)pb * 128 : nullptr;
+        for (int k0 = 0; k0 < 128; k0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = (h0 && valid) ? __ldg(h0 + k0 + i) : 0.0f;
+            hf[(k0 + i) * 128 + row] = v[i];
+          }
+          sw_store8(hs, row, k0, v);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(hs_full);
+      }
 
       // initial [z0, a0, 0...] row (group 0)
       if (grp == 0) {
@@ -440,12 +539,158 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && threadIdx.x % 128 == 0;
         unsigned long long* trp = kp.trace + ((1 + grp) * MAX_JOBS + j) * 2;
 
+        if (DRNN && type >= J_G) {
+          // ---- NormGRUCell (models/rnns.py:19-29): thread = trajectory, LayerNorm over the 128 gate values in-thread ----
+          if (type == J_GH) continue;                                  // MMAs only
+          if (type == J_G) {
+            const int b = nbuf; nbuf ^= 1;
+            const uint32_t xf = x_phase;
+            if (chunk == 0) { ga = (uint32_t)b; x_phase ^= 1; }
+            if (b != grp) continue;
+            if (tr) trp[0] = clock64();
+            const uint32_t acc = tlane + TM_ACC + b * 128;
+            acc_wait();
+            tcgen05_fence_after();
+            float sum = 0.0f, ssq = 0.0f;
+            tmem_stream(acc, 4, [&](int, uint32_t (&v)[32]) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { const float y = __uint_as_float(v[i]); sum += y; ssq = fmaf(y, y, ssq); }
+            });
+            const float mu = sum * (1.0f / 128.0f);
+            const float rstd = 1.0f / sqrtf(fmaxf(ssq * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
+            const float* lg = m.gln_g[chunk];
+            const float* lb = m.gln_b[chunk];
+            if (chunk == 0) {
+              // reset gate: r = sigmoid(LN_r(.)); the parked gh_n is scaled in place, X <- r * X  (rnns.py:26-28)
+              mbar_wait(x_full, xf, 12);
+              tcgen05_fence_after();
+#pragma unroll 1
+              for (int sg = 0; sg < 4; ++sg) {
+                uint32_t a[32], x[32];
+                tmem_ld32(acc + sg * 32, a);
+                tmem_ld32(tlane + TM_X + sg * 32, x);
+                tmem_wait_ld_dep(a);
+                tmem_wait_ld_dep(x);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 gg = ldg4(lg, sg * 8 + i), bb = ldg4(lb, sg * 8 + i);
+                  x[4 * i] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i]) - mu) * rstd * gg.x + bb.x) * __uint_as_float(x[4 * i]));
+                  x[4 * i + 1] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 1]) - mu) * rstd * gg.y + bb.y) * __uint_as_float(x[4 * i + 1]));
+                  x[4 * i + 2] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 2]) - mu) * rstd * gg.z + bb.z) * __uint_as_float(x[4 * i + 2]));
+                  x[4 * i + 3] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 3]) - mu) * rstd * gg.w + bb.w) * __uint_as_float(x[4 * i + 3]));
+                }
+                tmem_st32(tlane + TM_X + sg * 32, x);
+              }
+              tmem_wait_st();
+              tcgen05_fence_before();
+              mbar_arrive(x_scaled);
+              mbar_arrive(&acc_empty[b]);
+            } else {
+              // update gate: u = sigmoid(LN_u(.)) written back over its accumulator; the n-gate epilogue reads it and
+              // then releases the buffer
+#pragma unroll 1
+              for (int sg = 0; sg < 4; ++sg) {
+                uint32_t a[32];
+                tmem_ld32(acc + sg * 32, a);
+                tmem_wait_ld_dep(a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 gg = ldg4(lg, sg * 8 + i), bb = ldg4(lb, sg * 8 + i);
+                  a[4 * i] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i]) - mu) * rstd * gg.x + bb.x));
+                  a[4 * i + 1] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 1]) - mu) * rstd * gg.y + bb.y));
+                  a[4 * i + 2] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 2]) - mu) * rstd * gg.z + bb.z));
+                  a[4 * i + 3] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 3]) - mu) * rstd * gg.w + bb.w));
+                }
+                tmem_st32(acc + sg * 32, a);
+              }
+              tmem_wait_st();
+              tcgen05_fence_before();
+              mbar_arrive(u_ready);
+            }
+            if (tr) trp[1] = clock64();
+            continue;
+          }
+          // J_GI: n = tanh(LN_n(gi_n + r * gh_n)); h' = u * n + (1 - u) * h  (rnns.py:27-28), by the reset gate's group
+          const uint32_t xf = x_phase, uf = u_phase;
+          x_phase ^= 1; u_phase ^= 1;
+          if (ga != (uint32_t)grp) continue;
+          if (tr) trp[0] = clock64();
+          mbar_wait(x_full, xf, 13);
+          tcgen05_fence_after();
+          float sum = 0.0f, ssq = 0.0f;
+          tmem_stream(tlane + TM_X, 4, [&](int, uint32_t (&v)[32]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float y = __uint_as_float(v[i]); sum += y; ssq = fmaf(y, y, ssq); }
+          });
+          const float mu = sum * (1.0f / 128.0f);
+          const float rstd = 1.0f / sqrtf(fmaxf(ssq * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
+          mbar_wait(u_ready, uf, 14);
+          tcgen05_fence_after();
+          const uint32_t accu = tlane + TM_ACC + (ga ^ 1u) * 128;
+#pragma unroll 1
+          for (int sg = 0; sg < 4; ++sg) {
+            uint32_t x[32], u[32];
+            tmem_ld32(tlane + TM_X + sg * 32, x);
+            tmem_ld32(accu + sg * 32, u);
+            tmem_wait_ld_dep(x);
+            tmem_wait_ld_dep(u);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int k = sg * 32 + c8 * 8 + i;
+                const float nv = tanh_fast((__uint_as_float(x[c8 * 8 + i]) - mu) * rstd * __ldg(m.gln_g[2] + k) + __ldg(m.gln_b[2] + k));
+                const float uu = __uint_as_float(u[c8 * 8 + i]);
+                const float hn = uu * nv + (1.0f - uu) * hf[k * 128 + row];
+                hf[k * 128 + row] = hn;
+                o[i] = hn;
+              }
+              sw_store8(hs, row, sg * 32 + c8 * 8, o);
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(hs_full);
+          tcgen05_fence_before();
+          mbar_arrive(&acc_empty[ga ^ 1u]);
+          if (tr) trp[1] = clock64();
+          continue;
+        }
         if (type <= J_L3) {
           const int b = nbuf; nbuf ^= 1;
           const bool mine = b == grp;
           if (tr && (mine || (type == J_L2 && chain == CH_REW && chunk == 3))) trp[0] = clock64();
           if (type == J_L1) {
             if (!mine) continue;
+            if (DRNN && (flags & F_BN)) {
+              // prior MLP layer 1: Linear, eval-mode BatchNorm1d (folded: y = acc * scale + shift'), ELU -> TMEM h1
+              const float* sc = m.bn_scale + chunk * 128;
+              const float* sh = m.bn_shift + chunk * 128;
+              const uint32_t dst = tlane + TM_A + chunk * 64;
+              float4 x0[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x0[i] = ldg4(sc, i);
+              acc_wait();
+              tcgen05_fence_after();
+              tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int sg, float4 (&x)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = ldg4(sc, sg * 8 + i);
+              }, [&](int sg, uint32_t (&v)[32], float4 (&x)[8]) {
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 t4 = ldg4(sh, sg * 8 + i);
+                  o[2 * i] = pack_bf16x2(elu_fast(fmaf(__uint_as_float(v[4 * i]), x[i].x, t4.x)), elu_fast(fmaf(__uint_as_float(v[4 * i + 1]), x[i].y, t4.y)));
+                  o[2 * i + 1] = pack_bf16x2(elu_fast(fmaf(__uint_as_float(v[4 * i + 2]), x[i].z, t4.z)), elu_fast(fmaf(__uint_as_float(v[4 * i + 3]), x[i].w, t4.w)));
+                }
+                tmem_st16(dst + sg * 16, o);
+              });
+              tmem_wait_st();
+              tcgen05_fence_before();
+              mbar_arrive(&h1_full[chunk]);
+              mbar_arrive(&acc_empty[b]);
+              continue;
+            }
             // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
             const float* bias = ch.b1 + chunk * 128;
             const uint32_t dst = tlane + TM_A + chunk * 64;
@@ -731,17 +976,45 @@ __global__ void pack_tiles_kernel(const float* __restrict__ W, int N, int K, uin
   *reinterpret_cast<uint4*>(dst + tile_off + sw128_offset(r, g * 8)) = u;
 }
 
+__global__ void fold_bias_kernel(const float* b, const float* scale, const float* shift, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaf(b[i], scale[i], shift[i]);
+}
+
 int launch_pack(const float* W, int N, int K, uint8_t* dst, int n_chunks, int nkb, int tile_rows, cudaStream_t st) {
   const long long total = (long long)n_chunks * nkb * tile_rows * 8;
   pack_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, N, K, dst, n_chunks, nkb, tile_rows);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-std::vector<uint32_t> build_jobs(int mode, int H) {
+std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false) {
   std::vector<uint32_t> j;
   auto chain12 = [&](int type, int chain, int t, int first_flags) {
     for (int c = 0; c < 4; ++c) j.push_back(tc_job(type, chain, c, t, c == 0 ? first_flags : 0));
   };
+  if (drnn) {
+    // DSSM.next with GRU dynamics (tdmpc_icem_similarity_drnn.py:56-59): gates, h', prior MLP -> z', reward MLP(h').
+    // Value mode only: the (short) policy rollout and the single post-plan step run on the fp32 kernel.
+    if (mode != MODE_VALUE) return j;
+    for (int t = 0; t < H; ++t) {
+      j.push_back(tc_job(J_G, 0, 0, t, F_WAIT_ZA | (t == 0 ? F_WAIT_HS : 0)));
+      j.push_back(tc_job(J_G, 0, 1, t, 0));
+      j.push_back(tc_job(J_GH, 0, 0, t, 0));
+      j.push_back(tc_job(J_GI, 0, 0, t, 0));
+      for (int c = 0; c < 4; ++c) j.push_back(tc_job(J_L1, CH_DYN, c, t, F_A_HS | F_BN | (c == 0 ? F_WAIT_HS : 0)));
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, F_A_TMEM | (t == H - 1 ? F_LAST_STEP : 0)));
+      for (int c = 0; c < 4; ++c) j.push_back(tc_job(J_L1, CH_REW, c, t, F_A_HS));
+      chain12(J_L2, CH_REW, t, 0);
+    }
+    chain12(J_L1, CH_PI, 0, F_WAIT_ZA);
+    chain12(J_L2, CH_PI, 0, 0);
+    j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
+    j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
+    j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
+    j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+    return j;
+  }
   if (mode == MODE_VALUE) {
     for (int t = 0; t < H; ++t) {
       chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
@@ -778,10 +1051,13 @@ std::vector<uint32_t> build_jobs(int mode, int H) {
 // ------------------------------------------------------------------------------------------------
 const char* tc_supported(const tdmpc_model_cfg& c) {
   if (c.mlp_dim != 512) return "mlp_dim must be 512";
+  if (c.dynamics == TDMPC_DYN_DRNN && c.hidden_dim != 128) return "DRNN: hidden_dim must be 128";
   if (c.latent_dim > 128) return "latent_dim must be <= 128";
   if (c.latent_dim + c.action_dim > 192) return "latent_dim + action_dim must be <= 192";
   return nullptr;
 }
+
+static int gi_pad_tiles(int nkb1) { return (4 - (3 * nkb1 + 6) % 4) % 4; }     // GRU tiles per step: 2 (nkb1 + 2) + 2 + nkb1
 
 static int tc_tiles_total(const tdmpc_model_cfg& c, int* nkb1_out, int l3rows[CH_COUNT]) {
   const int K1p = (c.latent_dim + c.action_dim + 15) & ~15;
@@ -791,11 +1067,15 @@ static int tc_tiles_total(const tdmpc_model_cfg& c, int* nkb1_out, int l3rows[CH
   for (int i = 0; i < CH_COUNT; ++i) l3rows[i] = 0;
   l3rows[CH_DYN] = n3_dyn <= 64 ? 64 : 128;
   l3rows[CH_PI] = n3_pi <= 64 ? 64 : 128;
+  const bool drnn = c.dynamics == TDMPC_DYN_DRNN;
   int tiles = 0;
   for (int ch = 0; ch < CH_COUNT; ++ch) {
-    tiles += 4 * nkb1 + 32;
+    const bool hs_in = drnn && (ch == CH_DYN || ch == CH_REW);         // layer 1 reads the hidden state (K = 128)
+    tiles += 4 * (hs_in ? 2 : nkb1);
+    if (!(drnn && ch == CH_DYN)) tiles += 32;                           // the prior MLP has no 512 x 512 layer
     if (l3rows[ch]) tiles += l3rows[ch] == 128 ? 8 : 4;
   }
+  if (drnn) tiles += 2 * (nkb1 + 2) + 2 + nkb1 + gi_pad_tiles(nkb1);
   return tiles;
 }
 
@@ -808,7 +1088,7 @@ static size_t jobs_bytes_total() {
 
 size_t tc_arena_bytes(const tdmpc_model_cfg& c) {
   int nkb1, l3rows[CH_COUNT];
-  return (size_t)tc_tiles_total(c, &nkb1, l3rows) * TILE_BYTES + jobs_bytes_total() + 1024;
+  return (size_t)tc_tiles_total(c, &nkb1, l3rows) * TILE_BYTES + jobs_bytes_total() + 512 * sizeof(float) + 1024;
 }
 
 int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m32, void* arena, TcModel* out, cudaStream_t st) {
@@ -825,10 +1105,12 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
   if (cudaMemsetAsync(base, 0, (size_t)tiles * TILE_BYTES, st) != cudaSuccess) return -1;
 
-  const float* W1[CH_COUNT] = {w.dyn_w[0], w.rew_w[0], w.pi_w[0], w.q_w[0][0], w.q_w[1][0]};
-  const float* W2[CH_COUNT] = {w.dyn_w[1], w.rew_w[1], w.pi_w[1], w.q_w[0][1], w.q_w[1][1]};
-  const float* W3[CH_COUNT] = {w.dyn_w[2], nullptr, w.pi_w[2], nullptr, nullptr};
-  const int K1[CH_COUNT] = {L + A, L + A, L, L + A, L + A};
+  const bool drnn = c.dynamics == TDMPC_DYN_DRNN;
+  const int Hd = 128;
+  const float* W1[CH_COUNT] = {drnn ? w.prior_w[0] : w.dyn_w[0], w.rew_w[0], w.pi_w[0], w.q_w[0][0], w.q_w[1][0]};
+  const float* W2[CH_COUNT] = {drnn ? nullptr : w.dyn_w[1], w.rew_w[1], w.pi_w[1], w.q_w[0][1], w.q_w[1][1]};
+  const float* W3[CH_COUNT] = {drnn ? w.prior_w[1] : w.dyn_w[2], nullptr, w.pi_w[2], nullptr, nullptr};
+  const int K1[CH_COUNT] = {drnn ? Hd : L + A, drnn ? Hd : L + A, L, L + A, L + A};
   const int N3[CH_COUNT] = {L, 0, A, 0, 0};
   const LinearT* lin[CH_COUNT] = {m32.dyn, m32.rew, m32.pi, m32.q[0], m32.q[1]};
 
@@ -836,30 +1118,65 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   uint32_t tile = 0;
   for (int ch = 0; ch < CH_COUNT; ++ch) {
     TcChain& t = m.chain[ch];
+    const int nkb = (drnn && (ch == CH_DYN || ch == CH_REW)) ? 2 : nkb1;
     t.l1_tile = tile;
-    if (launch_pack(W1[ch], 512, K1[ch], base + (size_t)tile * TILE_BYTES, 4, nkb1, 128, st) < 0) return -1;
-    tile += 4 * nkb1; ++launches;
+    if (launch_pack(W1[ch], 512, K1[ch], base + (size_t)tile * TILE_BYTES, 4, nkb, 128, st) < 0) return -1;
+    tile += 4 * nkb; ++launches;
     t.l2_tile = tile;
-    if (launch_pack(W2[ch], 512, 512, base + (size_t)tile * TILE_BYTES, 4, 8, 128, st) < 0) return -1;
-    tile += 32; ++launches;
+    if (W2[ch]) {
+      if (launch_pack(W2[ch], 512, 512, base + (size_t)tile * TILE_BYTES, 4, 8, 128, st) < 0) return -1;
+      tile += 32; ++launches;
+    }
     t.l3_tile = tile;
     if (W3[ch]) {
       if (launch_pack(W3[ch], N3[ch], 512, base + (size_t)tile * TILE_BYTES, 1, 8, m.l3rows[ch], st) < 0) return -1;
       tile += m.l3rows[ch] == 128 ? 8 : 4; ++launches;
     }
-    t.b1 = lin[ch][0].b; t.b2 = lin[ch][1].b; t.b3 = lin[ch][2].b;
-    t.w3 = N3[ch] == 0 ? lin[ch][2].wt : nullptr;      // [512][1] transposed == the weight row itself
+    if (drnn && ch == CH_DYN) {
+      t.b1 = nullptr; t.b2 = nullptr; t.b3 = m32.prior[1].b; t.w3 = nullptr;      // layer-1 bias lives in bn_shift
+    } else {
+      t.b1 = lin[ch][0].b; t.b2 = lin[ch][1].b; t.b3 = lin[ch][2].b;
+      t.w3 = N3[ch] == 0 ? lin[ch][2].wt : nullptr;      // [512][1] transposed == the weight row itself
+    }
     if (ch >= CH_Q1) {
       for (int i = 0; i < 2; ++i) { t.ln_g[i] = m32.q_ln[ch - CH_Q1][i].g; t.ln_b[i] = m32.q_ln[ch - CH_Q1][i].b; }
     }
   }
+  m.drnn = drnn ? 1 : 0;
+  if (drnn) {
+    // gate weights, one 128-row chunk per gate (reset, update, newval), in the order the jobs consume them:
+    //   J_G(g): W_ih[g] then W_hh[g];  J_GH: W_hh[newval];  J_GI: W_ih[newval] (+ padding tiles)
+    const int KI = L + A;
+    for (int g = 0; g < 2; ++g) {
+      m.g_tile[g] = tile;
+      if (launch_pack(w.gru_w_ih + (size_t)g * Hd * KI, Hd, KI, base + (size_t)tile * TILE_BYTES, 1, nkb1, 128, st) < 0) return -1;
+      tile += nkb1;
+      if (launch_pack(w.gru_w_hh + (size_t)g * Hd * Hd, Hd, Hd, base + (size_t)tile * TILE_BYTES, 1, 2, 128, st) < 0) return -1;
+      tile += 2; launches += 2;
+    }
+    m.gh_tile = tile;
+    if (launch_pack(w.gru_w_hh + (size_t)2 * Hd * Hd, Hd, Hd, base + (size_t)tile * TILE_BYTES, 1, 2, 128, st) < 0) return -1;
+    tile += 2;
+    m.gi_tile = tile;
+    if (launch_pack(w.gru_w_ih + (size_t)2 * Hd * KI, Hd, KI, base + (size_t)tile * TILE_BYTES, 1, nkb1, 128, st) < 0) return -1;
+    m.gi_pad = gi_pad_tiles(nkb1);
+    tile += nkb1 + m.gi_pad; launches += 2;
+    for (int g = 0; g < 3; ++g) { m.gln_g[g] = m32.gru_ln[g].g; m.gln_b[g] = m32.gru_ln[g].b; }
+    // eval-mode BatchNorm after the prior's first Linear: y = (acc + b) * scale + shift = acc * scale + (b * scale + shift)
+    float* shiftp = reinterpret_cast<float*>(base + (size_t)tiles * TILE_BYTES + jobs_bytes_total());
+    fold_bias_kernel<<<2, 256, 0, st>>>(m32.prior[0].b, m32.prior[0].post_scale, m32.prior[0].post_shift, 512, shiftp);
+    ++launches;
+    m.bn_scale = m32.prior[0].post_scale;
+    m.bn_shift = shiftp;
+  }
+  if ((int)tile != tiles) return -1;
   // job programs for every (mode, horizon)
   uint32_t* jdst = reinterpret_cast<uint32_t*>(base + (size_t)tiles * TILE_BYTES);
   std::vector<uint32_t> all;
   size_t off = 0;
   for (int mode = 0; mode < 2; ++mode)
     for (int H = 1; H <= TDMPC_MAX_H; ++H) {
-      std::vector<uint32_t> j = build_jobs(mode, H);
+      std::vector<uint32_t> j = build_jobs(mode, H, drnn);
       m.jobs[mode][H] = jdst + off;
       m.njobs[mode][H] = (int)j.size();
       j.resize((j.size() + 3) & ~(size_t)3, 0);
@@ -870,14 +1187,15 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 17) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 21) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
   if (stages < 2) return -1;
   m.stages = stages;
   m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
-  if (cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem_bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem_bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem_bytes) != cudaSuccess) return -1;
   *out = m;
   return launches;
 }
@@ -900,6 +1218,8 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) kp.producers = v; }
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
-  rollout_tc_kernel<<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  if (kp.njobs <= 0) return -1;
+  if (m.drnn) rollout_tc_kernel<true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  else rollout_tc_kernel<false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   return 1;
 }

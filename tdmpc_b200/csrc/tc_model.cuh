@@ -13,11 +13,22 @@ enum TcJobType {
   J_L2 = 1,    // h1 (tmem)     x W2 chunk -> 128 cols;  epilogue: +b, ELU  -> XS chunk (dyn, pi) | dot with w3 (reward)
   J_L3 = 2,    // h2 (smem XS)  x W3       -> n3 cols;   epilogue: z' -> ZA (dyn) | tanh+noise -> action -> ZA (pi)
   J_QL1 = 3,   // [z,a] (smem)  x W1       -> 512 cols;  epilogue: +b, LayerNorm, tanh -> XS
-  J_QL2 = 4    // h1 (smem XS)  x W2       -> 512 cols;  epilogue: +b, LayerNorm, ELU, dot with w3 -> Q
+  J_QL2 = 4,   // h1 (smem XS)  x W2       -> 512 cols;  epilogue: +b, LayerNorm, ELU, dot with w3 -> Q
+  // DRNN (GRU latent dynamics, models/rnns.py:19-29): the gate pre-activations.  chunk = gate (0 reset, 1 update).
+  J_G = 5,     // [z,a] x W_ih[g] + h (smem HS) x W_hh[g] -> one accumulator; epilogue: LayerNorm (in-thread), sigmoid;
+               //   reset: multiplies the parked gh_n in place (X <- r * X);  update: u written back over the accumulator
+  J_GH = 6,    // h x W_hh[newval] -> X (128 TMEM columns of the h1 region); no epilogue
+  J_GI = 7     // X += [z,a] x W_ih[newval];  epilogue: n = tanh(LN(X)), h' = u n + (1-u) h -> fp32 state + bf16 operand HS
 };
-enum TcJobFlags { F_WAIT_ZA = 1, F_LAST_STEP = 2, F_TERMINAL = 4 };
+enum TcJobFlags {
+  F_WAIT_ZA = 1, F_LAST_STEP = 2, F_TERMINAL = 4,
+  F_WAIT_HS = 8,     // MMA: first consumer of a freshly written hidden-state operand HS
+  F_A_HS = 16,       // J_L1: A operand = HS (K = hidden_dim = 128, two k-blocks) instead of [z,a]
+  F_A_TMEM = 32,     // J_L3: A operand = h1 in TMEM (TS) instead of XS (the DRNN prior MLP has two layers only)
+  F_BN = 64          // J_L1 epilogue: eval-mode BatchNorm folded to y = acc * scale + shift before the ELU
+};
 
-// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,16)
+// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,20)
 __host__ __device__ inline uint32_t tc_job(int type, int chain, int chunk, int t, int flags) {
   return (uint32_t)type | ((uint32_t)chain << 3) | ((uint32_t)chunk << 6) | ((uint32_t)t << 8) | ((uint32_t)flags << 13);
 }
@@ -41,6 +52,15 @@ struct TcModel {
   int njobs[2][TDMPC_MAX_H + 1];
   int stages;                  // weight ring depth that fits in shared memory
   size_t smem_bytes;
+  // DRNN (TDMPC_DYN_DRNN): chain CH_DYN is the prior MLP (layer 1: K = hidden_dim, layer 3 slot = its second Linear),
+  // chain CH_REW's layer 1 reads the hidden state; gate weights live in their own tiles.
+  int drnn;
+  uint32_t g_tile[2];          // J_G  gate g: nkb1 tiles of W_ih[g] followed by 2 tiles of W_hh[g]
+  uint32_t gh_tile;            // J_GH: 2 tiles of W_hh[newval]
+  uint32_t gi_tile;            // J_GI: nkb1 tiles of W_ih[newval] (+ gi_pad padding tiles that keep the ring aligned)
+  int gi_pad;
+  const float* gln_g[3]; const float* gln_b[3];    // LayerNorm of the reset / update / newval gates (eps 1e-3)
+  const float* bn_scale; const float* bn_shift;    // prior_mlp.1 folded: y = acc * scale + (b * scale + shift)
 };
 
 const char* tc_supported(const tdmpc_model_cfg& c);     // nullptr when the shape is supported

@@ -484,8 +484,6 @@ def accelerate(agent, precision="bf16"):
     cfg = agent.cfg
     sd = agent.model.state_dict()
     drnn = hasattr(agent.model._dynamics, "gru_cell")
-    if drnn and precision != "fp32":
-        raise RuntimeError("the GRU (DRNN) dynamics are available in the fp32 mode only")
     agent._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
                              enc_layernorm="_encoder.3.weight" in sd, precision=precision, device=agent.device,
                              dynamics="drnn" if drnn else "mlp", hidden_dim=cfg.hidden_dim if drnn else 0)

@@ -724,3 +724,43 @@ def test_full_size_properties_cfg3():
     assert torch.isfinite(a_a).all() and a_a.abs().max() <= 1.0 and torch.isfinite(m_a).all()
     assert (m_a[:, 1] >= cfg.min_std - 1e-6).all() and (m_a[:, 1] <= 2.0).all()        # current_std inside its clamp
     assert not torch.equal(a_a[0], a_a[1])
+
+
+@pytest.mark.parametrize("cfg_name,seed", [("tiny_drnn", 6), ("cfg5", 7)])
+def test_drnn_bf16_first_iteration_matches_quantised_oracle(cfg_name, seed):
+    """GRU dynamics on the tcgen05 path (value rollouts; the policy rollout and the post-plan step stay fp32): iteration-0
+    values of the SAMPLED rows (identical action rows on both sides) against the oracle run with the same bf16 operands,
+    over two planning steps with the hidden state and the carried planner state teacher-forced from the oracle."""
+    from tdmpc_b200 import TdICemSimDssm
+    cfg = synth.make_cfg(cfg_name, device="cuda", precision="bf16")
+    sd = synth.make_drnn_weights(cfg, seed)
+    agent = TdICemSimDssm(cfg)
+    agent.model.load_state_dict(sd, strict=False)
+    agent.model.eval()
+    agent.std = cfg.min_std
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    A = cfg.action_dim
+    hidden_o = torch.zeros(1, cfg.hidden_dim)
+    for s in range(2):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        t0 = s == 0
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_drnn_sizes(cfg, O.linear_schedule(cfg.regularization_schedule, 10 ** 6), have, t0)
+        H = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, 10 ** 6)))
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have and not t0, single_beta=True)
+        if have:
+            agent._elite_actions = state["_elite_actions"].cuda()
+            agent._prev_mean = state["_prev_mean"].cuda()
+        hidden_in = hidden_o.clone()
+        a_o, hidden_o, m_o, taps_o = O.plan_icem_drnn(sd, cfg, obs, hidden_o, eval_mode=True, step=10 ** 6, t0=t0, state=state, noise=nz, quant=True)
+        agent._inject_noise = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in synth.icem_noise_abi(nz, sizes, H, A).items()}
+        agent._want_taps = True
+        a, hidden_g, m = agent.plan(obs, hidden_in.cuda(), eval_mode=True, step=10 ** 6, t0=t0)
+        torch.cuda.synchronize()
+        N0, E0, P0 = sizes[0]
+        v_o = taps_o["values"][0][:N0 + E0]
+        v_g = agent._last_taps["values"][0, 0, :N0 + E0].cpu()
+        err = (v_g - v_o).abs() / v_o.abs().max()
+        print(f"drnn bf16 {cfg_name} step {s}: it0 value rel err median {err.median().item():.2e} p90 {err.quantile(0.9).item():.2e} max {err.max().item():.2e}")
+        assert err.median().item() <= TOL_BF16 and (err <= TOL_BF16).float().mean().item() >= 0.75
+        assert torch.isfinite(a).all() and a.abs().max() <= 1.0 and torch.isfinite(hidden_g).all()
