@@ -276,9 +276,9 @@ static void fill_disc(double gamma, int H, float* disc) {
 
 static int run_rollout(tdmpc_handle* h, const RolloutParams& p, cudaStream_t st) {
   if ((long long)p.B * p.T <= 0) return 0;
-  // DRNN in bf16 mode: the value rollouts (all the work) run on tcgen05; the policy rollout (P rows) and the single
-  // post-plan transition keep the fp32 kernel
-  const bool tc = h->cfg.precision == TDMPC_PREC_BF16 && !(h->cfg.dynamics == TDMPC_DYN_DRNN && p.mode != MODE_VALUE);
+  // DRNN in bf16 mode: value and policy rollouts run on tcgen05 (the policy rollout needs action_dim <= 8, else its job
+  // list is empty); the single post-plan transition keeps the fp32 kernel
+  const bool tc = h->cfg.precision == TDMPC_PREC_BF16 && p.mode != MODE_STEP && h->tc.njobs[p.mode][p.H] > 0;
   if (tc) {
     int n = launch_rollout_tc(h->tc, p, h->num_sms, st);
     if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "tcgen05 rollout launch failed");

@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const float* act_row = p.actions ? p.actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
       float* pi_row = p.pi_actions ? p.pi_actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
       float G = 0.0f, rlast = 0.0f, dot = 0.0f, q1v = 0.0f;
+      float pd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // DRNN policy rollout: partial outputs of the last policy Linear
 
       if (DRNN && grp == 1) {
         // initial GRU state of the problem (tdmpc_icem_similarity_drnn.py:202): fp32 copy + bf16 operand.  XS was last
@@ -714,14 +715,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             mbar_arrive(&acc_empty[b]);
             if (tr) trp[1] = clock64();
           } else if (type == J_L2) {
-            const bool to_xs = chain != CH_REW;
+            const bool pidot = DRNN && (flags & F_PIDOT);
+            const bool to_xs = chain != CH_REW && !pidot;
             if (mine) {
               const float* bias = ch.b2 + chunk * 128;
               float4 x0[8];
               load8(bias, 0, x0);
               acc_wait();
               tcgen05_fence_after();
-              if (to_xs) {
+              if (pidot) {
+                // last policy Linear (A <= 8 rows) as dot products: h2 and W3 rounded to bf16 like the MMA operands would be
+                const float* w3q = m.pi_w3q + chunk * 128;
+                tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                                [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float h0 = __bfloat162float(__float2bfloat16(elu_fast(__uint_as_float(v[4 * i]) + x[i].x)));
+                    const float h1 = __bfloat162float(__float2bfloat16(elu_fast(__uint_as_float(v[4 * i + 1]) + x[i].y)));
+                    const float h2 = __bfloat162float(__float2bfloat16(elu_fast(__uint_as_float(v[4 * i + 2]) + x[i].z)));
+                    const float h3 = __bfloat162float(__float2bfloat16(elu_fast(__uint_as_float(v[4 * i + 3]) + x[i].w)));
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+                      if (a < A) {
+                        const float4 w = ldg4(w3q + a * 512, s * 8 + i);
+                        pd[a] = fmaf(h0, w.x, pd[a]); pd[a] = fmaf(h1, w.y, pd[a]); pd[a] = fmaf(h2, w.z, pd[a]); pd[a] = fmaf(h3, w.w, pd[a]);
+                      }
+                  }
+                });
+              } else if (to_xs) {
                 tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
@@ -754,7 +775,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               tcgen05_fence_before();
               mbar_arrive(&acc_empty[b]);
             }
-            if (!to_xs && chunk == 3) {
+            if (pidot) {
+              if (chunk == 3) {
+                // a = clamp(tanh(W3 h2 + b3) + clip(eps * std)): combine the two groups' partial sums in group 0 (qcs is idle
+                // outside the Q phase), write the action into [z,a] and the output row  (tdmpc.py:39-45, helper.py:86-96)
+#pragma unroll
+                for (int a = 0; a < 8; ++a) if (a < A) qcs[(a * 2 + grp) * 128 + row] = pd[a];
+                epi_bar_sync();
+                if (grp == 0) {
+                  const uint64_t nbase = p.noise_base + (uint64_t)t * p.noise_tstride + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
+#pragma unroll
+                  for (int a = 0; a < 8; ++a)
+                    if (a < A) {
+                      float x = 0.0f;
+                      if (valid) {
+                        const float mu = tanhf((pd[a] + qcs[(a * 2 + 1) * 128 + row]) + __ldg(m.chain[CH_PI].b3 + a));
+                        x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
+                        pi_row[(size_t)t * A + a] = x;
+                      }
+                      if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
+                    }
+                  if (!(flags & F_LAST_STEP)) { fence_proxy_async_smem(); mbar_arrive(za_full); }
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) pd[a] = 0.0f;
+                epi_bar_sync();                  // qcs may be rewritten by the next exchange
+              }
+            } else if (!to_xs && chunk == 3) {
               // both groups hold a partial reward dot product of this row: combine in group 0
               m_dot[row] = dot;
               epi_bar_sync();
@@ -976,6 +1023,11 @@ __global__ void pack_tiles_kernel(const float* __restrict__ W, int N, int K, uin
   *reinterpret_cast<uint4*>(dst + tile_off + sw128_offset(r, g * 8)) = u;
 }
 
+__global__ void round_bf16_kernel(const float* w, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(__float2bfloat16(w[i]));
+}
+
 __global__ void fold_bias_kernel(const float* b, const float* scale, const float* shift, int n, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = fmaf(b[i], scale[i], shift[i]);
@@ -987,7 +1039,7 @@ int launch_pack(const float* W, int N, int K, uint8_t* dst, int n_chunks, int nk
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false) {
+std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) {
   std::vector<uint32_t> j;
   auto chain12 = [&](int type, int chain, int t, int first_flags) {
     for (int c = 0; c < 4; ++c) j.push_back(tc_job(type, chain, c, t, c == 0 ? first_flags : 0));
@@ -995,7 +1047,26 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false) {
   if (drnn) {
     // DSSM.next with GRU dynamics (tdmpc_icem_similarity_drnn.py:56-59): gates, h', prior MLP -> z', reward MLP(h').
     // Value mode only: the (short) policy rollout and the single post-plan step run on the fp32 kernel.
-    if (mode != MODE_VALUE) return j;
+    auto gru_prior = [&](int t, bool last) {
+      j.push_back(tc_job(J_G, 0, 0, t, F_WAIT_ZA | (t == 0 ? F_WAIT_HS : 0)));
+      j.push_back(tc_job(J_G, 0, 1, t, 0));
+      j.push_back(tc_job(J_GH, 0, 0, t, 0));
+      j.push_back(tc_job(J_GI, 0, 0, t, 0));
+      for (int c = 0; c < 4; ++c) j.push_back(tc_job(J_L1, CH_DYN, c, t, F_A_HS | F_BN | (c == 0 ? F_WAIT_HS : 0)));
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, F_A_TMEM | (last ? F_LAST_STEP : 0)));
+    };
+    if (mode != MODE_VALUE) {
+      // policy rollout (tdmpc_icem_similarity_drnn.py:196-200): a_t = pi(z), then the GRU step.  Needs the dot-product
+      // policy head (A <= 8); otherwise the list stays empty and the fp32 kernel runs this (short) part.
+      if (A > 8) return j;
+      for (int t = 0; t < H; ++t) {
+        const bool last = t == H - 1;
+        chain12(J_L1, CH_PI, t, F_WAIT_ZA);
+        for (int c = 0; c < 4; ++c) j.push_back(tc_job(J_L2, CH_PI, c, t, F_PIDOT | (last ? F_LAST_STEP : 0)));
+        if (!last) gru_prior(t, false);
+      }
+      return j;
+    }
     for (int t = 0; t < H; ++t) {
       j.push_back(tc_job(J_G, 0, 0, t, F_WAIT_ZA | (t == 0 ? F_WAIT_HS : 0)));
       j.push_back(tc_job(J_G, 0, 1, t, 0));
@@ -1088,7 +1159,7 @@ static size_t jobs_bytes_total() {
 
 size_t tc_arena_bytes(const tdmpc_model_cfg& c) {
   int nkb1, l3rows[CH_COUNT];
-  return (size_t)tc_tiles_total(c, &nkb1, l3rows) * TILE_BYTES + jobs_bytes_total() + 512 * sizeof(float) + 1024;
+  return (size_t)tc_tiles_total(c, &nkb1, l3rows) * TILE_BYTES + jobs_bytes_total() + (512 + 8 * 512) * sizeof(float) + 1024;
 }
 
 int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m32, void* arena, TcModel* out, cudaStream_t st) {
@@ -1168,6 +1239,10 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
     ++launches;
     m.bn_scale = m32.prior[0].post_scale;
     m.bn_shift = shiftp;
+    float* w3q = shiftp + 512;
+    if (cudaMemsetAsync(w3q, 0, 8 * 512 * sizeof(float), st) != cudaSuccess) return -1;
+    if (A <= 8) { round_bf16_kernel<<<(A * 512 + 255) / 256, 256, 0, st>>>(w.pi_w[2], A * 512, w3q); ++launches; }
+    m.pi_w3q = w3q;
   }
   if ((int)tile != tiles) return -1;
   // job programs for every (mode, horizon)
@@ -1176,7 +1251,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   size_t off = 0;
   for (int mode = 0; mode < 2; ++mode)
     for (int H = 1; H <= TDMPC_MAX_H; ++H) {
-      std::vector<uint32_t> j = build_jobs(mode, H, drnn);
+      std::vector<uint32_t> j = build_jobs(mode, H, drnn, A);
       m.jobs[mode][H] = jdst + off;
       m.njobs[mode][H] = (int)j.size();
       j.resize((j.size() + 3) & ~(size_t)3, 0);

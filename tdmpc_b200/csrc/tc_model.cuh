@@ -25,10 +25,12 @@ enum TcJobFlags {
   F_WAIT_HS = 8,     // MMA: first consumer of a freshly written hidden-state operand HS
   F_A_HS = 16,       // J_L1: A operand = HS (K = hidden_dim = 128, two k-blocks) instead of [z,a]
   F_A_TMEM = 32,     // J_L3: A operand = h1 in TMEM (TS) instead of XS (the DRNN prior MLP has two layers only)
-  F_BN = 64          // J_L1 epilogue: eval-mode BatchNorm folded to y = acc * scale + shift before the ELU
+  F_BN = 64,         // J_L1 epilogue: eval-mode BatchNorm folded to y = acc * scale + shift before the ELU
+  F_PIDOT = 128      // J_L2 of the policy chain: the last Linear (A <= 8 outputs) as fp32 dot products in the epilogue (DRNN
+                     //   policy rollout: XS holds the GRU state, so there is no h2 operand for a layer-3 MMA)
 };
 
-// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,20)
+// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,21)
 __host__ __device__ inline uint32_t tc_job(int type, int chain, int chunk, int t, int flags) {
   return (uint32_t)type | ((uint32_t)chain << 3) | ((uint32_t)chunk << 6) | ((uint32_t)t << 8) | ((uint32_t)flags << 13);
 }
@@ -61,6 +63,7 @@ struct TcModel {
   int gi_pad;
   const float* gln_g[3]; const float* gln_b[3];    // LayerNorm of the reset / update / newval gates (eps 1e-3)
   const float* bn_scale; const float* bn_shift;    // prior_mlp.1 folded: y = acc * scale + (b * scale + shift)
+  const float* pi_w3q;         // [8][512] fp32 copy of the bf16-rounded last policy Linear (rows >= A zero), F_PIDOT
 };
 
 const char* tc_supported(const tdmpc_model_cfg& c);     // nullptr when the shape is supported

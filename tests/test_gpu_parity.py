@@ -764,3 +764,30 @@ def test_drnn_bf16_first_iteration_matches_quantised_oracle(cfg_name, seed):
         print(f"drnn bf16 {cfg_name} step {s}: it0 value rel err median {err.median().item():.2e} p90 {err.quantile(0.9).item():.2e} max {err.max().item():.2e}")
         assert err.median().item() <= TOL_BF16 and (err <= TOL_BF16).float().mean().item() >= 0.75
         assert torch.isfinite(a).all() and a.abs().max() <= 1.0 and torch.isfinite(hidden_g).all()
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny_drnn", "cfg5"])
+def test_drnn_bf16_policy_rollout_matches_quantised_oracle(cfg_name):
+    """Policy rollout through the GRU dynamics on the tcgen05 path (dot-product policy head, GRU step, prior MLP) against the
+    oracle with the same bf16 operands; initial hidden state zero (tdmpc_pi_rollout has no hidden argument)."""
+    from tdmpc_b200 import Planner
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_drnn_weights(cfg, 2)
+    pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, enc_layernorm=True, precision="bf16",
+                 dynamics="drnn", hidden_dim=cfg.hidden_dim)
+    pl.sync_weights({k: v.cuda() for k, v in sd.items()})
+    H, P, A = cfg.horizon, 300, cfg.action_dim
+    rs = np.random.RandomState(4)
+    obs = synth.make_obs(cfg, 9)
+    z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
+    eps = torch.from_numpy(rs.standard_normal((H, P, A)).astype(np.float32))
+    pi_o = torch.empty(H, P, A)
+    z, hdn = z0.repeat(P, 1), torch.zeros(P, cfg.hidden_dim)
+    for t in range(H):
+        pi_o[t] = O.told_pi(sd, z, cfg.min_std, eps[t], True)
+        z, hdn, _ = O.dssm_next(sd, z, pi_o[t], hdn, True)
+    pi_g = pl.pi_rollout(z0.cuda(), P, H, min_std=cfg.min_std, noise_pi=eps.unsqueeze(0))
+    torch.cuda.synchronize()
+    err = (pi_g[0].permute(1, 0, 2).cpu() - pi_o).abs()
+    print(f"drnn bf16 pi rollout {cfg_name}: action abs err median {err.median().item():.2e} p90 {err.flatten().quantile(0.9).item():.2e} max {err.max().item():.2e}")
+    assert err.median().item() <= TOL_BF16 and (err <= 10 * TOL_BF16).float().mean().item() >= 0.9
