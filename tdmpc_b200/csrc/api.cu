@@ -150,7 +150,7 @@ extern "C" int32_t tdmpc_abi_sizes(int32_t* out, int32_t n) {
   return m;
 }
 extern "C" uint64_t tdmpc_launch_count(const tdmpc_handle* h) { return h ? h->launches : 0; }
-extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;select=bitonic"; }
+extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;dynamics=mlp,gru;select=bitonic"; }
 
 extern "C" int tdmpc_reserve(tdmpc_handle* h, int32_t batch, int32_t max_rows, int32_t max_horizon, int32_t max_elites) {
   if (!h) return TDMPC_ERR_INVALID;
