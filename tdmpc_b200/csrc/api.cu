@@ -141,6 +141,13 @@ int tc_trace_slots();
 // clock64 stamps [role][job][start,end] of one tile of the tcgen05 rollout kernel; NULL disables.
 extern "C" __attribute__((visibility("default"))) int tdmpc_debug_set_trace(void* dev_buf) { tc_set_trace((unsigned long long*)dev_buf); return tc_trace_slots(); }
 
+// Debug hook (not part of the public header): copies the job program of (mode, horizon) to the host; returns its length.
+extern "C" __attribute__((visibility("default"))) int tdmpc_debug_jobs(tdmpc_handle* h, int mode, int horizon, uint32_t* out, int cap) {
+  if (!h || !h->weights_set || h->cfg.precision != TDMPC_PREC_BF16 || mode < 0 || mode > 1 || horizon < 1 || horizon > TDMPC_MAX_H) return -1;
+  const int n = h->tc.njobs[mode][horizon];
+  if (out && cap >= n) cudaMemcpy(out, h->tc.jobs[mode][horizon], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
+  return n;
+}
 extern "C" int32_t tdmpc_abi_sizes(int32_t* out, int32_t n) {
   const int32_t v[] = {(int32_t)sizeof(tdmpc_model_cfg), (int32_t)sizeof(tdmpc_weights), (int32_t)sizeof(tdmpc_plan_args),
                        (int32_t)offsetof(tdmpc_plan_args, obs), (int32_t)offsetof(tdmpc_plan_args, seed),

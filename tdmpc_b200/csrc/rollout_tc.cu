@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) { mbar_init(&h1_full[i], 128); mbar_init(&xs_full[i], 128); }
     mbar_init(za_full, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
-    mbar_init(hs_full, 128); mbar_init(x_full, 1); mbar_init(x_scaled, 128); mbar_init(u_ready, 128);
+    mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(x_scaled, 128); mbar_init(u_ready, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -495,11 +495,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       float G = 0.0f, rlast = 0.0f, dot = 0.0f, q1v = 0.0f;
       float pd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // DRNN policy rollout: partial outputs of the last policy Linear
 
-      if (DRNN && grp == 1) {
-        // initial GRU state of the problem (tdmpc_icem_similarity_drnn.py:202): fp32 copy + bf16 operand.  XS was last
-        // read by the previous tile's Q-head MMAs, which this group has seen complete.
+      if (DRNN) {
+        // initial GRU state of the problem (tdmpc_icem_similarity_drnn.py:202): fp32 copy + bf16 operand, 64 columns per
+        // group.  XS was last read by the previous tile's Q-head MMAs, which both groups have seen complete.
         const float* h0 = p.hidden0 ? p.hidden0 + (size_t)pb * 128 : nullptr;
-        for (int k0 = 0; k0 < 128; k0 += 8) {
+        for (int k0 = grp * 64; k0 < grp * 64 + 64; k0 += 8) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -611,49 +611,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             if (tr) trp[1] = clock64();
             continue;
           }
-          // J_GI: n = tanh(LN_n(gi_n + r * gh_n)); h' = u * n + (1 - u) * h  (rnns.py:27-28), by the reset gate's group
+          // J_GI: n = tanh(LN_n(gi_n + r * gh_n)); h' = u * n + (1 - u) * h  (rnns.py:27-28).  Both groups work on it, 64
+          // columns each (it sits on the step's critical path); the LayerNorm statistics are exchanged through `xch`.
           const uint32_t xf = x_phase, uf = u_phase;
           x_phase ^= 1; u_phase ^= 1;
-          if (ga != (uint32_t)grp) continue;
           if (tr) trp[0] = clock64();
+          const int c0 = grp * 64;
           mbar_wait(x_full, xf, 13);
           tcgen05_fence_after();
           float sum = 0.0f, ssq = 0.0f;
-          tmem_stream(tlane + TM_X, 4, [&](int, uint32_t (&v)[32]) {
+          tmem_stream(tlane + TM_X + c0, 2, [&](int, uint32_t (&v)[32]) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float y = __uint_as_float(v[i]); sum += y; ssq = fmaf(y, y, ssq); }
           });
-          const float mu = sum * (1.0f / 128.0f);
-          const float rstd = 1.0f / sqrtf(fmaxf(ssq * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
+          m_sum[row] = sum; m_ssq[row] = ssq;
+          epi_bar_sync();
+          const float s0 = grp == 0 ? sum : x_sum[row], s1 = grp == 0 ? x_sum[row] : sum;        // same order in both groups
+          const float q0 = grp == 0 ? ssq : x_ssq[row], q1 = grp == 0 ? x_ssq[row] : ssq;
+          const float mu = (s0 + s1) * (1.0f / 128.0f);
+          const float rstd = 1.0f / sqrtf(fmaxf((q0 + q1) * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
           mbar_wait(u_ready, uf, 14);
           tcgen05_fence_after();
-          const uint32_t accu = tlane + TM_ACC + (ga ^ 1u) * 128;
+          const uint32_t accu = tlane + TM_ACC + (ga ^ 1u) * 128 + c0;
 #pragma unroll 1
-          for (int sg = 0; sg < 4; ++sg) {
+          for (int sg = 0; sg < 2; ++sg) {
             uint32_t x[32], u[32];
-            tmem_ld32(tlane + TM_X + sg * 32, x);
+            tmem_ld32(tlane + TM_X + c0 + sg * 32, x);
             tmem_ld32(accu + sg * 32, u);
             tmem_wait_ld_dep(x);
             tmem_wait_ld_dep(u);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
+              const int k8 = c0 + sg * 32 + c8 * 8;
+              const float4 g0 = ldg4(m.gln_g[2], k8 >> 2), g1 = ldg4(m.gln_g[2], (k8 >> 2) + 1);
+              const float4 e0 = ldg4(m.gln_b[2], k8 >> 2), e1 = ldg4(m.gln_b[2], (k8 >> 2) + 1);
+              const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float es[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
               float o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int k = sg * 32 + c8 * 8 + i;
-                const float nv = tanh_fast((__uint_as_float(x[c8 * 8 + i]) - mu) * rstd * __ldg(m.gln_g[2] + k) + __ldg(m.gln_b[2] + k));
+                const float nv = tanh_fast((__uint_as_float(x[c8 * 8 + i]) - mu) * rstd * gs[i] + es[i]);
                 const float uu = __uint_as_float(u[c8 * 8 + i]);
-                const float hn = uu * nv + (1.0f - uu) * hf[k * 128 + row];
-                hf[k * 128 + row] = hn;
+                const float hn = uu * nv + (1.0f - uu) * hf[(k8 + i) * 128 + row];
+                hf[(k8 + i) * 128 + row] = hn;
                 o[i] = hn;
               }
-              sw_store8(hs, row, sg * 32 + c8 * 8, o);
+              sw_store8(hs, row, k8, o);
             }
           }
           fence_proxy_async_smem();
           mbar_arrive(hs_full);
           tcgen05_fence_before();
-          mbar_arrive(&acc_empty[ga ^ 1u]);
+          epi_bar_sync();                                   // both halves have read the update gate (and the exchange slots)
+          if (ga == (uint32_t)grp) mbar_arrive(&acc_empty[ga ^ 1u]);
           if (tr) trp[1] = clock64();
           continue;
         }

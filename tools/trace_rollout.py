@@ -7,8 +7,12 @@ from tests import synth
 from tdmpc_b200 import Planner, _lib
 ap = argparse.ArgumentParser(); ap.add_argument("--workload", default="cfg3"); ap.add_argument("--batch", type=int, default=512)
 a = ap.parse_args()
-cfg = synth.make_cfg(a.workload); sd = synth.make_told_weights(cfg, 0); H, N, P, T = synth.plan_dims(cfg)
-pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, precision="bf16")
+cfg = synth.make_cfg(a.workload)
+H, N, P, T = synth.plan_dims(cfg)
+drnn = a.workload in ("cfg5", "tiny_drnn")
+sd = synth.make_drnn_weights(cfg, 0) if drnn else synth.make_told_weights(cfg, 0)
+pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, precision="bf16", enc_layernorm=drnn,
+             dynamics="drnn" if drnn else "mlp", hidden_dim=cfg.hidden_dim if drnn else 0)
 pl.sync_weights({k: v.cuda() for k, v in sd.items()})
 lib = _lib.load(); lib.tdmpc_debug_set_trace.argtypes = [C.c_void_p]; lib.tdmpc_debug_set_trace.restype = C.c_int
 n = lib.tdmpc_debug_set_trace(None)
@@ -20,18 +24,18 @@ lib.tdmpc_debug_set_trace(C.c_void_p(buf.data_ptr()))
 pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
 torch.cuda.synchronize(); lib.tdmpc_debug_set_trace(None)
 tr = buf.cpu().numpy().reshape(3, -1, 2)
-names = {0: "L1", 1: "L2", 2: "L3", 3: "QL1", 4: "QL2"}; chains = ["dyn", "rew", "pi", "q1", "q2"]
-# rebuild the job list exactly as build_jobs(MODE_VALUE, H) does
-jobs = []
-for t in range(H):
-    jobs += [(0, 0, c, t) for c in range(4)] + [(1, 0, c, t) for c in range(4)] + [(0, 1, c, t) for c in range(4)] + [(2, 0, 0, t)] + [(1, 1, c, t) for c in range(4)]
-jobs += [(0, 2, c, 0) for c in range(4)] + [(1, 2, c, 0) for c in range(4)] + [(2, 2, 0, 0), (3, 3, 0, 0), (4, 3, 0, 0), (3, 4, 0, 0), (4, 4, 0, 0)]
+# the job list the kernel walked (word layout: tc_model.cuh)
+lib.tdmpc_debug_jobs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]; lib.tdmpc_debug_jobs.restype = C.c_int
+words = (C.c_uint32 * 1024)()
+nj = lib.tdmpc_debug_jobs(pl._h, 0, H, words, 1024)
+names = ["L1", "L2", "L3", "QL1", "QL2", "G", "GH", "GI"]; chains = ["dyn", "rew", "pi", "q1", "q2"]
+jobs = [(w & 7, (w >> 3) & 7, (w >> 6) & 3, (w >> 8) & 31) for w in words[:nj]]
 t0 = tr[0, 0, 0]
 print(f"{'job':>4} {'what':14} | {'mma start':>9} {'mma end':>9} {'dur':>6} | {'epi0 start':>10} {'end':>8} {'dur':>6} | {'epi1 start':>10} {'end':>8} {'dur':>6}")
 for j, (ty, chn, c, t) in enumerate(jobs):
     row = [f"{j:4d} {names[ty] + ' ' + chains[chn] + ' c' + str(c) + ' t' + str(t):14}"]
     for r in range(3):
-        s, e = tr[r, j]
-        row.append(f"{(s - t0) if s else 0:>10} {(e - t0) if e else 0:>8} {(e - s) if s and e else 0:>6}")
+        s_, e_ = tr[r, j]
+        row.append(f"{(s_ - t0) if s_ else 0:>10} {(e_ - t0) if e_ else 0:>8} {(e_ - s_) if s_ and e_ else 0:>6}")
     print(" | ".join(row))
 print("tile total cycles:", tr[:, :len(jobs), 1].max() - t0)
