@@ -791,3 +791,43 @@ def test_drnn_bf16_policy_rollout_matches_quantised_oracle(cfg_name):
     err = (pi_g[0].permute(1, 0, 2).cpu() - pi_o).abs()
     print(f"drnn bf16 pi rollout {cfg_name}: action abs err median {err.median().item():.2e} p90 {err.flatten().quantile(0.9).item():.2e} max {err.max().item():.2e}")
     assert err.median().item() <= TOL_BF16 and (err <= 10 * TOL_BF16).float().mean().item() >= 0.9
+
+
+def test_icem_batched_problems_are_independent():
+    """iCEM planning (decaying sample counts, shifted + carried elites, colored built-in noise replaced by injected draws)
+    for B problems in one call == the same problems one at a time, bit for bit, in both precision modes."""
+    gu = _gu()
+    cfg = synth.make_cfg("tiny_icem")
+    sd = synth.make_told_weights(cfg, 4, enc_ln=True)
+    B, H, K, I, A = 4, cfg.horizon, cfg.num_elites, cfg.iterations, cfg.action_dim
+    sizes = O.icem_sizes(cfg, 0.5, True)
+    N0, E0, P0 = sizes[0]
+    Nmax, Tmax = max(s[0] for s in sizes), max(sum(s) for s in sizes)
+    rs = np.random.RandomState(8)
+    obs = torch.from_numpy(np.stack([synth.make_obs(cfg, 80 + b) for b in range(B)])).cuda()
+    elites0 = torch.from_numpy(rs.uniform(-1, 1, (B, K, H, A)).astype(np.float32)).cuda()
+    prev0 = torch.from_numpy(rs.uniform(-0.5, 0.5, (B, H, A)).astype(np.float32)).cuda()
+    noise = {"pi": torch.from_numpy(rs.standard_normal((B, H, P0, A)).astype(np.float32)),
+             "cem": torch.from_numpy(rs.standard_normal((B, I, H, Nmax, A)).astype(np.float32)),
+             "term": torch.from_numpy(rs.standard_normal((B, I, Tmax, A)).astype(np.float32)),
+             "out": torch.from_numpy(rs.standard_normal((B, A)).astype(np.float32)),
+             "shift": torch.from_numpy(rs.standard_normal((B, H, E0, A)).astype(np.float32)),
+             "u": rs.random_sample(B)}
+    for prec in ("fp32", "bf16"):
+        pl = gu.make_planner(cfg, sd, prec)
+        kw = dict(horizon=H, num_samples=cfg.num_samples, num_pi_trajs=P0, num_elites=K, iterations=I, discount=cfg.discount,
+                  temperature=cfg.temperature, momentum=cfg.momentum, min_std=cfg.min_std, std_floor=cfg.min_std, init_std=0.5,
+                  eval_mode=False, t0=False, has_prev=True, n_samples=[s[0] for s in sizes], n_reuse=[s[1] for s in sizes],
+                  n_pi=[s[2] for s in sizes], elite_horizon=H, warm_last=True, best_a_last=True, shift_elites=True, taps=True)
+        eb = elites0.clone()
+        res = pl.plan(obs, **kw, prev_mean=prev0.clone(), elite_actions=eb, noise=noise)
+        torch.cuda.synchronize()
+        for b in range(B):
+            nb = {k: (v[b:b + 1] if k != "u" else v[b:b + 1]) for k, v in noise.items()}
+            e1 = elites0[b:b + 1].clone()
+            one = pl.plan(obs[b:b + 1], **kw, prev_mean=prev0[b:b + 1].clone(), elite_actions=e1, noise=nb)
+            torch.cuda.synchronize()
+            assert torch.equal(one["taps"]["values"][:, 0], res["taps"]["values"][:, b]), (prec, b)
+            assert torch.equal(one["action"][0], res["action"][b]) and torch.equal(one["prev_mean"][0], res["prev_mean"][b])
+            assert torch.equal(e1[0], eb[b])
+        assert not torch.equal(eb, elites0)
