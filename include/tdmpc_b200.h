@@ -192,6 +192,13 @@ TDMPC_API int tdmpc_estimate_value(tdmpc_handle* h, const float* z0, const float
                          int32_t batch, int32_t rows, int32_t horizon, double discount, float min_std,
                          uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream);
 
+/* Same for the GRU latent dynamics: TdICemSimDssm.estimate_value(z, actions, hidden) (tdmpc_icem_similarity_drnn.py:124-133).
+ * hidden [B, hidden_dim] is the GRU state the B problems start from (NULL = zeros, which is also what
+ * tdmpc_estimate_value uses on a TDMPC_DYN_DRNN handle). */
+TDMPC_API int tdmpc_estimate_value_drnn(tdmpc_handle* h, const float* z0, const float* hidden, const float* actions,
+                              const float* noise_term, int32_t batch, int32_t rows, int32_t horizon, double discount,
+                              float min_std, uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream);
+
 /* Replaces the policy rollout of TDMPC.plan (tdmpc.py:113-118):
  * for t: a_t = pi(z, min_std); z = next(z, a_t).  pi_actions [B,P,H,A]; noise_pi [B,H,P,A] or NULL. */
 TDMPC_API int tdmpc_pi_rollout(tdmpc_handle* h, const float* z0, const float* noise_pi, int32_t batch, int32_t rows,

@@ -17,7 +17,7 @@ DYN_MLP, DYN_DRNN = 0, 1
 
 EXPORTS = [
     "tdmpc_create", "tdmpc_destroy", "tdmpc_last_error", "tdmpc_reserve", "tdmpc_set_weights",
-    "tdmpc_encode", "tdmpc_estimate_value", "tdmpc_pi_rollout", "tdmpc_select_update", "tdmpc_plan",
+    "tdmpc_encode", "tdmpc_estimate_value", "tdmpc_estimate_value_drnn", "tdmpc_pi_rollout", "tdmpc_select_update", "tdmpc_plan",
     "tdmpc_fill_noise", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes",
 ]
 
@@ -93,6 +93,8 @@ def load():
     lib.tdmpc_encode.argtypes = [H, _fp, C.c_int32, _fp, C.c_void_p]
     lib.tdmpc_estimate_value.argtypes = [H, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_float,
                                          C.c_uint64, C.c_uint64, _fp, _fp, C.c_void_p]
+    lib.tdmpc_estimate_value_drnn.argtypes = [H, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_float,
+                                              C.c_uint64, C.c_uint64, _fp, _fp, C.c_void_p]
     lib.tdmpc_pi_rollout.argtypes = [H, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64,
                                      _fp, C.c_void_p]
     lib.tdmpc_select_update.argtypes = [H, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double,

@@ -303,22 +303,35 @@ extern "C" int tdmpc_encode(tdmpc_handle* h, const float* obs, int32_t batch, fl
   return check_launch(h, "encode");
 }
 
-extern "C" int tdmpc_estimate_value(tdmpc_handle* h, const float* z0, const float* actions, const float* noise_term,
-                                    int32_t batch, int32_t rows, int32_t horizon, double discount, float min_std,
-                                    uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream) {
+static int estimate_value_impl(tdmpc_handle* h, const float* z0, const float* hidden, const float* actions, const float* noise_term,
+                               int32_t batch, int32_t rows, int32_t horizon, double discount, float min_std,
+                               uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream) {
   if (!h || !z0 || !actions || !values) return TDMPC_ERR_INVALID;
   if (!h->weights_set) FAIL(h, TDMPC_ERR_STATE, "estimate_value: weights not set");
   if (batch <= 0 || rows <= 0 || horizon <= 0 || horizon > TDMPC_MAX_H) FAIL(h, TDMPC_ERR_INVALID, "estimate_value: bad shape");
+  if (hidden && h->cfg.dynamics != TDMPC_DYN_DRNN) FAIL(h, TDMPC_ERR_INVALID, "estimate_value: hidden state given to a model without GRU dynamics");
   cudaSetDevice(h->cfg.device);
   RolloutParams p{};
   p.mode = MODE_VALUE; p.B = batch; p.T = rows; p.Tcap = rows; p.H = horizon;
   p.L = h->cfg.latent_dim; p.A = h->cfg.action_dim; p.M = h->cfg.mlp_dim;
-  p.z0 = z0; p.actions = actions; p.values = values; p.last_reward = last_reward;
+  p.z0 = z0; p.hidden0 = hidden; p.actions = actions; p.values = values; p.last_reward = last_reward;
   p.noise = NoiseSrc{noise_term, seed, call, NS_TERM};
   p.noise_base = 0; p.noise_bstride = (uint64_t)rows * p.A; p.noise_tstride = 0;
   p.min_std = min_std;
   fill_disc(discount, horizon, p.disc);
   return run_rollout(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int tdmpc_estimate_value(tdmpc_handle* h, const float* z0, const float* actions, const float* noise_term,
+                                    int32_t batch, int32_t rows, int32_t horizon, double discount, float min_std,
+                                    uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream) {
+  return estimate_value_impl(h, z0, nullptr, actions, noise_term, batch, rows, horizon, discount, min_std, seed, call, values, last_reward, stream);
+}
+
+extern "C" int tdmpc_estimate_value_drnn(tdmpc_handle* h, const float* z0, const float* hidden, const float* actions,
+                                         const float* noise_term, int32_t batch, int32_t rows, int32_t horizon, double discount,
+                                         float min_std, uint64_t seed, uint64_t call, float* values, float* last_reward, void* stream) {
+  return estimate_value_impl(h, z0, hidden, actions, noise_term, batch, rows, horizon, discount, min_std, seed, call, values, last_reward, stream);
 }
 
 extern "C" int tdmpc_pi_rollout(tdmpc_handle* h, const float* z0, const float* noise_pi, int32_t batch, int32_t rows,

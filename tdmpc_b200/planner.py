@@ -156,16 +156,24 @@ class Planner:
         self._check(self.lib.tdmpc_encode(self._h, _ptr(obs), obs.shape[0], _ptr(z), self._stream()), "tdmpc_encode")
         return z
 
-    def estimate_value(self, z0, actions, *, discount, min_std, noise_term=None, seed=0, call=0):
-        """TDMPC.estimate_value (tdmpc.py:83-92).  z0 [B,L]; actions [B,T,H,A]; noise_term [B,T,A]."""
+    def estimate_value(self, z0, actions, *, discount, min_std, noise_term=None, seed=0, call=0, hidden=None):
+        """TDMPC.estimate_value (tdmpc.py:83-92).  z0 [B,L]; actions [B,T,H,A]; noise_term [B,T,A]; GRU dynamics:
+        hidden [B,Hd] (tdmpc_icem_similarity_drnn.py:124-133; None = zeros)."""
         z0, actions = _f32(z0, self.device), _f32(actions, self.device)
         B, T, H, _ = actions.shape
         values = torch.empty(B, T, device=self.device)
         last_r = torch.empty(B, T, device=self.device)
         nz = _f32(noise_term, self.device) if noise_term is not None else None
-        self._check(self.lib.tdmpc_estimate_value(self._h, _ptr(z0), _ptr(actions), _ptr(nz), B, T, H, float(discount),
-                                                  float(min_std), seed, call, _ptr(values), _ptr(last_r), self._stream()),
-                    "tdmpc_estimate_value")
+        if hidden is not None:
+            hidden = _f32(hidden, self.device)
+            assert tuple(hidden.shape) == (B, self.Hd)
+            self._check(self.lib.tdmpc_estimate_value_drnn(self._h, _ptr(z0), _ptr(hidden), _ptr(actions), _ptr(nz), B, T, H, float(discount),
+                                                           float(min_std), seed, call, _ptr(values), _ptr(last_r), self._stream()),
+                        "tdmpc_estimate_value_drnn")
+        else:
+            self._check(self.lib.tdmpc_estimate_value(self._h, _ptr(z0), _ptr(actions), _ptr(nz), B, T, H, float(discount),
+                                                      float(min_std), seed, call, _ptr(values), _ptr(last_r), self._stream()),
+                        "tdmpc_estimate_value")
         return values, last_r
 
     def pi_rollout(self, z0, rows, horizon, *, min_std, noise_pi=None, seed=0, call=0):
@@ -580,5 +588,11 @@ class TdICemSimDssm(TDMPC):
 
     plan = _fast_plan_icem_drnn
 
+    @torch.no_grad()
     def estimate_value(self, z, actions, hidden):
-        raise NotImplementedError("use Planner.plan / TdICemSimDssm.plan; the stage-level DRNN value call is not exposed")
+        """Reference signature (tdmpc_icem_similarity_drnn.py:124-133): z [T,L], actions [H,T,A], hidden [T,Hd] -> (G [T,1], float)."""
+        self._planner.sync_weights(self.model)
+        H = self.plan_horizon
+        acts = actions[:H].permute(1, 0, 2).unsqueeze(1).contiguous()      # one "problem" per trajectory: [T, 1, H, A]
+        v, r = self._planner.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std, hidden=hidden)
+        return v, float(r.mean().item())

@@ -15,7 +15,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "tdmpc_b200.h")).read()
     declared = re.findall(r"TDMPC_API\s+[\w\s\*]+?\b(tdmpc_\w+)\s*\(", hdr)
-    assert len(declared) >= 14 and set(declared) == set(_lib.EXPORTS)
+    assert len(declared) >= 15 and set(declared) == set(_lib.EXPORTS)
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name

@@ -831,3 +831,32 @@ def test_icem_batched_problems_are_independent():
             assert torch.equal(one["action"][0], res["action"][b]) and torch.equal(one["prev_mean"][0], res["prev_mean"][b])
             assert torch.equal(e1[0], eb[b])
         assert not torch.equal(eb, elites0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_drnn_estimate_value_with_per_row_hidden(precision):
+    """TdICemSimDssm.estimate_value(z, actions, hidden) with the reference signature (tdmpc_icem_similarity_drnn.py:124-133):
+    every trajectory starts from its own latent AND its own GRU state."""
+    from tdmpc_b200 import TdICemSimDssm
+    cfg = synth.make_cfg("tiny_drnn", device="cuda", precision=precision)
+    sd = synth.make_drnn_weights(cfg, 5)
+    agent = TdICemSimDssm(cfg)
+    agent.model.load_state_dict(sd, strict=False)
+    agent.model.eval()
+    agent.plan_horizon = cfg.horizon
+    H, T, A = cfg.horizon, 200, cfg.action_dim
+    rs = np.random.RandomState(12)
+    z = torch.from_numpy(rs.standard_normal((T, cfg.latent_dim)).astype(np.float32))
+    hid = torch.from_numpy(0.5 * rs.standard_normal((T, cfg.hidden_dim)).astype(np.float32))
+    acts = torch.from_numpy(rs.uniform(-1, 1, (H, T, A)).astype(np.float32))
+    # min_std > 0 draws terminal-policy noise from the built-in stream; use the deterministic policy for an exact comparison
+    cfg.min_std = 0.0
+    v_g, r_g = agent.estimate_value(z.cuda(), acts.cuda(), hid.cuda())
+    torch.cuda.synchronize()
+    v_o, r_o = O.estimate_value(sd, z, acts, H, cfg.discount, 0.0, None, quant=(precision == "bf16"), hidden=hid)
+    err = (v_g.cpu() - v_o).abs().squeeze(1) / v_o.abs().max()
+    assert v_g.shape == (T, 1) and isinstance(r_g, float)
+    if precision == "fp32":
+        assert err.max().item() <= TOL_FP32 and abs(r_g - r_o) <= 1e-5 * max(1.0, abs(r_o))
+    else:
+        assert err.median().item() <= TOL_BF16 and (err <= TOL_BF16).float().mean().item() >= 0.75
