@@ -100,15 +100,17 @@ __device__ __forceinline__ uint32_t job_first_tile(const TcModel& m, uint32_t jo
   }
 }
 
-// bf16 store of one element of the [z,a] operand (128B-swizzled k-blocks of 64)
+// bf16 store of one element of the [z,a] operand (128B-swizzled k-blocks of 64); explicit shared-space stores
 __device__ __forceinline__ void za_store1(uint8_t* za, int row, int k, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(za + (k >> 6) * TILE_BYTES + sw128_offset(row, k & 63)) = __float2bfloat16(v);
+  const uint32_t a = smem_u32(za) + (k >> 6) * TILE_BYTES + sw128_offset(row, k & 63);
+  const unsigned short b = __bfloat16_as_ushort(__float2bfloat16(v));
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(b) : "memory");
 }
 // 8 consecutive k (k0 % 8 == 0) as one 16-byte store
 __device__ __forceinline__ void sw_store8(uint8_t* base, int row, int k0, const float* v) {
-  uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(base + (k0 >> 6) * TILE_BYTES + sw128_offset(row, k0 & 63)) = u;
+  const uint32_t a = smem_u32(base) + (k0 >> 6) * TILE_BYTES + sw128_offset(row, k0 & 63);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
+               "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
 }
 
 template <bool DRNN>
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
   // holds the GRU state: fp32 [column][row] (conflict-free for thread = row) and the bf16 K-major operand HS (2 k-blocks).
   float* hf = reinterpret_cast<float*>(xs);
+  const uint32_t hf_addr = smem_u32(hf);
   uint8_t* hs = xs + 128 * 128 * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             v[i] = (h0 && valid) ? __ldg(h0 + k0 + i) : 0.0f;
-            hf[(k0 + i) * 128 + row] = v[i];
+            sts1(hf_addr + ((k0 + i) * 128 + row) * 4, v[i]);
           }
           sw_store8(hs, row, k0, v);
         }
@@ -652,8 +655,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int i = 0; i < 8; ++i) {
                 const float nv = tanh_fast((__uint_as_float(x[c8 * 8 + i]) - mu) * rstd * gs[i] + es[i]);
                 const float uu = __uint_as_float(u[c8 * 8 + i]);
-                const float hn = uu * nv + (1.0f - uu) * hf[(k8 + i) * 128 + row];
-                hf[(k8 + i) * 128 + row] = hn;
+                const uint32_t ha = hf_addr + ((k8 + i) * 128 + row) * 4;
+                const float hn = uu * nv + (1.0f - uu) * lds1(ha);
+                sts1(ha, hn);
                 o[i] = hn;
               }
               sw_store8(hs, row, k8, o);
@@ -908,10 +912,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           const bool first = type == J_QL1;
           // Stage the layer's per-column constants in shared memory: every thread needs all of them, and with 227 KB of
           // the SM given to shared memory the L1 is too small to keep the 8 KB vectors of all chains resident.
-          const float4* qb = reinterpret_cast<const float4*>(qcs);            // bias
-          const float4* qg = qb + 128;                                         // LayerNorm gamma
-          const float4* qe = qb + 256;                                         // LayerNorm beta
-          const float4* qw = qb + 384;                                         // head weights w3
+          const uint32_t qb = smem_u32(qcs);                                   // bias            (shared-space addresses)
+          const uint32_t qg = qb + 2048, qe = qb + 4096, qw = qb + 6144;       // LN gamma, LN beta, head weights w3
           epi_bar_sync();                                                      // the previous layer's readers are done
           {
             const float* srcs[4] = {first ? ch.b1 : ch.b2, ch.ln_g[first ? 0 : 1], ch.ln_b[first ? 0 : 1], ch.w3};
@@ -928,12 +930,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           for (int c = grp; c < 4; c += 2) {
             float4 x0[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x0[i] = qb[c * 32 + i];
+            for (int i = 0; i < 8; ++i) x0[i] = lds4(qb + (c * 32 + i) * 16);
             mbar_wait(&q_full[c], q_phase, 8);
             tcgen05_fence_after();
             tmem_stream_aux(tlane + c * 128, 4, x0, [&](int s, float4 (&x)[8]) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = qb[(c * 4 + s) * 8 + i];
+              for (int i = 0; i < 8; ++i) x[i] = lds4(qb + ((c * 4 + s) * 8 + i) * 16);
             },
                             [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
@@ -959,7 +961,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int vi = (c * 4 + s) * 8 + i;
-                const float4 x = qb[vi], gg = qg[vi], bb = qe[vi];
+                const float4 x = lds4(qb + vi * 16), gg = lds4(qg + vi * 16), bb = lds4(qe + vi * 16);
                 y[4 * i] = (__uint_as_float(v[4 * i]) + x.x - mu) * rstd * gg.x + bb.x;
                 y[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + x.y - mu) * rstd * gg.y + bb.y;
                 y[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + x.z - mu) * rstd * gg.z + bb.z;
@@ -973,7 +975,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float4 f = qw[(c * 4 + s) * 8 + i];
+                  const float4 f = lds4(qw + ((c * 4 + s) * 8 + i) * 16);
                   qdot = fmaf(elu_fast(y[4 * i]), f.x, qdot); qdot = fmaf(elu_fast(y[4 * i + 1]), f.y, qdot);
                   qdot = fmaf(elu_fast(y[4 * i + 2]), f.z, qdot); qdot = fmaf(elu_fast(y[4 * i + 3]), f.w, qdot);
                 }
