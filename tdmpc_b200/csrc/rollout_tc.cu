@@ -40,7 +40,7 @@ constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
 constexpr int MAX_JOBS = 17 * TDMPC_MAX_H + 16;
 constexpr uint32_t TM_ACC = 0, TM_A = 256;
-constexpr uint32_t TM_X = 256;             // DRNN: n-gate accumulator, inside the (then idle) h1 region
+constexpr uint32_t TM_X = 256, TM_Y = 384;  // DRNN: gh_n and gi_n of the newval gate, inside the (then idle) h1 region
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 232448;
 
@@ -137,11 +137,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint64_t* xs_full = h1_full + 4;       // XS chunk c written to smem  (layer-2 / QL1 epilogue -> layer-3 / QL2 MMAs)
   uint64_t* za_full = xs_full + 4;
   uint64_t* q_full = za_full + 1;        // Q-head accumulator chunk c complete (one barrier per chunk: never two phases ahead)
-  // DRNN only: hidden-state operand written / n-gate accumulator X complete / X scaled by the reset gate / update gate stored
+  // DRNN only: hidden-state operand written / newval-gate products X, Y complete / reset gate stored / update gate stored
   uint64_t* hs_full = q_full + 4;
   uint64_t* x_full = hs_full + 1;
-  uint64_t* x_scaled = x_full + 1;
-  uint64_t* u_ready = x_scaled + 1;
+  uint64_t* r_ready = x_full + 1;
+  uint64_t* u_ready = r_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_ready + 1);
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
   // holds the GRU state: fp32 [column][row] (conflict-free for thread = row) and the bf16 K-major operand HS (2 k-blocks).
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) { mbar_init(&h1_full[i], 128); mbar_init(&xs_full[i], 128); }
     mbar_init(za_full, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
-    mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(x_scaled, 128); mbar_init(u_ready, 128);
+    mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(r_ready, 128); mbar_init(u_ready, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
         xs_phase ^= 1u << c;
       };
-      uint32_t hs_phase = 0, xsc_phase = 0;
+      uint32_t hs_phase = 0;
       const uint32_t hs_addr = smem_u32(hs);
       // one k-block (<= 4 k-steps of 16) with both operands in shared memory
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
@@ -302,24 +302,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             if (leader) umma_commit(&acc_full[b]);
           } else if (DRNN && type == J_GH) {
-            // gh_n = h W_hh[newval]^T parked in X; the reset-gate epilogue scales it in place
+            // gh_n = h W_hh[newval]^T -> X
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t wt = tile_acquire();
               if (leader) kblock_ss(tmem + TM_X, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
               tile_release();
             }
-            if (leader) umma_commit(x_full);
           } else if (DRNN && type == J_GI) {
-            // X = r * gh_n (written by the epilogue) ; X += [z,a] W_ih[newval]^T
-            mbar_wait(x_scaled, xsc_phase, 11); xsc_phase ^= 1;
-            tcgen05_fence_after();
+            // gi_n = [z,a] W_ih[newval]^T -> Y; the n-gate epilogue forms gi_n + r * gh_n in registers (rnns.py:27)
             for (int kb = 0; kb < m.nkb1; ++kb) {
               const uint32_t wt = tile_acquire();
-              if (leader) kblock_ss(tmem + TM_X, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), false);
+              if (leader) kblock_ss(tmem + TM_Y, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
               tile_release();
             }
             for (int i = 0; i < m.gi_pad; ++i) { tile_acquire(); tile_release(); }     // padding tiles keep the ring aligned
-            if (leader) umma_commit(x_full);
+            if (leader) umma_commit(x_full);                                            // covers J_GH's MMAs too
           } else if (type == J_L2) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
@@ -471,7 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
     uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
-    uint32_t x_phase = 0, u_phase = 0, ga = 0;     // DRNN: phases of x_full / u_ready, group that owns the reset gate of this step
+    uint32_t x_phase = 0, ga = 0;                  // DRNN: phase of x_full / r_ready / u_ready, group that owns the reset gate of this step
     float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
     float* x_ssq = xch + (1 * 2 + (grp ^ 1)) * 128;
     float* x_dot = xch + (2 * 2 + (grp ^ 1)) * 128;
@@ -548,8 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           if (type == J_GH) continue;                                  // MMAs only
           if (type == J_G) {
             const int b = nbuf; nbuf ^= 1;
-            const uint32_t xf = x_phase;
-            if (chunk == 0) { ga = (uint32_t)b; x_phase ^= 1; }
+            if (chunk == 0) ga = (uint32_t)b;
             if (b != grp) continue;
             if (tr) trp[0] = clock64();
             const uint32_t acc = tlane + TM_ACC + b * 128;
@@ -564,84 +560,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const float rstd = 1.0f / sqrtf(fmaxf(ssq * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
             const float* lg = m.gln_g[chunk];
             const float* lb = m.gln_b[chunk];
-            if (chunk == 0) {
-              // reset gate: r = sigmoid(LN_r(.)); the parked gh_n is scaled in place, X <- r * X  (rnns.py:26-28)
-              mbar_wait(x_full, xf, 12);
-              tcgen05_fence_after();
+            // reset / update gate: sigmoid(LN(.)) written back over its own accumulator (rnns.py:25-26); the n-gate
+            // epilogue reads both and then releases the buffers
 #pragma unroll 1
-              for (int sg = 0; sg < 4; ++sg) {
-                uint32_t a[32], x[32];
-                tmem_ld32(acc + sg * 32, a);
-                tmem_ld32(tlane + TM_X + sg * 32, x);
-                tmem_wait_ld_dep(a);
-                tmem_wait_ld_dep(x);
+            for (int sg = 0; sg < 4; ++sg) {
+              uint32_t a[32];
+              tmem_ld32(acc + sg * 32, a);
+              tmem_wait_ld_dep(a);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 gg = ldg4(lg, sg * 8 + i), bb = ldg4(lb, sg * 8 + i);
-                  x[4 * i] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i]) - mu) * rstd * gg.x + bb.x) * __uint_as_float(x[4 * i]));
-                  x[4 * i + 1] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 1]) - mu) * rstd * gg.y + bb.y) * __uint_as_float(x[4 * i + 1]));
-                  x[4 * i + 2] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 2]) - mu) * rstd * gg.z + bb.z) * __uint_as_float(x[4 * i + 2]));
-                  x[4 * i + 3] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 3]) - mu) * rstd * gg.w + bb.w) * __uint_as_float(x[4 * i + 3]));
-                }
-                tmem_st32(tlane + TM_X + sg * 32, x);
+              for (int i = 0; i < 8; ++i) {
+                const float4 gg = ldg4(lg, sg * 8 + i), bb = ldg4(lb, sg * 8 + i);
+                a[4 * i] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i]) - mu) * rstd * gg.x + bb.x));
+                a[4 * i + 1] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 1]) - mu) * rstd * gg.y + bb.y));
+                a[4 * i + 2] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 2]) - mu) * rstd * gg.z + bb.z));
+                a[4 * i + 3] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 3]) - mu) * rstd * gg.w + bb.w));
               }
-              tmem_wait_st();
-              tcgen05_fence_before();
-              mbar_arrive(x_scaled);
-              mbar_arrive(&acc_empty[b]);
-            } else {
-              // update gate: u = sigmoid(LN_u(.)) written back over its accumulator; the n-gate epilogue reads it and
-              // then releases the buffer
-#pragma unroll 1
-              for (int sg = 0; sg < 4; ++sg) {
-                uint32_t a[32];
-                tmem_ld32(acc + sg * 32, a);
-                tmem_wait_ld_dep(a);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 gg = ldg4(lg, sg * 8 + i), bb = ldg4(lb, sg * 8 + i);
-                  a[4 * i] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i]) - mu) * rstd * gg.x + bb.x));
-                  a[4 * i + 1] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 1]) - mu) * rstd * gg.y + bb.y));
-                  a[4 * i + 2] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 2]) - mu) * rstd * gg.z + bb.z));
-                  a[4 * i + 3] = __float_as_uint(sigmoid_fast((__uint_as_float(a[4 * i + 3]) - mu) * rstd * gg.w + bb.w));
-                }
-                tmem_st32(acc + sg * 32, a);
-              }
-              tmem_wait_st();
-              tcgen05_fence_before();
-              mbar_arrive(u_ready);
+              tmem_st32(acc + sg * 32, a);
             }
+            tmem_wait_st();
+            tcgen05_fence_before();
+            mbar_arrive(chunk == 0 ? r_ready : u_ready);
             if (tr) trp[1] = clock64();
             continue;
           }
           // J_GI: n = tanh(LN_n(gi_n + r * gh_n)); h' = u * n + (1 - u) * h  (rnns.py:27-28).  Both groups work on it, 64
-          // columns each (it sits on the step's critical path); the LayerNorm statistics are exchanged through `xch`.
-          const uint32_t xf = x_phase, uf = u_phase;
-          x_phase ^= 1; u_phase ^= 1;
+          // columns each (it sits on the step's critical path); x = gi_n + r * gh_n stays in registers between the
+          // statistics pass and the normalising pass; the LayerNorm statistics are exchanged through `xch`.
+          const uint32_t gph = x_phase;                       // one phase of x_full / r_ready / u_ready per step
+          x_phase ^= 1;
           if (tr) trp[0] = clock64();
           const int c0 = grp * 64;
-          mbar_wait(x_full, xf, 13);
+          const uint32_t accr = tlane + TM_ACC + ga * 128 + c0, accu = tlane + TM_ACC + (ga ^ 1u) * 128 + c0;
+          mbar_wait(x_full, gph, 13);
+          mbar_wait(r_ready, gph, 12);
           tcgen05_fence_after();
+          float xv[64];
           float sum = 0.0f, ssq = 0.0f;
-          tmem_stream(tlane + TM_X + c0, 2, [&](int, uint32_t (&v)[32]) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { const float y = __uint_as_float(v[i]); sum += y; ssq = fmaf(y, y, ssq); }
-          });
+          for (int sg = 0; sg < 2; ++sg) {
+            uint32_t r[32], gi[32], gh[32];
+            tmem_ld32(accr + sg * 32, r);
+            tmem_ld32(tlane + TM_Y + c0 + sg * 32, gi);
+            tmem_ld32(tlane + TM_X + c0 + sg * 32, gh);
+            tmem_wait_ld_dep(r); tmem_wait_ld_dep(gi); tmem_wait_ld_dep(gh);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float y = fmaf(__uint_as_float(r[i]), __uint_as_float(gh[i]), __uint_as_float(gi[i]));
+              xv[sg * 32 + i] = y; sum += y; ssq = fmaf(y, y, ssq);
+            }
+          }
           m_sum[row] = sum; m_ssq[row] = ssq;
           epi_bar_sync();
           const float s0 = grp == 0 ? sum : x_sum[row], s1 = grp == 0 ? x_sum[row] : sum;        // same order in both groups
           const float q0 = grp == 0 ? ssq : x_ssq[row], q1 = grp == 0 ? x_ssq[row] : ssq;
           const float mu = (s0 + s1) * (1.0f / 128.0f);
           const float rstd = 1.0f / sqrtf(fmaxf((q0 + q1) * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
-          mbar_wait(u_ready, uf, 14);
+          mbar_wait(u_ready, gph, 14);
           tcgen05_fence_after();
-          const uint32_t accu = tlane + TM_ACC + (ga ^ 1u) * 128 + c0;
-#pragma unroll 1
+#pragma unroll
           for (int sg = 0; sg < 2; ++sg) {
-            uint32_t x[32], u[32];
-            tmem_ld32(tlane + TM_X + c0 + sg * 32, x);
+            uint32_t u[32];
             tmem_ld32(accu + sg * 32, u);
-            tmem_wait_ld_dep(x);
             tmem_wait_ld_dep(u);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
@@ -653,7 +632,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               float o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float nv = tanh_fast((__uint_as_float(x[c8 * 8 + i]) - mu) * rstd * gs[i] + es[i]);
+                const float nv = tanh_fast((xv[sg * 32 + c8 * 8 + i] - mu) * rstd * gs[i] + es[i]);
                 const float uu = __uint_as_float(u[c8 * 8 + i]);
                 const uint32_t ha = hf_addr + ((k8 + i) * 128 + row) * 4;
                 const float hn = uu * nv + (1.0f - uu) * lds1(ha);
@@ -666,8 +645,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           fence_proxy_async_smem();
           mbar_arrive(hs_full);
           tcgen05_fence_before();
-          epi_bar_sync();                                   // both halves have read the update gate (and the exchange slots)
-          if (ga == (uint32_t)grp) mbar_arrive(&acc_empty[ga ^ 1u]);
+          epi_bar_sync();                                   // both halves have read the gates (and the exchange slots)
+          if (ga == (uint32_t)grp) { mbar_arrive(&acc_empty[0]); mbar_arrive(&acc_empty[1]); }
           if (tr) trp[1] = clock64();
           continue;
         }

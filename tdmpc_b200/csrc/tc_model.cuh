@@ -15,10 +15,11 @@ enum TcJobType {
   J_QL1 = 3,   // [z,a] (smem)  x W1       -> 512 cols;  epilogue: +b, LayerNorm, tanh -> XS
   J_QL2 = 4,   // h1 (smem XS)  x W2       -> 512 cols;  epilogue: +b, LayerNorm, ELU, dot with w3 -> Q
   // DRNN (GRU latent dynamics, models/rnns.py:19-29): the gate pre-activations.  chunk = gate (0 reset, 1 update).
-  J_G = 5,     // [z,a] x W_ih[g] + h (smem HS) x W_hh[g] -> one accumulator; epilogue: LayerNorm (in-thread), sigmoid;
-               //   reset: multiplies the parked gh_n in place (X <- r * X);  update: u written back over the accumulator
-  J_GH = 6,    // h x W_hh[newval] -> X (128 TMEM columns of the h1 region); no epilogue
-  J_GI = 7     // X += [z,a] x W_ih[newval];  epilogue: n = tanh(LN(X)), h' = u n + (1-u) h -> fp32 state + bf16 operand HS
+  J_G = 5,     // [z,a] x W_ih[g] + h (smem HS) x W_hh[g] -> one accumulator; epilogue: LayerNorm (in-thread), sigmoid,
+               //   written back over the accumulator (r or u)
+  J_GH = 6,    // gh_n = h x W_hh[newval]     -> X (TMEM columns 256-383 of the idle h1 region); no epilogue
+  J_GI = 7     // gi_n = [z,a] x W_ih[newval] -> Y (columns 384-511); epilogue: n = tanh(LN(gi_n + r gh_n)),
+               //   h' = u n + (1-u) h -> fp32 state + bf16 operand HS
 };
 enum TcJobFlags {
   F_WAIT_ZA = 1, F_LAST_STEP = 2, F_TERMINAL = 4,
