@@ -480,6 +480,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       mbar_wait(&acc_full[grp], fcnt & 1, 7);
       ++fcnt;
     };
+    // early release: the accumulator goes back to the MMA warp as soon as it sits in registers (tmem_drain_aux)
+    const bool late_release = (kp.debug & 2) != 0;      // experiment: release after the activation math, as before
+    auto acc_release = [&]() {
+      if (!late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
+    };
+    auto acc_release_late = [&]() {
+      if (late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
+    };
     auto load8 = [&](const float* ptr, int idx, float4 (&x)[8]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = ldg4(ptr, idx * 8 + i);
@@ -666,7 +674,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int i = 0; i < 8; ++i) x0[i] = ldg4(sc, i);
               acc_wait();
               tcgen05_fence_after();
-              tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int sg, float4 (&x)[8]) {
+              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int sg, float4 (&x)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = ldg4(sc, sg * 8 + i);
               }, [&](int sg, uint32_t (&v)[32], float4 (&x)[8]) {
@@ -682,7 +690,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               tmem_wait_st();
               tcgen05_fence_before();
               mbar_arrive(&h1_full[chunk]);
-              mbar_arrive(&acc_empty[b]);
+              acc_release_late();
               continue;
             }
             // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
@@ -692,8 +700,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             load8(bias, 0, x0);
             acc_wait();
             tcgen05_fence_after();
-            tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
-                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
+            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                           [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
               uint32_t o[16];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -705,7 +713,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tmem_wait_st();
             tcgen05_fence_before();
             mbar_arrive(&h1_full[chunk]);
-            mbar_arrive(&acc_empty[b]);
+            acc_release_late();
             if (tr) trp[1] = clock64();
           } else if (type == J_L2) {
             const bool pidot = DRNN && (flags & F_PIDOT);
@@ -719,7 +727,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (pidot) {
                 // last policy Linear (A <= 8 rows) as dot products: h2 and W3 rounded to bf16 like the MMA operands would be
                 const float* w3q = m.pi_w3q + chunk * 128;
-                tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -736,7 +744,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   }
                 });
               } else if (to_xs) {
-                tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -753,7 +761,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               } else {
                 // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
                 const float* w3 = ch.w3 + chunk * 128;
-                tmem_stream_aux(tlane + TM_ACC + b * 128, 4, x0, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -765,8 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   }
                 });
               }
-              tcgen05_fence_before();
-              mbar_arrive(&acc_empty[b]);
+              acc_release_late();
             }
             if (pidot) {
               if (chunk == 3) {
@@ -980,6 +987,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           mbar_arrive(&acc_empty[grp]);
           if (tr) trp[1] = clock64();
         }
+      }
+      if (kp.trace && blockIdx.x == 0 && threadIdx.x == 128 && it < 128) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        kp.trace[3 * MAX_JOBS * 2 + it] = clock64();
+        kp.trace[3 * MAX_JOBS * 2 + 128 + it] = ns;
       }
     }
   }
@@ -1268,7 +1281,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
 
 static unsigned long long* g_tc_trace = nullptr;
 void tc_set_trace(unsigned long long* dev_buf) { g_tc_trace = dev_buf; }
-int tc_trace_slots() { return 3 * MAX_JOBS * 2; }
+int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256; }      // + end-of-tile stamps of block 0's first 128 tiles
 
 int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st) {
   if (p.H < 1 || p.H > TDMPC_MAX_H) return -1;

@@ -144,6 +144,27 @@ __device__ __forceinline__ void tmem_stream_aux(uint32_t taddr, int nsub, float4
     }
   }
 }
+// Early-release variant for one 128-column accumulator: all four 32-column groups are pulled into registers first, then
+// `release()` hands the accumulator back to the MMA warp (which can start the job after next while this one's activation
+// math is still running), then f(s, v, aux) runs on the register copy with the aux operand prefetched one group ahead.
+template <typename R, typename LA, typename F>
+__device__ __forceinline__ void tmem_drain_aux(uint32_t taddr, float4 (&xa)[8], R&& release, LA&& load_aux, F&& f) {
+  uint32_t v0[32], v1[32], v2[32], v3[32];
+  float4 xb[8];
+  tmem_ld32(taddr, v0);
+  tmem_ld32(taddr + 32, v1);
+  tmem_ld32(taddr + 64, v2);
+  tmem_ld32(taddr + 96, v3);
+  tmem_wait_ld_dep(v0); tmem_wait_ld_dep(v1); tmem_wait_ld_dep(v2); tmem_wait_ld_dep(v3);
+  release();
+  load_aux(1, xb);
+  f(0, v0, xa);
+  load_aux(2, xa);
+  f(1, v1, xb);
+  load_aux(3, xb);
+  f(2, v2, xa);
+  f(3, v3, xb);
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");

@@ -23,7 +23,9 @@ pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, 
 lib.tdmpc_debug_set_trace(C.c_void_p(buf.data_ptr()))
 pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
 torch.cuda.synchronize(); lib.tdmpc_debug_set_trace(None)
-tr = buf.cpu().numpy().reshape(3, -1, 2)
+raw = buf.cpu().numpy()
+ends = raw[-256:-128]; ns = raw[-128:][ends > 0]; ends = ends[ends > 0]
+tr = raw[:-256].reshape(3, -1, 2)
 # the job list the kernel walked (word layout: tc_model.cuh)
 lib.tdmpc_debug_jobs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]; lib.tdmpc_debug_jobs.restype = C.c_int
 words = (C.c_uint32 * 1024)()
@@ -39,3 +41,5 @@ for j, (ty, chn, c, t) in enumerate(jobs):
         row.append(f"{(s_ - t0) if s_ else 0:>10} {(e_ - t0) if e_ else 0:>8} {(e_ - s_) if s_ and e_ else 0:>6}")
     print(" | ".join(row))
 print("tile total cycles:", tr[:, :len(jobs), 1].max() - t0)
+print("tile periods of block 0 (cycles):", " ".join(str(int(x)) for x in np.diff(ends)))
+if len(ends) > 1: print(f"SM clock from globaltimer: {(ends[-1] - ends[0]) / max(1, ns[-1] - ns[0]) * 1e3:.0f} MHz over {len(ends) - 1} tiles")
