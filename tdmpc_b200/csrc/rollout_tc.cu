@@ -33,12 +33,14 @@ namespace {
 
 constexpr int TILE_ROWS = 128;
 constexpr int NTHREADS = 384;              // warps 0-3: producer / MMA / 2 idle; warps 4-7, 8-11: epilogue groups 0 and 1
-constexpr int REGS_CTRL = 56, REGS_EPI = 224;   // setmaxnreg: frees (168-56)*128 = takes (224-168)*256 registers, exactly
+// setmaxnreg: the control warpgroup frees (168-C)*128 registers, the two epilogue groups take (E-168)*256 -- exactly.  The MLP
+// kernel's MMA warp spills its barrier phases at 56 (LDL/STL inside the issue loop); the GRU kernel's epilogue needs the 224.
+template <bool DRNN> struct Regs { static constexpr int CTRL = DRNN ? 56 : 72, EPI = DRNN ? 224 : 216; };
 constexpr int XCH_FLOATS = 3 * 2 * 128;   // epilogue-group exchange: {sum, sum-of-squares, dot} x 2 groups x 128 rows
 constexpr int QC_FLOATS = 4 * 512;         // per-column constants of the current Q-head layer: bias, LN gamma, LN beta, w3
 constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
-constexpr int MAX_JOBS = 17 * TDMPC_MAX_H + 16;
+constexpr int MAX_JOBS = 18 * TDMPC_MAX_H + 16;
 constexpr uint32_t TM_ACC = 0, TM_A = 256;
 constexpr uint32_t TM_X = 256, TM_Y = 384;  // DRNN: gh_n and gi_n of the newval gate, inside the (then idle) h1 region
 constexpr int MAX_STAGES = 6;
@@ -54,7 +56,11 @@ struct KParams {
   int producers;               // producer threads (warps 0, 2, 3); divides the ring depth
   int debug;                   // experiments only (TDMPC_TC_DEBUG): bit0 = producer skips the weight copies (timing probe, wrong results)
   unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py)
+  // The job program again, in the kernel-parameter (constant) bank: the MMA warp reads it with uniform loads, which keeps its
+  // whole control flow -- and with it every MMA operand -- in the uniform datapath.
+  uint32_t jw[MAX_JOBS];
 };
+static_assert(sizeof(KParams) <= 4096, "kernel parameter space");
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float elu_fast(float x) {
@@ -62,11 +68,17 @@ __device__ __forceinline__ float elu_fast(float x) {
   return x > 0.0f ? x : e;
 }
 __device__ __forceinline__ float tanh_fast(float x) {
-#ifdef TDMPC_TANH_APPROX
-  float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-#else
   const float e = ex2_approx(x * 2.8853900817779268f);       // exp(2x)
   return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+// tanh of a value that is rounded to bf16 right afterwards (Q-head layer 1 -> operand of layer 2): one MUFU instead of two.
+// tanh.approx.f32 is good to 2^-11 relative, a quarter of the bf16 rounding step that follows; measured effect on the plan
+// values: 4e-5 median relative (gate: 1e-3).  -DTDMPC_TANH_PRECISE restores the two-MUFU form.
+__device__ __forceinline__ float tanh_bf16(float x) {
+#ifdef TDMPC_TANH_PRECISE
+  return tanh_fast(x);
+#else
+  float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 #endif
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
@@ -80,7 +92,7 @@ __device__ __forceinline__ int job_tiles(const TcModel& m, uint32_t job) {
     case J_GH: return 2;
     case J_GI: return m.nkb1 + m.gi_pad;
     case J_L2: return 8;
-    case J_L3: return m.l3rows[chain] == 128 ? 8 : 4;
+    case J_L3: return ((job >> 13) & F_EPI) ? 0 : (m.l3rows[chain] == 128 ? 8 : 4);
     case J_QL1: return 4 * m.nkb1;
     default: return 32;
   }
@@ -142,7 +154,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint64_t* x_full = hs_full + 1;
   uint64_t* r_ready = x_full + 1;
   uint64_t* u_ready = r_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_ready + 1);
+  uint64_t* d3_full = u_ready + 1;       // parked layer-3 accumulator complete (and the [z,a] tile no longer read)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 1);
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
   // holds the GRU state: fp32 [column][row] (conflict-free for thread = row) and the bf16 K-major operand HS (2 k-blocks).
   float* hf = reinterpret_cast<float*>(xs);
@@ -159,6 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     mbar_init(za_full, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
     mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(r_ready, 128); mbar_init(u_ready, 128);
+    mbar_init(d3_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   if (warp < 4) {
     // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
     // registers to the two epilogue warpgroups.
-    setmaxnreg_dec<REGS_CTRL>();
+    setmaxnreg_dec<Regs<DRNN>::CTRL>();
     if (warp != 1) {
       // ============================== producers: weight tiles, L2 -> smem ring ==============================
       // One thread can only issue a bulk copy every ~400 cycles (measured: tools/smem_contention.cu), which caps a
@@ -205,7 +219,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     } else if (warp == 1) {
       // ============================== MMA issuer ==============================
       // The whole warp walks the job list converged (waits are warp-wide); one elected lane issues.
-      const bool leader = elect_one();      // elected once while converged: the same lane issues every MMA and commit
+      // Elected once while converged: the same lane issues every MMA and commit.  The warp stays converged and the election
+      // predicate sits inside the asm statements (tc_prims.cuh, umma_*_p), which keeps the operands in uniform registers.
+      const uint32_t lead = elect_one() ? 1u : 0u;
       uint32_t stage = 0, wphase = 0;
       uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
       // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         return ring_addr + cur_stage * TILE_BYTES;
       };
       auto tile_release = [&]() {            // commit -> frees the slot when the MMAs that read it retire
-        if (leader) umma_commit(&w_empty[cur_stage]);
+        umma_commit_p(&w_empty[cur_stage], lead);
       };
       auto acc_acquire = [&](int b) {
         mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
@@ -253,17 +269,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          if (ks < nks) umma_ss(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (first && ks == 0) ? 0u : 1u);
+          if (ks < nks) umma_ss_p(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (first && ks == 0) ? 0u : 1u, lead);
       };
 
       for (int it = 0; it < my_tiles; ++it)
         for (int j = 0; j < kp.njobs; ++j) {
-          const uint32_t job = sjobs[j];
+          const uint32_t job = kp.jw[j];
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
           const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
           if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
           if (DRNN && (flags & F_WAIT_HS)) { mbar_wait(hs_full, hs_phase, 10); hs_phase ^= 1; tcgen05_fence_after(); }
+          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
@@ -273,17 +290,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               // prior / reward layer 1 of the DRNN model: A = the hidden state h' (K = 128)
               for (int kb = 0; kb < 2; ++kb) {
                 const uint32_t wt = tile_acquire();
-                if (leader) kblock_ss(d, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
+                kblock_ss(d, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
                 tile_release();
               }
             } else {
               for (int kb = 0; kb < m.nkb1; ++kb) {
                 const uint32_t wt = tile_acquire();
-                if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+                kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
                 tile_release();
               }
             }
-            if (leader) umma_commit(&acc_full[b]);
+            umma_commit_p(&acc_full[b], lead);
+            // every MMA issued so far -- the parked layer 3 and all layer-1 jobs that read this step's [z,a] -- complete
+            if (!DRNN && (flags & F_D3)) umma_commit_p(d3_full, lead);
           } else if (DRNN && type == J_G) {
             // gate pre-activation: [z,a] W_ih[g]^T + h W_hh[g]^T accumulated into one buffer (no biases, rnns.py:13-14)
             const int b = nbuf; nbuf ^= 1;
@@ -292,37 +311,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint32_t d = tmem + TM_ACC + b * 128;
             for (int kb = 0; kb < m.nkb1; ++kb) {
               const uint32_t wt = tile_acquire();
-              if (leader) kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+              kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
               tile_release();
             }
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t wt = tile_acquire();
-              if (leader) kblock_ss(d, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, false);
+              kblock_ss(d, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, false);
               tile_release();
             }
-            if (leader) umma_commit(&acc_full[b]);
+            umma_commit_p(&acc_full[b], lead);
           } else if (DRNN && type == J_GH) {
             // gh_n = h W_hh[newval]^T -> X
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t wt = tile_acquire();
-              if (leader) kblock_ss(tmem + TM_X, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
+              kblock_ss(tmem + TM_X, hs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
               tile_release();
             }
           } else if (DRNN && type == J_GI) {
             // gi_n = [z,a] W_ih[newval]^T -> Y; the n-gate epilogue forms gi_n + r * gh_n in registers (rnns.py:27)
             for (int kb = 0; kb < m.nkb1; ++kb) {
               const uint32_t wt = tile_acquire();
-              if (leader) kblock_ss(tmem + TM_Y, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+              kblock_ss(tmem + TM_Y, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
               tile_release();
             }
             for (int i = 0; i < m.gi_pad; ++i) { tile_acquire(); tile_release(); }     // padding tiles keep the ring aligned
-            if (leader) umma_commit(x_full);                                            // covers J_GH's MMAs too
+            umma_commit_p(x_full, lead);                                            // covers J_GH's MMAs too
           } else if (type == J_L2) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
             tcgen05_fence_after();
             const uint32_t d = tmem + TM_ACC + b * 128;
-            if (S == 4 && stage == 0) {
+            if (!DRNN && (flags & F_A_XS)) {
+              // reward chain of the overlapped schedule: A = its hidden activation in XS (both operands in shared memory)
+#pragma unroll
+              for (int kb = 0; kb < 8; ++kb) {
+                if (chunk == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
+                const uint32_t wt = tile_acquire();
+                kblock_ss(d, xs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
+                tile_release();
+              }
+            } else if (S == 4 && stage == 0) {
               // Static fast path.  With a 4-slot ring every layer consumes a multiple of 4 tiles, so a layer-2 job
               // always starts at slot 0 and its 8 tiles are two full turns of the ring: slot, barrier and
               // descriptor of every k-block are compile-time choices among 4 precomputed values, which keeps the
@@ -333,12 +361,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
                 mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
                 tcgen05_fence_after();
-                if (leader) {
+                {
                   const uint32_t blo = ring_lo[st];
                   const uint32_t a = tmem + TM_A + kb * 32;
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
-                  umma_commit(&w_empty[st]);
+                  for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
+                  umma_commit_p(&w_empty[st], lead);
                 }
               }
               ready = 0;                       // slot 0 again, same parity: the early probe must be redone
@@ -347,21 +375,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int kb = 0; kb < 8; ++kb) {
                 if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
                 const uint32_t wt = tile_acquire();
-                if (leader) {
+                {
                   const uint32_t blo = umma_desc_lo(wt);
                   const uint32_t a = tmem + TM_A + kb * 32;
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma_ts(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
+                  for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
                 }
                 tile_release();
               }
             }
-            if (leader) umma_commit(&acc_full[b]);
+            umma_commit_p(&acc_full[b], lead);
+          } else if (!DRNN && type == J_L3 && (flags & F_EPI)) {
+            // epilogue-only job
           } else if (type == J_L3) {
-            const int b = nbuf; nbuf ^= 1;
-            acc_acquire(b);
+            const bool park = !DRNN && (flags & F_PARK);
+            int b = 0;
+            if (!park) { b = nbuf; nbuf ^= 1; acc_acquire(b); }
             tcgen05_fence_after();
-            const uint32_t d = tmem + TM_ACC + b * 128;
+            // parked: the accumulator lives in the first columns of the h1 region, which this step's layer-2 MMAs (issued
+            // earlier, executed in order) were the last to read and nobody writes before the parked result is consumed
+            const uint32_t d = park ? tmem + TM_A : tmem + TM_ACC + b * 128;
             const uint32_t idesc = umma_idesc_bf16(128, m.n3p[chain]);
             const bool half = m.l3rows[chain] == 64;
             if (DRNN && (flags & F_A_TMEM)) {
@@ -371,10 +404,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int kb = 0; kb < 8; ++kb) {
                 if ((kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
                 if (!half || (kb & 1) == 0) wt = tile_acquire();
-                if (leader) {
+                {
                   const uint32_t blo = umma_desc_lo(wt + ((half && (kb & 1)) ? 8192u : 0u));
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma_ts(d, tmem + TM_A + kb * 32 + ks * 8, umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u);
+                  for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, tmem + TM_A + kb * 32 + ks * 8, umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u, lead);
                 }
                 if (!half || (kb & 1)) tile_release();
               }
@@ -388,12 +421,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   mbar_wait(&w_full[st], wphase, 2);
                   tcgen05_fence_after();
                 }
-                if (leader) {
+                {
                   const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES), blo = ring_lo[st] + ((kb & 1) ? (8192u >> 4) : 0u);
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
-                    umma_ss(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u);
-                  if (kb & 1) umma_commit(&w_empty[st]);
+                    umma_ss_p(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u, lead);
+                  if (kb & 1) umma_commit_p(&w_empty[st], lead);
                 }
               }
               wphase ^= 1;                     // one full turn
@@ -404,11 +437,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int kb = 0; kb < 8; ++kb) {
                 if ((kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
                 if (!half || (kb & 1) == 0) wt = tile_acquire();
-                if (leader) kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
+                kblock_ss(d, xs_addr + kb * TILE_BYTES, wt + ((half && (kb & 1)) ? 8192u : 0u), idesc, 4, kb == 0);
                 if (!half || (kb & 1)) tile_release();
               }
             }
-            if (leader) umma_commit(&acc_full[b]);
+            if (!park) umma_commit_p(&acc_full[b], lead);
           } else {
             // Q-head layers: one 512-column accumulator = both ping-pong buffers + the h1 region.
             // Each 128-column chunk is committed to its own barrier so the epilogue can accumulate the
@@ -426,15 +459,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   if (c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
                   mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
                   tcgen05_fence_after();
-                  if (leader) {
+                  {
                     const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES), blo = ring_lo[st];
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                      umma_ss(tmem + c * 128, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u);
-                    umma_commit(&w_empty[st]);
+                      umma_ss_p(tmem + c * 128, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
+                    umma_commit_p(&w_empty[st], lead);
                   }
                 }
-                if (leader) umma_commit(&q_full[c]);
+                umma_commit_p(&q_full[c], lead);
               }
               ready = 0;
             } else
@@ -442,12 +475,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int kb = 0; kb < nkb; ++kb) {
                 if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
                 const uint32_t wt = tile_acquire();
-                if (leader)
-                  kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
+                kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
                             first ? min(4, ks1_total - kb * 4) : 4, kb == 0);
                 tile_release();
               }
-              if (leader) umma_commit(&q_full[c]);
+              umma_commit_p(&q_full[c], lead);
             }
           }
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2 + 1] = clock64();
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     // the two groups drain consecutive 128-column chunks concurrently (two warps per SM sub-partition
     // hide each other's TMEM / L1 / MUFU latencies).  Row-wise reductions that span chunks (reward
     // dot product, LayerNorm statistics, Q dot product) are combined through `xch` in shared memory.
-    setmaxnreg_inc<REGS_EPI>();
+    setmaxnreg_inc<Regs<DRNN>::EPI>();
     const int grp = (warp - 4) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -468,6 +500,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
     uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
+    uint32_t d3_phase = 0;                          // overlapped schedule: phase of d3_full (group 0 only)
     uint32_t x_phase = 0, ga = 0;                  // DRNN: phase of x_full / r_ready / u_ready, group that owns the reset gate of this step
     float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
     float* x_ssq = xch + (1 * 2 + (grp ^ 1)) * 128;
@@ -659,11 +692,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           continue;
         }
         if (type <= J_L3) {
-          const int b = nbuf; nbuf ^= 1;
+          if (!DRNN && type == J_L3 && (flags & F_PARK)) continue;             // MMAs only (overlapped schedule)
+          const bool epi_only = !DRNN && type == J_L3 && (flags & F_EPI);      // epilogue of the parked layer 3: group 0
+          if (epi_only && grp != 0) continue;
+          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
+          int b = grp;
+          if (!epi_only) { b = nbuf; nbuf ^= 1; }
           const bool mine = b == grp;
           if (tr && (mine || (type == J_L2 && chain == CH_REW && chunk == 3))) trp[0] = clock64();
           if (type == J_L1) {
             if (!mine) continue;
+            if (!DRNN && (flags & F_TO_XS)) {
+              // reward chain of the overlapped schedule: h1 chunk = ELU(acc + b1) -> bf16 -> XS (the layer-3 MMAs that read
+              // XS were issued before this job's MMAs, so the accumulator barrier covers them)
+              const float* bias = ch.b1 + chunk * 128;
+              float4 x0[8];
+              load8(bias, 0, x0);
+              acc_wait();
+              tcgen05_fence_after();
+              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                             [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float h[8];
+                  h[0] = elu_fast(__uint_as_float(v[8 * i]) + x[2 * i].x); h[1] = elu_fast(__uint_as_float(v[8 * i + 1]) + x[2 * i].y);
+                  h[2] = elu_fast(__uint_as_float(v[8 * i + 2]) + x[2 * i].z); h[3] = elu_fast(__uint_as_float(v[8 * i + 3]) + x[2 * i].w);
+                  h[4] = elu_fast(__uint_as_float(v[8 * i + 4]) + x[2 * i + 1].x); h[5] = elu_fast(__uint_as_float(v[8 * i + 5]) + x[2 * i + 1].y);
+                  h[6] = elu_fast(__uint_as_float(v[8 * i + 6]) + x[2 * i + 1].z); h[7] = elu_fast(__uint_as_float(v[8 * i + 7]) + x[2 * i + 1].w);
+                  sw_store8(xs, row, chunk * 128 + s * 32 + i * 8, h);
+                }
+              });
+              fence_proxy_async_smem();
+              mbar_arrive(&xs_full[chunk]);
+              acc_release_late();
+              if (tr) trp[1] = clock64();
+              continue;
+            }
             if (DRNN && (flags & F_BN)) {
               // prior MLP layer 1: Linear, eval-mode BatchNorm1d (folded: y = acc * scale + shift'), ELU -> TMEM h1
               const float* sc = m.bn_scale + chunk * 128;
@@ -801,6 +865,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 for (int a = 0; a < 8; ++a) pd[a] = 0.0f;
                 epi_bar_sync();                  // qcs may be rewritten by the next exchange
               }
+            } else if (!DRNN && !to_xs && (flags & F_SOLO)) {
+              // overlapped schedule: this group (0: it owns G) drained all four chunks of the reward head itself
+              if (mine && chunk == 3) {
+                const float r = dot + __ldg(ch.b3);
+                G = __fadd_rn(G, __fmul_rn(p.disc[t], r));
+                rlast = r;
+                dot = 0.0f;
+              }
             } else if (!to_xs && chunk == 3) {
               // both groups hold a partial reward dot product of this row: combine in group 0
               m_dot[row] = dot;
@@ -815,48 +887,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             if (tr && (mine || (!to_xs && chunk == 3))) trp[1] = clock64();
           } else {
             if (!mine) continue;
-            acc_wait();
+            // the next step's actions of this row are fetched before waiting for the accumulator
+            float an[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) an[a] = 0.0f;
+            if (chain == CH_DYN && p.mode == MODE_VALUE && !(flags & F_LAST_STEP) && valid) {
+#pragma unroll
+              for (int a = 0; a < 8; ++a) if (a < A) an[a] = __ldg(act_row + (size_t)(t + 1) * A + a);
+            }
+            if (epi_only) { mbar_wait(d3_full, d3_phase, 15); d3_phase ^= 1; }
+            else acc_wait();
             tcgen05_fence_after();
+            const uint32_t l3src = epi_only ? tlane + TM_A : tlane + TM_ACC + b * 128;
             if (chain == CH_DYN) {
               // z' = acc + b3 -> [z', a_{t+1}, 0...] row of the next step.  Columns >= L+A of the row are
               // zero padding written once per tile and never touched again.
               const bool next_act = p.mode == MODE_VALUE && !(flags & F_LAST_STEP);
-              for (int k0 = 0; k0 < L + A; k0 += 32) {
+              for (int k0 = 0; k0 < L; k0 += 32) {
                 uint32_t v[32];
                 float4 bz[8];
+                tmem_ld32(l3src + k0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k0 < L) {
-                  tmem_ld32(tlane + TM_ACC + b * 128 + k0, v);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) if (k0 + 4 * i < L) bz[i] = ldg4(ch.b3, (k0 >> 2) + i);    // b3 is zero padded to a multiple of 4
-                  tmem_wait_ld_dep(v);
-                }
+                for (int i = 0; i < 8; ++i) bz[i] = (k0 + 4 * i < L) ? ldg4(ch.b3, (k0 >> 2) + i) : make_float4(0.f, 0.f, 0.f, 0.f);   // b3 is zero padded to a multiple of 4
+                tmem_wait_ld_dep(v);
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                   const int kk = k0 + c8 * 8;
-                  if (kk < L + A) {
+                  if (kk < L) {
                     float o[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                      const int k = kk + i;
                       const float4 bb = bz[c8 * 2 + (i >> 2)];
-                      const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
-                      float x = 0.0f;
-                      if (k < L) x = __uint_as_float(v[c8 * 8 + i]) + bv;
-                      else if (k < L + A && next_act && valid) x = __ldg(act_row + (size_t)(t + 1) * A + (k - L));
-                      o[i] = x;
+                      o[i] = __uint_as_float(v[c8 * 8 + i]) + ((i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w);
                     }
-                    if (kk + 8 <= L || next_act) sw_store8(za, row, kk, o);     // pure-z group, or the action is replaced too
+                    if (kk + 8 <= L) sw_store8(za, row, kk, o);
                     else {
-                      // group holds action columns that must survive (policy rollout / last step): z elements only
+                      // the 8-column group that also holds action columns: z elements only
 #pragma unroll
                       for (int i = 0; i < 8; ++i) if (kk + i < L) za_store1(za, row, kk + i, o[i]);
                     }
                   }
                 }
+              }
+              if (next_act) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) if (a < A) za_store1(za, row, L + a, an[a]);
+                for (int a = 8; a < A; ++a) za_store1(za, row, L + a, valid ? __ldg(act_row + (size_t)(t + 1) * A + a) : 0.0f);
               }
             } else {
               // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
@@ -883,7 +959,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
             }
             tcgen05_fence_before();
-            mbar_arrive(&acc_empty[b]);
+            if (!epi_only) mbar_arrive(&acc_empty[b]);
             if (!(chain == CH_PI && (flags & F_LAST_STEP))) {
               fence_proxy_async_smem();
               mbar_arrive(za_full);
@@ -940,6 +1016,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           const float mu = sum * (1.0f / 512.0f);
           const float var = fmaxf(ssq * (1.0f / 512.0f) - mu * mu, 0.0f);      // biased variance, as nn.LayerNorm
           const float rstd = 1.0f / sqrtf(var + 1e-5f);
+          const float nmr = -mu * rstd;
           float qdot = 0.0f;
           for (int c = grp; c < 4; c += 2) {
             tmem_stream(tlane + c * 128, 4, [&](int s, uint32_t (&v)[32]) {
@@ -948,14 +1025,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int i = 0; i < 8; ++i) {
                 const int vi = (c * 4 + s) * 8 + i;
                 const float4 x = lds4(qb + vi * 16), gg = lds4(qg + vi * 16), bb = lds4(qe + vi * 16);
-                y[4 * i] = (__uint_as_float(v[4 * i]) + x.x - mu) * rstd * gg.x + bb.x;
-                y[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + x.y - mu) * rstd * gg.y + bb.y;
-                y[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + x.z - mu) * rstd * gg.z + bb.z;
-                y[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + x.w - mu) * rstd * gg.w + bb.w;
+                y[4 * i] = fmaf(fmaf(__uint_as_float(v[4 * i]) + x.x, rstd, nmr), gg.x, bb.x);          // ((v + b) - mu) * rstd * g + beta
+                y[4 * i + 1] = fmaf(fmaf(__uint_as_float(v[4 * i + 1]) + x.y, rstd, nmr), gg.y, bb.y);
+                y[4 * i + 2] = fmaf(fmaf(__uint_as_float(v[4 * i + 2]) + x.z, rstd, nmr), gg.z, bb.z);
+                y[4 * i + 3] = fmaf(fmaf(__uint_as_float(v[4 * i + 3]) + x.w, rstd, nmr), gg.w, bb.w);
               }
               if (first) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = tanh_fast(y[i]);
+                for (int i = 0; i < 32; ++i) y[i] = tanh_bf16(y[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sw_store8(xs, row, c * 128 + s * 32 + i * 8, y + i * 8);
               } else {
@@ -1090,7 +1167,8 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
     j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
     return j;
   }
-  if (mode == MODE_VALUE) {
+  if (mode == MODE_VALUE && !getenv("TDMPC_TC_OVERLAP")) {
+    // the plain schedule (default): dynamics and reward alternate on the one TMEM h1 buffer
     for (int t = 0; t < H; ++t) {
       chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
       chain12(J_L2, CH_DYN, t, 0);
@@ -1099,6 +1177,35 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
       chain12(J_L2, CH_REW, t, 0);
     }
     chain12(J_L1, CH_PI, 0, F_WAIT_ZA);
+    chain12(J_L2, CH_PI, 0, 0);
+    j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
+    j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
+    j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
+    j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+  } else if (mode == MODE_VALUE) {
+    // Overlapped schedule (TDMPC_TC_OVERLAP=1; measured slower).  The two MLPs of a step share one TMEM h1 buffer, which forces dyn and reward to alternate and
+    // leaves the tensor pipe idle during every layer-1 epilogue.  Here the reward chain keeps ITS hidden activation in XS
+    // (free once the dynamics' layer 3 has read h2), so reward layer 2 of step t (SS, epilogue group 0) runs interleaved,
+    // chunk by chunk, with layer 1 of the next consumer of z' (dynamics of step t+1, or the terminal policy; epilogue
+    // group 1 -> TMEM h1).  The dynamics' layer-3 accumulator is parked in the h1 region so that its epilogue (z' -> [z,a])
+    // can wait until the reward's layer-1 MMAs have read the old [z,a].
+    chain12(J_L1, CH_DYN, 0, F_WAIT_ZA);
+    for (int t = 0; t < H; ++t) {
+      const bool last = t == H - 1;
+      chain12(J_L2, CH_DYN, t, 0);
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, F_PARK));
+      // d3_full: committed behind the last reward layer-1 job -- the parked layer 3 and everything that reads the old
+      // [z,a] have then completed; z' -> [z,a] (F_EPI, epilogue group 0) follows
+      for (int c = 0; c < 4; ++c) j.push_back(tc_job(J_L1, CH_REW, c, t, F_TO_XS | (c == 0 ? F_BUF0 : 0) | (c == 3 ? F_D3 : 0)));
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, F_EPI | (last ? F_LAST_STEP : 0)));
+      // reward layer 2 (R) interleaved with the next layer 1 (N): R0 R1 N0 N1 R2 N2 R3 N3 on alternating accumulators, so
+      // no job waits for the drain of its direct predecessor and the last layer-1 epilogue hides under R3's MMAs
+      const int nch = last ? CH_PI : CH_DYN, nt = last ? 0 : t + 1;
+      auto R = [&](int c) { j.push_back(tc_job(J_L2, CH_REW, c, t, F_A_XS | (c == 0 ? F_BUF0 : 0))); };
+      auto N = [&](int c) { j.push_back(tc_job(J_L1, nch, c, nt, c == 0 ? F_WAIT_ZA : 0)); };
+      R(0); R(1); N(0); N(1); R(2); N(2); R(3); N(3);
+    }
     chain12(J_L2, CH_PI, 0, 0);
     j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
     j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
@@ -1266,7 +1373,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 21) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 22) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
@@ -1298,6 +1405,11 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) kp.producers = v; }
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   if (kp.njobs <= 0) return -1;
+  {
+    const std::vector<uint32_t> jl = build_jobs(p.mode, p.H, m.drnn != 0, m.A);
+    if ((int)jl.size() != kp.njobs || kp.njobs > MAX_JOBS) return -1;
+    for (int i = 0; i < kp.njobs; ++i) kp.jw[i] = jl[i];
+  }
   if (m.drnn) rollout_tc_kernel<true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   else rollout_tc_kernel<false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   return 1;

@@ -27,11 +27,20 @@ enum TcJobFlags {
   F_A_HS = 16,       // J_L1: A operand = HS (K = hidden_dim = 128, two k-blocks) instead of [z,a]
   F_A_TMEM = 32,     // J_L3: A operand = h1 in TMEM (TS) instead of XS (the DRNN prior MLP has two layers only)
   F_BN = 64,         // J_L1 epilogue: eval-mode BatchNorm folded to y = acc * scale + shift before the ELU
-  F_PIDOT = 128      // J_L2 of the policy chain: the last Linear (A <= 8 outputs) as fp32 dot products in the epilogue (DRNN
+  F_PIDOT = 128,     // J_L2 of the policy chain: the last Linear (A <= 8 outputs) as fp32 dot products in the epilogue (DRNN
                      //   policy rollout: XS holds the GRU state, so there is no h2 operand for a layer-3 MMA)
+  // Overlapped value-mode schedule (MLP dynamics): the reward chain keeps its hidden activation in shared memory (XS) so
+  // that its 512x512 layer can run while the NEXT step's layer-1 epilogue fills the TMEM h1 buffer.
+  F_TO_XS = 256,     // J_L1: epilogue writes the XS chunk (bf16, swizzled) instead of the TMEM h1 chunk
+  F_A_XS = 512,      // J_L2: A operand = XS in shared memory (SS) instead of h1 in TMEM
+  F_SOLO = 1024,     // J_L2 reward head: all four chunks are drained by one epilogue group (no cross-group exchange)
+  F_PARK = 2048,     // J_L3: MMAs only; the accumulator is parked in the (idle) h1 region instead of a ping-pong buffer
+  F_EPI = 4096,      // J_L3: epilogue only (group 0), on the parked accumulator once `d3_full` has completed
+  F_BUF0 = 8192,     // this job uses accumulator buffer 0 (the ping-pong continues from there)
+  F_D3 = 16384       // J_L1: after this job's MMAs the MMA warp also commits d3_full
 };
 
-// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,21)
+// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,28)
 __host__ __device__ inline uint32_t tc_job(int type, int chain, int chunk, int t, int flags) {
   return (uint32_t)type | ((uint32_t)chain << 3) | ((uint32_t)chunk << 6) | ((uint32_t)t << 8) | ((uint32_t)flags << 13);
 }

@@ -250,6 +250,27 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Predicated forms for a CONVERGED issuing warp: every lane executes the statement, the elected lane's predicate sits inside
+// the asm.  The operands are then computed in uniform control flow, so ptxas keeps descriptors and TMEM addresses in uniform
+// registers (UMOV / UIADD) instead of moving them there with an R2UR per operand inside a divergent `if (leader)` region:
+// tools/mma_rate.cu measures 94 cycles per TS MMA (N = 128) for the divergent form and 64 (the pipe's rate) for this one.
+__device__ __forceinline__ void umma_ss_p(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead) : "memory");
+}
+__device__ __forceinline__ void umma_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead) : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t lead) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(lead) : "memory");
+}
+
 // ------------------------------------------------------------------------------- layout helpers
 // Byte offset of element (row, k) inside one [rows x 64] bf16 K-block stored with the 128 B swizzle.
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
