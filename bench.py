@@ -395,6 +395,32 @@ def main():
                                                  f"mixture 0.5, I=6, precision {prec}", "ms_per_plan_wall": ms1, "plans_per_sec": 1e3 / ms1}
             # BASELINE.json configs[4]: batched iCEM planning through the GRU latent dynamics (256 environments per launch here)
             extra["cfg5_b256"] = drnn_batched(dev, args.precision, 256)
+            # the batched environment-stepping loop (tdmpc_b200.PlanLoop): numpy observations in, numpy
+            # actions out, one pinned H2D + one CUDA-graph replay of the whole plan + one D2H per step (wall clock, host included)
+            from tdmpc_b200 import PlanLoop
+            for wn, bl in (("cfg3", B), ("cfg1", 1)):
+                c2 = synth.make_cfg(WORKLOADS[wn][0])
+                _, _, (h2, n2, p2, t2) = flops_and_steps(c2)
+                p1 = pl if wn == args.workload else Planner(c2.obs_shape[0], c2.action_dim, c2.latent_dim, c2.mlp_dim, c2.enc_dim,
+                                                            precision=args.precision, device=dev)
+                if p1 is not pl:
+                    p1.sync_weights({k: v.to(dev) for k, v in synth.make_told_weights(c2, 0).items()})
+                k2 = dict(horizon=h2, num_samples=n2, num_pi_trajs=p2, num_elites=c2.num_elites, iterations=c2.iterations,
+                          discount=c2.discount, temperature=c2.temperature, momentum=c2.momentum, min_std=c2.min_std, std_floor=c2.min_std)
+                res = {}
+                for graph in (True, False):
+                    loop = PlanLoop(p1, bl, k2, eval_mode=True, use_graph=graph)
+                    on = synth.make_obs(c2, 5, batch=bl)
+                    for i in range(3):
+                        loop.step(on, i == 0)
+                    nrep = 5 if bl > 1 else 50
+                    t_0 = time.perf_counter()
+                    for i in range(nrep):
+                        loop.step(on, False)
+                    res[graph] = (time.perf_counter() - t_0) * 1e3 / nrep
+                extra[f"plan_loop_{wn}_b{bl}"] = {"workload": WORKLOADS[wn][2], "envs": bl, "ms_per_step_graph": res[True], "ms_per_step_eager": res[False],
+                                                 "plans_per_sec_graph": bl * 1e3 / res[True], "h2d_bytes_per_step": loop.h2d_bytes_per_step,
+                                                 "d2h_bytes_per_step": loop.d2h_bytes_per_step, "timing": "wall clock incl. host copies"}
 
     if rank == 0:
         cpu_rate, n_cpu, med = cpu_plan_rate(cfg, sd, args.cpu_budget) if world == 1 else (None, 0, None)

@@ -147,6 +147,9 @@ typedef struct {
    * or, where a pointer is NULL, the built-in Philox4x32-10 stream keyed by (seed, call).        */
   uint64_t seed;
   uint64_t call;            /* plan-call counter: distinct noise per call                         */
+  uint64_t* call_dev;       /* device [1] or NULL: added to `call` by every kernel of the plan and incremented by the
+                             * library at the end of it, so that replays of a CUDA graph that captured this call draw
+                             * fresh noise (the batched stepping loop: train.py:94-99 calls plan once per env step)  */
   const float* noise_pi;    /* device [B, H, P, A]           TruncatedNormal draws of the pi rollout  */
   const float* noise_cem;   /* device [B, I, H, Nmax, A]     torch.randn(H,N,A) of each iteration     */
   const float* noise_term;  /* device [B, I, Tmax, A]        terminal-policy draws in estimate_value  */

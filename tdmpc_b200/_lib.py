@@ -56,7 +56,7 @@ class PlanArgs(C.Structure):
         ("n_white", C.c_int32 * TDMPC_MAX_ITERS), ("n_color1", C.c_int32 * TDMPC_MAX_ITERS),
         ("obs", _fp), ("z0", _fp), ("t0", _fp), ("prev_mean", _fp), ("elite_actions", _fp),
         ("hidden", _fp), ("hidden_out", _fp),
-        ("seed", C.c_uint64), ("call", C.c_uint64),
+        ("seed", C.c_uint64), ("call", C.c_uint64), ("call_dev", _fp),
         ("noise_pi", _fp), ("noise_cem", _fp), ("noise_term", _fp), ("noise_out", _fp), ("noise_shift", _fp), ("u_pick", _fp),
         ("action", _fp), ("metrics", _fp),
         ("tap_values", _fp), ("tap_elite_idx", _fp), ("tap_mean", _fp), ("tap_std", _fp), ("tap_z0", _fp),

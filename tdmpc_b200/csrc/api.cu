@@ -418,7 +418,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
   if (P0 > 0) {
     RolloutParams pp = rp;
     pp.mode = MODE_PI; pp.T = P0; pp.Tcap = P0; pp.pi_actions = h->pi_actions;
-    pp.noise = NoiseSrc{a->noise_pi, a->seed, a->call, NS_PI};
+    pp.noise = NoiseSrc{a->noise_pi, a->seed, a->call, NS_PI, a->call_dev};
     pp.noise_base = 0; pp.noise_bstride = (uint64_t)H * P0 * A; pp.noise_tstride = (uint64_t)P0 * A;
     if (int r = run_rollout(h, pp, st)) return r;
   }
@@ -434,7 +434,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
   // time rows of the cem noise stream: injected buffers are [.., H, Nmax, A]; the built-in colored
   // generator needs color_len white rows per trajectory
   const int Trows = (a->noise_cem || CL == 0) ? H : CL;
-  const NoiseSrc cem{a->noise_cem, a->seed, a->call, NS_CEM};
+  const NoiseSrc cem{a->noise_cem, a->seed, a->call, NS_CEM, a->call_dev};
   const uint64_t cem_bstride = (uint64_t)I * Trows * Nmax * A;
   auto spec = [&](int i) {
     SampleSpec sp{};
@@ -451,7 +451,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
   ip.init_std = a->init_std; ip.t0_all = a->t0_all; ip.t0 = a->t0; ip.has_prev = a->has_prev; ip.warm_last = a->warm_last;
   ip.prev_mean = a->prev_mean; ip.mean = h->mean; ip.std = h->std; ip.actions = h->actions;
   ip.pi_actions = h->pi_actions; ip.P0 = P0; ip.elite_actions = elites; ip.K = K; ip.shift_elites = a->shift_elites; ip.elite_h = eh;
-  ip.shift = NoiseSrc{a->noise_shift, a->seed, a->call, NS_SHIFT};
+  ip.shift = NoiseSrc{a->noise_shift, a->seed, a->call, NS_SHIFT, a->call_dev};
   ip.shift_mat = (CL > 0 && !a->noise_shift) ? a->color_mats + 2 * (size_t)CL * CL : nullptr;
   launch_init(ip, st);
   if (int r = check_launch(h, "init")) return r;
@@ -461,7 +461,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     float* values = a->tap_values ? a->tap_values + (size_t)i * B * Tmax : h->values;
     RolloutParams vp = rp;
     vp.mode = MODE_VALUE; vp.T = T; vp.Tcap = Tmax; vp.actions = h->actions; vp.values = values; vp.last_reward = h->last_reward;
-    vp.noise = NoiseSrc{a->noise_term, a->seed, a->call, NS_TERM};
+    vp.noise = NoiseSrc{a->noise_term, a->seed, a->call, NS_TERM, a->call_dev};
     vp.noise_base = (uint64_t)i * Tmax * A; vp.noise_bstride = (uint64_t)I * Tmax * A;
     if (int r = run_rollout(h, vp, st)) return r;
 
@@ -480,8 +480,8 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
       sp.pi_actions = h->pi_actions; sp.P0 = P0;
     }
     sp.eval_mode = a->eval_mode;
-    sp.out_noise = NoiseSrc{a->noise_out, a->seed, a->call, NS_OUT};
-    sp.pick = NoiseSrc{nullptr, a->seed, a->call, NS_PICK};
+    sp.out_noise = NoiseSrc{a->noise_out, a->seed, a->call, NS_OUT, a->call_dev};
+    sp.pick = NoiseSrc{nullptr, a->seed, a->call, NS_PICK, a->call_dev};
     sp.u_pick = a->u_pick;
     sp.action = a->action; sp.metrics = a->metrics; sp.prev_mean = a->prev_mean;
     sp.tap_elite_idx = a->tap_elite_idx; sp.tap_mean = a->tap_mean; sp.tap_std = a->tap_std;
@@ -493,6 +493,10 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     RolloutParams sp = rp;
     sp.mode = MODE_STEP; sp.T = 1; sp.Tcap = 1; sp.H = 1; sp.actions = a->action; sp.hidden_out = a->hidden_out;
     if (int r = run_rollout(h, sp, st)) return r;
+  }
+  if (a->call_dev) {
+    launch_bump_counter(a->call_dev, st);
+    if (int r = check_launch(h, "call counter")) return r;
   }
   return TDMPC_OK;
 }

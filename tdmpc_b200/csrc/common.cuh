@@ -43,6 +43,7 @@ struct NoiseSrc {
   const float* inj;      // nullptr -> Philox
   uint64_t seed, call;
   int stream;
+  const uint64_t* call_dev;   // optional device counter added to `call` (CUDA-graph replays: tdmpc_plan_args.call_dev)
 };
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -62,8 +63,9 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 }
 
 __device__ __forceinline__ void philox_block(const NoiseSrc& s, uint64_t e4, uint32_t out[4]) {
-  philox4x32_10((uint32_t)e4, (uint32_t)(e4 >> 32), (uint32_t)s.stream, (uint32_t)s.call,
-                (uint32_t)s.seed, (uint32_t)(s.seed >> 32) ^ (uint32_t)(s.call >> 32), out);
+  const uint64_t call = s.call + (s.call_dev ? __ldg(reinterpret_cast<const unsigned long long*>(s.call_dev)) : 0ull);
+  philox4x32_10((uint32_t)e4, (uint32_t)(e4 >> 32), (uint32_t)s.stream, (uint32_t)call,
+                (uint32_t)s.seed, (uint32_t)(s.seed >> 32) ^ (uint32_t)(call >> 32), out);
 }
 
 // i-th standard normal of the stream (Box-Muller on the Philox block holding element e).
@@ -77,6 +79,22 @@ __device__ __forceinline__ float philox_normal(const NoiseSrc& s, uint64_t e) {
   float sn, cs;
   sincospif(2.0f * u2, &sn, &cs);
   return (e & 1) ? rad * sn : rad * cs;
+}
+
+// The four standard normals of one Philox block (elements 4*e4 .. 4*e4+3), bit-identical to four philox_normal calls.
+__device__ __forceinline__ void philox_normal4(const NoiseSrc& s, uint64_t e4, float z[4]) {
+  uint32_t r[4];
+  philox_block(s, e4, r);
+#pragma unroll
+  for (int pair = 0; pair < 4; pair += 2) {
+    const float u1 = ((float)r[pair] + 1.0f) * 2.3283064365386963e-10f;
+    const float u2 = (float)r[pair + 1] * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[pair] = rad * cs;
+    z[pair + 1] = rad * sn;
+  }
 }
 
 __device__ __forceinline__ float noise_at(const NoiseSrc& s, uint64_t e) {
@@ -201,5 +219,6 @@ void launch_rollout_fp32(const ModelFp32& m, const RolloutParams& p, cudaStream_
 int  launch_rollout_tc(const struct TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st);
 void launch_select(const SelectParams& p, cudaStream_t st);
 void launch_init(const InitParams& p, cudaStream_t st);
+void launch_bump_counter(uint64_t* c, cudaStream_t st);     // *c += 1 (tdmpc_plan_args.call_dev)
 void launch_fill_noise(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out, cudaStream_t st);
 void launch_transpose_pack(const float* w, int N, int K, int Kp, int Kdst_off, float* wt, cudaStream_t st);

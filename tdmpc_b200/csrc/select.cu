@@ -98,6 +98,25 @@ __device__ void sample_rows(int b, const SampleSpec& sp, int Tcap, int H, int A,
                             float* actions, const float* pi_actions, int P0, const float* reuse, int reuse_rows) {
   const int HA = H * A;
   float* out = actions + (size_t)b * Tcap * HA;
+  const uint64_t row0 = sp.cem_base + (uint64_t)b * sp.cem_bstride;
+  if (!sp.cem.inj && sp.color_len == 0 && (A & 3) == 0 && (row0 & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // white built-in noise, A a multiple of 4: the 4 actions of one (row, step, a..a+3) group are the 4 normals of ONE
+    // Philox block -- one block and two Box-Muller pairs per 4 outputs instead of per output, one 16-byte store
+    for (int q = threadIdx.x; q < sp.N * HA / 4; q += NT) {
+      const int e = q * 4;
+      const int n = e / HA, ta = e - n * HA;
+      const int t = ta / A, a = ta - t * A;
+      float z[4];
+      philox_normal4(sp.cem, (row0 + ((uint64_t)t * sp.cem_rows + n) * A + a) >> 2, z);
+      float4 v;
+      v.x = fminf(fmaxf(mean_s[ta] + std_s[ta] * z[0], -1.0f), 1.0f);
+      v.y = fminf(fmaxf(mean_s[ta + 1] + std_s[ta + 1] * z[1], -1.0f), 1.0f);
+      v.z = fminf(fmaxf(mean_s[ta + 2] + std_s[ta + 2] * z[2], -1.0f), 1.0f);
+      v.w = fminf(fmaxf(mean_s[ta + 3] + std_s[ta + 3] * z[3], -1.0f), 1.0f);
+      if (sp.best_a && n == 0) v = make_float4(mean_s[ta], mean_s[ta + 1], mean_s[ta + 2], mean_s[ta + 3]);
+      *reinterpret_cast<float4*>(out + e) = v;
+    }
+  } else
   for (int e = threadIdx.x; e < sp.N * HA; e += NT) {
     const int n = e / HA, ta = e - n * HA;
     const int t = ta / A, a = ta - t * A;
@@ -295,6 +314,8 @@ void launch_select(const SelectParams& p, cudaStream_t st) {
   select_kernel<<<p.B, NT, smem, st>>>(p);
 }
 
+__global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }
+void launch_bump_counter(uint64_t* c, cudaStream_t st) { bump_counter_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(c)); }
 void launch_init(const InitParams& p, cudaStream_t st) { init_kernel<<<p.B, NT, 0, st>>>(p); }
 
 void launch_fill_noise(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out, cudaStream_t st) {

@@ -209,7 +209,8 @@ class Planner:
              temperature, momentum, min_std, std_floor, std_max=2.0, init_std=2.0, eval_mode=False, t0=True,
              prev_mean=None, has_prev=None, noise=None, taps=False, seed=None, call=None,
              n_samples=None, n_reuse=None, n_pi=None, out=None, elite_actions=None, elite_horizon=0,
-             warm_last=False, best_a_last=False, shift_elites=False, color=None, hidden=None, hidden_out=None):
+             warm_last=False, best_a_last=False, shift_elites=False, color=None, hidden=None, hidden_out=None,
+             call_dev=None):
         """TDMPC.plan (tdmpc.py:94-163) for a batch of independent problems.
 
         obs [B,D] (or z0 [B,L]) on the device.  prev_mean [B,H,A] is read (warm start) and
@@ -271,6 +272,9 @@ class Planner:
             self.call += 1
             call = self.call
         a.call = call
+        if call_dev is not None:            # device int64 [1]: added to `call`, incremented at the end of the plan (graph replays)
+            assert call_dev.dtype == torch.int64 and call_dev.numel() == 1 and call_dev.is_cuda
+            keep.append(call_dev); a.call_dev = call_dev.data_ptr()
         if noise is not None:
             exp = {"pi": (B, H, int(num_pi_trajs), A), "cem": (B, I, H, Nmax, A), "term": (B, I, Tmax, A), "out": (B, A),
                    "shift": (B, H, nr[0], A)}

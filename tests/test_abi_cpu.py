@@ -56,3 +56,29 @@ def test_told_state_dict_keys_match_reference_layout():
     # the reference zero-initialises the reward / Q heads (tdmpc.py:21-23)
     assert float(m._reward[-1].weight.abs().sum()) == 0.0 and float(m._Q2[-1].bias.abs().sum()) == 0.0
     m.load_state_dict(synth.make_told_weights(cfg))
+
+
+def test_batched_episodes_mirror_reference_episode_layout():
+    """tdmpc_b200.BatchedEpisodes keeps, per environment, the fields of the reference's Episode (helper.py:383-415):
+    obs [T+1, D] with the reset observation first, action [T, A], reward [T], cumulative_reward, done, first."""
+    import numpy as np
+    from tdmpc_b200.collector import BatchedEpisodes
+    B, T, D, A = 3, 4, 5, 2
+    rng = np.random.RandomState(0)
+    obs0 = rng.randn(B, D).astype(np.float32)
+    ep = BatchedEpisodes(B, T, D, A, obs0)
+    assert ep.first and len(ep) == 0
+    obs, act, rew = [], [], []
+    for t in range(T):
+        o, a, r = rng.randn(B, D).astype(np.float32), rng.randn(B, A).astype(np.float32), rng.randn(B).astype(np.float32)
+        ep += (o, a, r, t == T - 1)
+        obs.append(o); act.append(a); rew.append(r)
+    assert len(ep) == T and not ep.first and ep.done.all()
+    e1 = ep.episode(1)
+    assert tuple(e1.obs.shape) == (T + 1, D) and tuple(e1.action.shape) == (T, A) and tuple(e1.reward.shape) == (T,)
+    assert np.array_equal(e1.obs[0].numpy(), obs0[1]) and np.array_equal(e1.obs[3].numpy(), obs[2][1])
+    assert np.array_equal(e1.action[2].numpy(), act[2][1]) and np.array_equal(e1.reward.numpy(), np.stack(rew)[:, 1])
+    assert abs(e1.cumulative_reward - float(np.stack(rew)[:, 1].astype(np.float64).sum())) < 1e-6 and e1.done
+    import pytest
+    with pytest.raises(IndexError):
+        ep.add(obs[0], act[0], rew[0], True)

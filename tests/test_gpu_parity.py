@@ -688,6 +688,43 @@ def test_plan_is_cuda_graph_capturable():
             assert torch.equal(out["action"], a_eager) and torch.equal(prev, p_eager), prec
 
 
+def test_plan_loop_graph_replay_matches_eager_calls():
+    """tdmpc_b200.PlanLoop (reference loop train.py:94-99): the CUDA-graph replayed stepping loop gives,
+    step after step, bit for bit the actions / metrics of individual Planner.plan calls with call = call0 + step -- i.e.
+    every replay draws fresh noise through the device-side call counter -- including per-environment episode resets
+    (t0 flags) in the middle, in both precision modes."""
+    gu = _gu()
+    from tdmpc_b200 import PlanLoop
+    cfg = synth.make_cfg("tiny")
+    sd = synth.make_told_weights(cfg, 4)
+    B, steps = 5, 4
+    rng = np.random.RandomState(7)
+    obs_seq = rng.randn(steps, B, cfg.obs_shape[0]).astype(np.float32)
+    t0_seq = np.zeros((steps, B), dtype=np.uint8); t0_seq[0] = 1; t0_seq[2, [1, 3]] = 1        # two environments reset at step 2
+    for prec in ("fp32", "bf16"):
+        kw = gu.plan_kwargs(cfg)
+        pl = gu.make_planner(cfg, sd, prec)
+        loop = PlanLoop(pl, B, kw, eval_mode=False, use_graph=True, seed=11, call0=100)
+        got = []
+        for s_ in range(steps):
+            a, m = loop.step(obs_seq[s_], t0_seq[s_])
+            got.append((a.copy(), m.copy()))
+        assert loop.graph is not None
+        pl2 = gu.make_planner(cfg, sd, prec)
+        prev = torch.zeros(B, kw["horizon"], cfg.action_dim, device="cuda")
+        for s_ in range(steps):
+            res = pl2.plan(torch.from_numpy(obs_seq[s_]).cuda(), **kw, eval_mode=False, t0=torch.from_numpy(t0_seq[s_]).cuda(),
+                           prev_mean=prev, has_prev=True, seed=11, call=100 + s_)
+            torch.cuda.synchronize()
+            assert np.array_equal(res["action"].cpu().numpy(), got[s_][0]), (prec, s_)
+            assert np.array_equal(res["metrics"].cpu().numpy(), got[s_][1]), (prec, s_)
+        # different steps really used different noise: same observation twice gives different exploration noise
+        loop2 = PlanLoop(pl, B, kw, eval_mode=False, use_graph=True, seed=11, call0=100)
+        a0 = loop2.step(obs_seq[0], 1)[0].copy()
+        a1 = loop2.step(obs_seq[0], 1)[0].copy()
+        assert not np.array_equal(a0, a1)
+
+
 # ------------------------------------------------------------------------------------------------- full size
 def test_full_size_properties_cfg3():
     """BASELINE.json's batched configuration (4096 quadrotor environments x 537 trajectories x H=5) through properties that
