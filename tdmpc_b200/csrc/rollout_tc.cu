@@ -204,11 +204,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
             for (int i = 0; i < nt; ++i) {
               if (mine == (uint32_t)pk) {
+                const int ti = i;
                 mbar_wait(&w_empty[stage], phase ^ 1, 1);
                 if (kp.debug & 1) mbar_arrive(&w_full[stage]);
                 else {
                   mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
-                  bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)i * TILE_BYTES, TILE_BYTES, &w_full[stage]);
+                  bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)ti * TILE_BYTES, TILE_BYTES, &w_full[stage]);
                 }
               }
               if (++mine == (uint32_t)P) mine = 0;
@@ -451,7 +452,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const bool first = type == J_QL1;
             const int nkb = first ? m.nkb1 : 8;
             if (!first && S == 4 && stage == 0) {
-              // static fast path (see layer 2): 4 chunks x 8 tiles = 8 full turns of the ring
+              // static fast path (see layer 2): 4 chunks x 8 tiles = 8 full turns of the ring.  (N = 256 instructions over
+              // chunk pairs were tried -- an SS MMA is bound by its operand reads and a 256-wide one reads the A slice once
+              // for two chunks, 171 vs 2 x 107 cycles in tools/mma_rate.cu -- but the LayerNorm statistics pass then starts
+              // a chunk later and the tile got 1 % slower.)
               for (int c = 0; c < 4; ++c) {
 #pragma unroll
                 for (int kb = 0; kb < 8; ++kb) {
@@ -895,6 +899,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int a = 0; a < 8; ++a) if (a < A) an[a] = __ldg(act_row + (size_t)(t + 1) * A + a);
             }
+            // policy head: the noise of the first four action dimensions does not depend on the accumulator either (one
+            // Philox block when the stream offset is 4-aligned, e.g. A = 4)
+            const bool terminal = (flags & F_TERMINAL) != 0;
+            const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
+            const bool nz4 = chain == CH_PI && !p.noise.inj && (nbase & 3) == 0 && p.min_std > 0.0f;
+            float zn[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nz4 && valid) philox_normal4(p.noise, nbase >> 2, zn);
             if (epi_only) { mbar_wait(d3_full, d3_phase, 15); d3_phase ^= 1; }
             else acc_wait();
             tcgen05_fence_after();
@@ -936,12 +947,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
             } else {
               // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
-              const bool terminal = (flags & F_TERMINAL) != 0;
-              const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
 #pragma unroll 1
               for (int a0 = 0; a0 < A; a0 += 4) {
                 uint32_t v[4];
                 tmem_ld4(tlane + TM_ACC + b * 128 + a0, v);
+                if (nz4 && a0 > 0 && valid) philox_normal4(p.noise, (nbase + a0) >> 2, zn);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -950,7 +960,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                     float x = 0.0f;
                     if (valid) {
                       const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
-                      x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
+                      x = policy_sample(mu, p.min_std, nz4 ? zn[i] : noise_at(p.noise, nbase + a));
                       if (!terminal) pi_row[(size_t)t * A + a] = x;
                     }
                     if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
