@@ -40,7 +40,7 @@ constexpr int XCH_FLOATS = 3 * 2 * 128;   // epilogue-group exchange: {sum, sum-
 constexpr int QC_FLOATS = 4 * 512;         // per-column constants of the current Q-head layer: bias, LN gamma, LN beta, w3
 constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
-constexpr int MAX_JOBS = 18 * TDMPC_MAX_H + 16;
+constexpr int MAX_JOBS = 22 * TDMPC_MAX_H + 20;
 constexpr uint32_t TM_ACC = 0, TM_A = 256;
 constexpr uint32_t TM_X = 256, TM_Y = 384;  // DRNN: gh_n and gi_n of the newval gate, inside the (then idle) h1 region
 constexpr int MAX_STAGES = 6;
@@ -59,6 +59,7 @@ struct KParams {
   // The job program again, in the kernel-parameter (constant) bank: the MMA warp reads it with uniform loads, which keeps its
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
   uint32_t jw[MAX_JOBS];
+  int one;                     // always 1 (an opaque branch condition: tc_prims.cuh, tmem_drain_aux)
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter space");
 
@@ -91,7 +92,7 @@ __device__ __forceinline__ int job_tiles(const TcModel& m, uint32_t job) {
     case J_G: return m.nkb1 + 2;
     case J_GH: return 2;
     case J_GI: return m.nkb1 + m.gi_pad;
-    case J_L2: return 8;
+    case J_L2: return ((job >> 13) & (F_KLO | F_KHI)) ? 4 : 8;
     case J_L3: return ((job >> 13) & F_EPI) ? 0 : (m.l3rows[chain] == 128 ? 8 : 4);
     case J_QL1: return 4 * m.nkb1;
     default: return 32;
@@ -105,7 +106,7 @@ __device__ __forceinline__ uint32_t job_first_tile(const TcModel& m, uint32_t jo
     case J_G: return m.g_tile[chunk];
     case J_GH: return m.gh_tile;
     case J_GI: return m.gi_tile;
-    case J_L2: return c.l2_tile + chunk * 8;
+    case J_L2: return c.l2_tile + chunk * 8 + (((job >> 13) & F_KHI) ? 4 : 0);
     case J_L3: return c.l3_tile;
     case J_QL1: return c.l1_tile;
     default: return c.l2_tile;
@@ -337,6 +338,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             for (int i = 0; i < m.gi_pad; ++i) { tile_acquire(); tile_release(); }     // padding tiles keep the ring aligned
             umma_commit_p(x_full, lead);                                            // covers J_GH's MMAs too
+          } else if (!DRNN && type == J_L2 && (flags & (F_KLO | F_KHI))) {
+            // half of a layer-2 chunk (see F_KLO): 4 k-blocks = 4 tiles = one turn of the ring
+            const bool hi = (flags & F_KHI) != 0;
+            const int b = nbuf; nbuf ^= 1;                 // KLO c0, KLO c1, KHI c0, KHI c1: the ping-pong lands on the same buffers
+            if (!hi) acc_acquire(b);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + TM_ACC + b * 128;
+            const int kb0 = hi ? 4 : 0;
+            if (S == 4 && stage == 0) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const int kb = kb0 + k4;
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                mbar_wait(&w_full[k4], wphase, 2);
+                tcgen05_fence_after();
+                const uint32_t blo = ring_lo[k4];
+                const uint32_t a = tmem + TM_A + kb * 32;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
+                umma_commit_p(&w_empty[k4], lead);
+              }
+              wphase ^= 1;                     // one full turn
+              ready = 0;
+            } else {
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const int kb = kb0 + k4;
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                const uint32_t wt = tile_acquire();
+                const uint32_t blo = umma_desc_lo(wt);
+                const uint32_t a = tmem + TM_A + kb * 32;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
+                tile_release();
+              }
+            }
+            if (hi) umma_commit_p(&acc_full[b], lead);
           } else if (type == J_L2) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
@@ -697,6 +734,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         }
         if (type <= J_L3) {
           if (!DRNN && type == J_L3 && (flags & F_PARK)) continue;             // MMAs only (overlapped schedule)
+          if (!DRNN && type == J_L2 && (flags & F_KLO)) continue;              // first half of a split layer-2 chunk: MMAs only
           const bool epi_only = !DRNN && type == J_L3 && (flags & F_EPI);      // epilogue of the parked layer 3: group 0
           if (epi_only && grp != 0) continue;
           if (!DRNN && (flags & F_BUF0)) nbuf = 0;
@@ -714,7 +752,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               load8(bias, 0, x0);
               acc_wait();
               tcgen05_fence_after();
-              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                              [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -742,7 +780,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int i = 0; i < 8; ++i) x0[i] = ldg4(sc, i);
               acc_wait();
               tcgen05_fence_after();
-              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int sg, float4 (&x)[8]) {
+              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int sg, float4 (&x)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = ldg4(sc, sg * 8 + i);
               }, [&](int sg, uint32_t (&v)[32], float4 (&x)[8]) {
@@ -768,7 +806,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             load8(bias, 0, x0);
             acc_wait();
             tcgen05_fence_after();
-            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
               uint32_t o[16];
 #pragma unroll
@@ -795,7 +833,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (pidot) {
                 // last policy Linear (A <= 8 rows) as dot products: h2 and W3 rounded to bf16 like the MMA operands would be
                 const float* w3q = m.pi_w3q + chunk * 128;
-                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -812,7 +850,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   }
                 });
               } else if (to_xs) {
-                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -829,7 +867,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               } else {
                 // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
                 const float* w3 = ch.w3 + chunk * 128;
-                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -878,7 +916,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 dot = 0.0f;
               }
             } else if (!to_xs && chunk == 3) {
-              // both groups hold a partial reward dot product of this row: combine in group 0
+              // both groups hold a partial reward dot product of this row: combine in group 0.  (A one-way hand-over -- group 1
+              // publishes its partial sum and moves on -- was measured: no gain, group 0's three chunks in a row stay critical.)
               m_dot[row] = dot;
               epi_bar_sync();
               if (grp == 0) {
@@ -1135,6 +1174,14 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
   auto chain12 = [&](int type, int chain, int t, int first_flags) {
     for (int c = 0; c < 4; ++c) j.push_back(tc_job(type, chain, c, t, c == 0 ? first_flags : 0));
   };
+  // layer 2 with chunks 0 and 1 split over k (tc_model.cuh, F_KLO): KLO c0, KLO c1, KHI c0, KHI c1, c2, c3
+  const bool split = !drnn && getenv("TDMPC_TC_SPLIT");      // measured slower than whole chunks: off
+  auto layer2 = [&](int chain, int t) {
+    if (!split) { chain12(J_L2, chain, t, 0); return; }
+    j.push_back(tc_job(J_L2, chain, 0, t, F_KLO)); j.push_back(tc_job(J_L2, chain, 1, t, F_KLO));
+    j.push_back(tc_job(J_L2, chain, 0, t, F_KHI)); j.push_back(tc_job(J_L2, chain, 1, t, F_KHI));
+    j.push_back(tc_job(J_L2, chain, 2, t, 0)); j.push_back(tc_job(J_L2, chain, 3, t, 0));
+  };
   if (drnn) {
     // DSSM.next with GRU dynamics (tdmpc_icem_similarity_drnn.py:56-59): gates, h', prior MLP -> z', reward MLP(h').
     // Value mode only: the (short) policy rollout and the single post-plan step run on the fp32 kernel.
@@ -1181,13 +1228,13 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
     // the plain schedule (default): dynamics and reward alternate on the one TMEM h1 buffer
     for (int t = 0; t < H; ++t) {
       chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
-      chain12(J_L2, CH_DYN, t, 0);
+      layer2(CH_DYN, t);
       chain12(J_L1, CH_REW, t, 0);
       j.push_back(tc_job(J_L3, CH_DYN, 0, t, t == H - 1 ? F_LAST_STEP : 0));
-      chain12(J_L2, CH_REW, t, 0);
+      layer2(CH_REW, t);
     }
     chain12(J_L1, CH_PI, 0, F_WAIT_ZA);
-    chain12(J_L2, CH_PI, 0, 0);
+    layer2(CH_PI, 0);
     j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
     j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
     j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
@@ -1226,11 +1273,11 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
     for (int t = 0; t < H; ++t) {
       const bool last = t == H - 1;
       chain12(J_L1, CH_PI, t, F_WAIT_ZA);
-      chain12(J_L2, CH_PI, t, 0);
+      layer2(CH_PI, t);
       j.push_back(tc_job(J_L3, CH_PI, 0, t, last ? F_LAST_STEP : 0));
       if (!last) {                      // the reference also steps z after the last action; its result is unused
         chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
-        chain12(J_L2, CH_DYN, t, 0);
+        layer2(CH_DYN, t);
         j.push_back(tc_job(J_L3, CH_DYN, 0, t, 0));
       }
     }
@@ -1410,6 +1457,7 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   const long long total = (long long)p.B * p.T;
   kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
   kp.trace = g_tc_trace;
+  kp.one = 1;
   { const char* e = getenv("TDMPC_TC_DEBUG"); kp.debug = e ? atoi(e) : 0; }
   kp.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) kp.producers = v; }

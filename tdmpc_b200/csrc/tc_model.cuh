@@ -37,7 +37,12 @@ enum TcJobFlags {
   F_PARK = 2048,     // J_L3: MMAs only; the accumulator is parked in the (idle) h1 region instead of a ping-pong buffer
   F_EPI = 4096,      // J_L3: epilogue only (group 0), on the parked accumulator once `d3_full` has completed
   F_BUF0 = 8192,     // this job uses accumulator buffer 0 (the ping-pong continues from there)
-  F_D3 = 16384       // J_L1: after this job's MMAs the MMA warp also commits d3_full
+  F_D3 = 16384,      // J_L1: after this job's MMAs the MMA warp also commits d3_full
+  // Split layer 2: chunk 0 and chunk 1 of a 512 x 512 layer first accumulate over the k-blocks of h1 chunks 0-1 only
+  // (F_KLO, no epilogue), which are written first, and later over the rest (F_KHI, epilogue as usual).  The tensor pipe
+  // then has two half-jobs of work while the layer-1 epilogue is still producing h1 chunks 2-3.
+  F_KLO = 32768,     // J_L2: k-blocks 0-3 only; acquires the accumulator, no commit, no epilogue
+  F_KHI = 65536      // J_L2: k-blocks 4-7 onto the accumulator its F_KLO half started; commit + epilogue
 };
 
 // job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,28)
