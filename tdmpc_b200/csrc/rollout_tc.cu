@@ -54,7 +54,6 @@ struct KParams {
   int stages;
   int num_tiles;
   int producers;               // producer threads (warps 0, 2, 3); divides the ring depth
-  int cluster;                 // CTAs per cluster sharing ONE weight stream (bulk-TMA multicast): 1 or 2
   int debug;                   // experiments only (TDMPC_TC_DEBUG): bit0 = producer skips the weight copies (timing probe, wrong results)
   unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py)
   // The job program again, in the kernel-parameter (constant) bank: the MMA warp reads it with uniform loads, which keeps its
@@ -168,7 +167,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 
   for (int i = threadIdx.x; i < kp.njobs; i += NTHREADS) sjobs[i] = kp.jobs[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kp.cluster); }   // every CTA of the cluster releases a slot
+    for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     for (int i = 0; i < 4; ++i) { mbar_init(&h1_full[i], 128); mbar_init(&xs_full[i], 128); }
     mbar_init(za_full, 128);
@@ -180,18 +179,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
-  if (kp.cluster > 1) cluster_sync_all();       // the peer's mbarriers are initialised before anything is multicast to them
   tcgen05_fence_after();
   if (*tmem_slot != 0) asm volatile("trap;");   // all 512 columns of the SM are ours: the base is 0, so TMEM addresses are immediates
   constexpr uint32_t tmem = 0;
-  // The CTAs of a cluster walk the same job list over C consecutive tiles (one each) in lock-step, because they share one
-  // weight stream; a tile past the end is processed as all-invalid rows.
-  const int C = kp.cluster;
-  const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
-  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
-  const int n_clusters = (int)gridDim.x / C, cluster_id = (int)blockIdx.x / C;
-  const int n_groups = (kp.num_tiles + C - 1) / C;
-  const int my_tiles = (n_groups - cluster_id + n_clusters - 1) / n_clusters;
+  const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < 4) {
     // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
@@ -206,10 +197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const int P = kp.producers;
       const int pk = warp == 0 ? 0 : warp - 1;
       if (lane == 0 && pk < P) {
-        // In a cluster every CTA arms its own w_full[stage] for every tile and the CTAs take turns issuing the copy, multicast
-        // to all of them; w_empty[stage] collects one arrival per CTA (the MMA warps commit to every CTA), so the issuer knows
-        // the slot is free everywhere before it overwrites it.
-        uint32_t stage = 0, phase = 0, mine = 0, turn = 0;    // mine: tile counter mod P; turn: tile counter mod C
+        uint32_t stage = 0, phase = 0, mine = 0;    // mine: tile counter mod P
         for (int it = 0; it < my_tiles; ++it)
           for (int j = 0; j < kp.njobs; ++j) {
             const uint32_t job = sjobs[j];
@@ -222,12 +210,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 if (kp.debug & 1) mbar_arrive(&w_full[stage]);
                 else {
                   mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
-                  if (C == 1) bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)ti * TILE_BYTES, TILE_BYTES, &w_full[stage]);
-                  else if (turn == crank)
-                    bulk_g2s_multicast(wring + stage * TILE_BYTES, src + (size_t)ti * TILE_BYTES, TILE_BYTES, &w_full[stage], cmask);
+                  bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)ti * TILE_BYTES, TILE_BYTES, &w_full[stage]);
                 }
               }
-              if (++turn == (uint32_t)C) turn = 0;
               if (++mine == (uint32_t)P) mine = 0;
               if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
             }
@@ -239,10 +224,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       // Elected once while converged: the same lane issues every MMA and commit.  The warp stays converged and the election
       // predicate sits inside the asm statements (tc_prims.cuh, umma_*_p), which keeps the operands in uniform registers.
       const uint32_t lead = elect_one() ? 1u : 0u;
-      auto w_release = [&](uint32_t st) {     // the slot is free once the MMAs issued so far retire -- in every CTA of the cluster
-        if (C == 1) umma_commit_p(&w_empty[st], lead);
-        else umma_commit_mc_p(&w_empty[st], cmask, lead);
-      };
       uint32_t stage = 0, wphase = 0;
       uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
       // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
@@ -269,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         return ring_addr + cur_stage * TILE_BYTES;
       };
       auto tile_release = [&]() {            // commit -> frees the slot when the MMAs that read it retire
-        w_release(cur_stage);
+        umma_commit_p(&w_empty[cur_stage], lead);
       };
       auto acc_acquire = [&](int b) {
         mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
@@ -376,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 const uint32_t a = tmem + TM_A + kb * 32;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
-                w_release(k4);
+                umma_commit_p(&w_empty[k4], lead);
               }
               wphase ^= 1;                     // one full turn
               ready = 0;
@@ -423,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   const uint32_t a = tmem + TM_A + kb * 32;
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
-                  w_release(st);
+                  umma_commit_p(&w_empty[st], lead);
                 }
               }
               ready = 0;                       // slot 0 again, same parity: the early probe must be redone
@@ -483,7 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
                     umma_ss_p(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (kb | ks) ? 1u : 0u, lead);
-                  if (kb & 1) w_release(st);
+                  if (kb & 1) umma_commit_p(&w_empty[st], lead);
                 }
               }
               wphase ^= 1;                     // one full turn
@@ -524,7 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                       umma_ss_p(tmem + c * 128, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
-                    w_release(st);
+                    umma_commit_p(&w_empty[st], lead);
                   }
                 }
                 umma_commit_p(&q_full[c], lead);
@@ -587,7 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     };
 
     for (int it = 0; it < my_tiles; ++it) {
-      const long long g = (((long long)cluster_id + (long long)it * n_clusters) * C + crank) * TILE_ROWS + row;
+      const long long g = ((long long)blockIdx.x + (long long)it * gridDim.x) * TILE_ROWS + row;
       const bool valid = g < total;
       const long long pb = valid ? g / p.T : 0;
       const long long pj = valid ? g - pb * p.T : 0;
@@ -1144,7 +1125,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 
   tcgen05_fence_before();
   __syncthreads();
-  if (kp.cluster > 1) cluster_sync_all();       // no CTA leaves while the peer may still signal its barriers or write its ring
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
@@ -1481,29 +1461,14 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   { const char* e = getenv("TDMPC_TC_DEBUG"); kp.debug = e ? atoi(e) : 0; }
   kp.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) kp.producers = v; }
-  // Optional (TDMPC_TC_CLUSTER=2): CTA pairs share one multicast weight stream, each tile is read from L2 once per pair.  The
-  // L2 -> SM path is not a throughput limit; the idea was energy (at full batch the board sits at its power cap and the
-  // weight stream is ~13 % of the power).
-  int C = 1;      // measured at the power cap: pairs in lock-step lose more cycles (309k -> 339k per tile) than the halved L2 reads save
-  if (const char* e = getenv("TDMPC_TC_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2) C = v; }
-  if (kp.num_tiles < 2 * C) C = 1;
-  kp.cluster = C;
-  const int groups = (kp.num_tiles + C - 1) / C;
-  const int max_clusters = num_sms / C;
-  const int grid = (groups < max_clusters ? groups : max_clusters) * C;
+  const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   if (kp.njobs <= 0) return -1;
   {
     const std::vector<uint32_t> jl = build_jobs(p.mode, p.H, m.drnn != 0, m.A);
     if ((int)jl.size() != kp.njobs || kp.njobs > MAX_JOBS) return -1;
     for (int i = 0; i < kp.njobs; ++i) kp.jw[i] = jl[i];
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = m.smem_bytes; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t le = m.drnn ? cudaLaunchKernelEx(&cfg, rollout_tc_kernel<true>, kp) : cudaLaunchKernelEx(&cfg, rollout_tc_kernel<false>, kp);
-  if (le != cudaSuccess) return -1;
+  if (m.drnn) rollout_tc_kernel<true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  else rollout_tc_kernel<false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   return 1;
 }

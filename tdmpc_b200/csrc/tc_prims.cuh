@@ -49,9 +49,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-#ifdef TDMPC_WAIT_SLEEP
-    __nanosleep(TDMPC_WAIT_SLEEP);
-#endif
     if (clock64() - t0 > 4000000000LL) {
 #ifdef TDMPC_DEBUG_HANG
       printf("tdmpc_b200: mbarrier wait timed out (tag %d, smem 0x%x, parity %u, block %d, thread %d)\n", tag, smem_u32(bar),
@@ -73,20 +70,6 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// Same copy, multicast to every CTA of the cluster whose bit is set in `mask`: the bytes land at the same shared-memory
-// offset in each of them and complete_tx is signalled on the mbarrier at the same offset there, so the tile is read from
-// L2 (and crosses the crossbar) once per cluster.
-__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-// ------------------------------------------------------------------------------- thread-block cluster
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA in the cluster
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------- TMEM
@@ -300,14 +283,6 @@ __device__ __forceinline__ void umma_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint
 __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t lead) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(lead) : "memory");
-}
-
-// commit arriving on the mbarrier at this offset in every CTA of the cluster named by `mask` (a weight-ring slot that was
-// filled by a multicast copy is free only when every CTA's MMAs have read it)
-__device__ __forceinline__ void umma_commit_mc_p(uint64_t* bar, uint16_t mask, uint32_t lead) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-               ::"r"(smem_u32(bar)), "h"(mask), "r"(lead) : "memory");
 }
 
 // ------------------------------------------------------------------------------- layout helpers
