@@ -21,8 +21,6 @@ independently (`_prev_mean` of that environment is zeroed, tdmpc.py:123-126).
 for B environments in pinned host memory, written once per step, handed out per environment in the
 reference's layout so that `buffer += episode` keeps working.
 """
-from types import SimpleNamespace
-
 import numpy as np
 import torch
 
@@ -146,7 +144,21 @@ class BatchedEpisodes:
     __iadd__ = lambda self, tr: self.add(*tr)
 
     def episode(self, i):
-        n = self._idx
-        return SimpleNamespace(obs=self.obs[i, :n + 1], action=self.action[i, :n], reward=self.reward[i, :n],
-                               cumulative_reward=float(self.cumulative_reward[i]), done=bool(self.done[i]), first=n == 0,
-                               __len__=lambda: n, _idx=n)
+        return EpisodeView(self.obs[i, :self._idx + 1], self.action[i, :self._idx], self.reward[i, :self._idx],
+                           float(self.cumulative_reward[i]), bool(self.done[i]))
+
+
+class EpisodeView:
+    """One environment's episode in the reference's `Episode` layout (helper.py:383-415): what `ReplayBuffer.__add__` reads."""
+
+    def __init__(self, obs, action, reward, cumulative_reward, done):
+        self.obs, self.action, self.reward = obs, action, reward
+        self.cumulative_reward, self.done = cumulative_reward, done
+        self._idx = action.shape[0]
+
+    def __len__(self):
+        return self._idx
+
+    @property
+    def first(self):
+        return self._idx == 0

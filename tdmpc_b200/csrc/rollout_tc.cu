@@ -54,7 +54,8 @@ struct KParams {
   int stages;
   int num_tiles;
   int producers;               // producer threads (warps 0, 2, 3); divides the ring depth
-  int debug;                   // experiments only (TDMPC_TC_DEBUG): bit0 = producer skips the weight copies (timing probe, wrong results)
+  int debug;                   // experiments only (TDMPC_TC_DEBUG; wrong results): bit0 = producers skip the weight copies, bit1 = accumulators
+                               //   are released after the activation math, bit2 = the activation math of the MLP layers is skipped
   unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py)
   // The job program again, in the kernel-parameter (constant) bank: the MMA warp reads it with uniform loads, which keeps its
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
@@ -555,6 +556,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       ++fcnt;
     };
     // early release: the accumulator goes back to the MMA warp as soon as it sits in registers (tmem_drain_aux)
+    const int go_math = (kp.debug & 4) ? 0 : kp.one;     // experiment (bit 2): skip the activation math of the MLP layers (power probe, wrong results)
     const bool late_release = (kp.debug & 2) != 0;      // experiment: release after the activation math, as before
     auto acc_release = [&]() {
       if (!late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
@@ -752,7 +754,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               load8(bias, 0, x0);
               acc_wait();
               tcgen05_fence_after();
-              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                              [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int i = 0; i < 8; ++i) x0[i] = ldg4(sc, i);
               acc_wait();
               tcgen05_fence_after();
-              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int sg, float4 (&x)[8]) {
+              tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int sg, float4 (&x)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = ldg4(sc, sg * 8 + i);
               }, [&](int sg, uint32_t (&v)[32], float4 (&x)[8]) {
@@ -806,7 +808,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             load8(bias, 0, x0);
             acc_wait();
             tcgen05_fence_after();
-            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
               uint32_t o[16];
 #pragma unroll
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (pidot) {
                 // last policy Linear (A <= 8 rows) as dot products: h2 and W3 rounded to bf16 like the MMA operands would be
                 const float* w3q = m.pi_w3q + chunk * 128;
-                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -850,7 +852,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   }
                 });
               } else if (to_xs) {
-                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -867,7 +869,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               } else {
                 // reward head (N = 1): fp32 dot product with w3 (helper.py:169-176 last Linear)
                 const float* w3 = ch.w3 + chunk * 128;
-                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, kp.one, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+                tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                                 [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {

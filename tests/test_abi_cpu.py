@@ -75,6 +75,7 @@ def test_batched_episodes_mirror_reference_episode_layout():
         obs.append(o); act.append(a); rew.append(r)
     assert len(ep) == T and not ep.first and ep.done.all()
     e1 = ep.episode(1)
+    assert len(e1) == T and not e1.first
     assert tuple(e1.obs.shape) == (T + 1, D) and tuple(e1.action.shape) == (T, A) and tuple(e1.reward.shape) == (T,)
     assert np.array_equal(e1.obs[0].numpy(), obs0[1]) and np.array_equal(e1.obs[3].numpy(), obs[2][1])
     assert np.array_equal(e1.action[2].numpy(), act[2][1]) and np.array_equal(e1.reward.numpy(), np.stack(rew)[:, 1])
