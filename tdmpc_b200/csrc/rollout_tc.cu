@@ -909,14 +909,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 for (int a = 0; a < 8; ++a) pd[a] = 0.0f;
                 epi_bar_sync();                  // qcs may be rewritten by the next exchange
               }
-            } else if (!DRNN && !to_xs && (flags & F_SOLO)) {
-              // overlapped schedule: this group (0: it owns G) drained all four chunks of the reward head itself
-              if (mine && chunk == 3) {
-                const float r = dot + __ldg(ch.b3);
-                G = __fadd_rn(G, __fmul_rn(p.disc[t], r));
-                rlast = r;
-                dot = 0.0f;
-              }
             } else if (!to_xs && chunk == 3) {
               // both groups hold a partial reward dot product of this row: combine in group 0.  (A one-way hand-over -- group 1
               // publishes its partial sum and moves on -- was measured: no gain, group 0's three chunks in a row stay critical.)
@@ -1243,12 +1235,12 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
     j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
     j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
   } else if (mode == MODE_VALUE) {
-    // Overlapped schedule (TDMPC_TC_OVERLAP=1; measured slower).  The two MLPs of a step share one TMEM h1 buffer, which forces dyn and reward to alternate and
-    // leaves the tensor pipe idle during every layer-1 epilogue.  Here the reward chain keeps ITS hidden activation in XS
-    // (free once the dynamics' layer 3 has read h2), so reward layer 2 of step t (SS, epilogue group 0) runs interleaved,
-    // chunk by chunk, with layer 1 of the next consumer of z' (dynamics of step t+1, or the terminal policy; epilogue
-    // group 1 -> TMEM h1).  The dynamics' layer-3 accumulator is parked in the h1 region so that its epilogue (z' -> [z,a])
-    // can wait until the reward's layer-1 MMAs have read the old [z,a].
+    // Overlapped schedule (TDMPC_TC_OVERLAP=1; measured slower).  The two MLPs of a step share one TMEM h1
+    // buffer, which forces dyn and reward to alternate and leaves the tensor pipe idle during every layer-1 epilogue.  Here
+    // the reward chain keeps ITS hidden activation in XS (free once the dynamics' layer 3 has read h2), so reward layer 2
+    // of step t (SS mode) runs interleaved with layer 1 of the next consumer of z' (dynamics of step t+1, or the terminal
+    // policy; its epilogue fills the TMEM h1 buffer).  The dynamics' layer-3 accumulator is parked in the h1 region so that
+    // its epilogue (z' -> [z,a]) can wait until the reward's layer-1 MMAs have read the old [z,a].
     chain12(J_L1, CH_DYN, 0, F_WAIT_ZA);
     for (int t = 0; t < H; ++t) {
       const bool last = t == H - 1;

@@ -33,7 +33,6 @@ enum TcJobFlags {
   // that its 512x512 layer can run while the NEXT step's layer-1 epilogue fills the TMEM h1 buffer.
   F_TO_XS = 256,     // J_L1: epilogue writes the XS chunk (bf16, swizzled) instead of the TMEM h1 chunk
   F_A_XS = 512,      // J_L2: A operand = XS in shared memory (SS) instead of h1 in TMEM
-  F_SOLO = 1024,     // J_L2 reward head: all four chunks are drained by one epilogue group (no cross-group exchange)
   F_PARK = 2048,     // J_L3: MMAs only; the accumulator is parked in the (idle) h1 region instead of a ping-pong buffer
   F_EPI = 4096,      // J_L3: epilogue only (group 0), on the parked accumulator once `d3_full` has completed
   F_BUF0 = 8192,     // this job uses accumulator buffer 0 (the ping-pong continues from there)
