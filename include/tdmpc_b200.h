@@ -224,12 +224,62 @@ TDMPC_API int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* args, void* str
 TDMPC_API int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,
                      void* out, void* stream);
 
+/* ---- prioritised replay sampling: ReplayBuffer.sample, algorithm/helper.py:506-534 ----
+ * Handle-less, stream-ordered, no allocation; errors go to tdmpc_last_error(NULL).
+ *
+ * tdmpc_replay_sample replaces helper.py:507-513:
+ *   probs = priorities[:total] ** per_alpha; probs /= probs.sum()                      (fp32)
+ *   idxs  = np.random.choice(total, batch, p=probs, replace=replace)                   (float64 cdf, searchsorted 'right';
+ *           replace=0: numpy's redraw rounds -- first occurrences kept in draw order, found entries zeroed, the rest redrawn)
+ *   weights = (total * probs[idxs]) ** (-per_beta); weights /= weights.max()
+ * without moving the priority vector to the host. */
+typedef struct {
+  const float* priorities;   /* device [total]: ReplayBuffer._priorities[:total]                                   */
+  int64_t total;             /* len(probs): capacity once the buffer is full, else ReplayBuffer.idx                */
+  int32_t batch;             /* cfg.batch_size, 1..4096                                                            */
+  int32_t replace;           /* np.random.choice(replace=...); the reference passes `not self._full`               */
+  float per_alpha;           /* cfg.per_alpha                                                                       */
+  float per_beta;            /* cfg.per_beta                                                                        */
+  const double* uniforms;    /* device, optional: U[0,1) float64 draws in the order numpy's random_sample yields
+                              * them (round r consumes batch - found_so_far values); NULL = built-in Philox stream  */
+  int64_t n_uniforms;        /* length of `uniforms`; round r is only run while batch*(r+1) values are available   */
+  uint64_t seed, call;       /* Philox key of the built-in stream                                                   */
+  int32_t max_rounds;        /* replace=0: upper bound on redraw rounds (0 = 8); see status                         */
+  int32_t _pad;
+  void* workspace;           /* device, >= tdmpc_replay_workspace_bytes(total, batch)                               */
+  int64_t workspace_bytes;
+  int64_t* idxs;             /* out device [batch] int64 (torch.long); -1 where max_rounds was not enough           */
+  float* weights;            /* out device [batch]                                                                   */
+  int32_t* status;           /* out device [2], optional: {indices found, rounds run}                               */
+} tdmpc_replay_sample_args;
+
+/* tdmpc_replay_gather replaces helper.py:515-528 (state modality): the horizon+1 step windows behind each index,
+ * the episode-final observation substituted on the last step (helper.py:526-527). */
+typedef struct {
+  const int64_t* idxs;       /* device [batch]                                                  */
+  int32_t batch, horizon;    /* ReplayBuffer.batch_size, ReplayBuffer.horizon                   */
+  int32_t obs_dim, action_dim;
+  int64_t episode_length;    /* cfg.episode_length                                              */
+  const float* obs_buf;      /* device ReplayBuffer._obs      [capacity + 1, obs_dim]           */
+  const float* last_obs_buf; /* device ReplayBuffer._last_obs [capacity / episode_length, obs_dim] */
+  const float* action_buf;   /* device ReplayBuffer._action   [capacity, action_dim]            */
+  const float* reward_buf;   /* device ReplayBuffer._reward   [capacity]                        */
+  float* obs;                /* out [batch, obs_dim]                                            */
+  float* next_obs;           /* out [horizon + 1, batch, obs_dim]                               */
+  float* action;             /* out [horizon + 1, batch, action_dim]                            */
+  float* reward;             /* out [horizon + 1, batch] (the reference returns reward.unsqueeze(2)) */
+} tdmpc_replay_gather_args;
+
+TDMPC_API int64_t tdmpc_replay_workspace_bytes(int64_t total, int32_t batch);
+TDMPC_API int tdmpc_replay_sample(const tdmpc_replay_sample_args* args, void* stream);
+TDMPC_API int tdmpc_replay_gather(const tdmpc_replay_gather_args* args, void* stream);
+
 /* Number of kernels of THIS library launched by the handle so far (bench.py's gpu_launches). */
 TDMPC_API uint64_t tdmpc_launch_count(const tdmpc_handle* h);
 
 /* Layout self-check for FFI bindings: writes up to n of {sizeof(tdmpc_model_cfg), sizeof(tdmpc_weights),
- * sizeof(tdmpc_plan_args), offsetof(plan_args, obs), offsetof(.., seed), offsetof(.., action), offsetof(.., tap_z0)}
- * and returns how many values exist. */
+ * sizeof(tdmpc_plan_args), offsetof(plan_args, obs), offsetof(.., seed), offsetof(.., action), offsetof(.., tap_z0),
+ * sizeof(tdmpc_replay_sample_args), sizeof(tdmpc_replay_gather_args)} and returns how many values exist. */
 TDMPC_API int32_t tdmpc_abi_sizes(int32_t* out, int32_t n);
 
 /* Build information: "sm_100a;tcgen05=1;..." */

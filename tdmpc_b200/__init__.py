@@ -2,3 +2,4 @@
 from .told import DSSM, DSSMRnn, TOLD, linear_schedule  # noqa: F401
 from .planner import Planner, TDMPC, TdICemSimDssm, TdICemSimMlp, accelerate, icem_sizes  # noqa: F401
 from .collector import BatchedEpisodes, PlanLoop  # noqa: F401,E402
+from .replay import ReplayBuffer  # noqa: F401,E402

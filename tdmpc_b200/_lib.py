@@ -19,6 +19,7 @@ EXPORTS = [
     "tdmpc_create", "tdmpc_destroy", "tdmpc_last_error", "tdmpc_reserve", "tdmpc_set_weights",
     "tdmpc_encode", "tdmpc_estimate_value", "tdmpc_estimate_value_drnn", "tdmpc_pi_rollout", "tdmpc_select_update", "tdmpc_plan",
     "tdmpc_fill_noise", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes",
+    "tdmpc_replay_workspace_bytes", "tdmpc_replay_sample", "tdmpc_replay_gather",
 ]
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -63,6 +64,23 @@ class PlanArgs(C.Structure):
     ]
 
 
+class ReplaySampleArgs(C.Structure):
+    _fields_ = [
+        ("priorities", _fp), ("total", C.c_int64), ("batch", C.c_int32), ("replace", C.c_int32),
+        ("per_alpha", C.c_float), ("per_beta", C.c_float), ("uniforms", _fp), ("n_uniforms", C.c_int64),
+        ("seed", C.c_uint64), ("call", C.c_uint64), ("max_rounds", C.c_int32), ("_pad", C.c_int32),
+        ("workspace", _fp), ("workspace_bytes", C.c_int64), ("idxs", _fp), ("weights", _fp), ("status", _fp),
+    ]
+
+
+class ReplayGatherArgs(C.Structure):
+    _fields_ = [
+        ("idxs", _fp), ("batch", C.c_int32), ("horizon", C.c_int32), ("obs_dim", C.c_int32), ("action_dim", C.c_int32),
+        ("episode_length", C.c_int64), ("obs_buf", _fp), ("last_obs_buf", _fp), ("action_buf", _fp), ("reward_buf", _fp),
+        ("obs", _fp), ("next_obs", _fp), ("action", _fp), ("reward", _fp),
+    ]
+
+
 def build(verbose=False):
     """Compile libtdmpc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     r = subprocess.run(["make", "-C", CSRC, "-j8", "all"], capture_output=True, text=True)
@@ -104,14 +122,17 @@ def load():
     lib.tdmpc_launch_count.argtypes = [H]; lib.tdmpc_launch_count.restype = C.c_uint64
     lib.tdmpc_build_info.argtypes = []; lib.tdmpc_build_info.restype = C.c_char_p
     lib.tdmpc_abi_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]; lib.tdmpc_abi_sizes.restype = C.c_int32
-    got = (C.c_int32 * 7)()
-    lib.tdmpc_abi_sizes(got, 7)
+    lib.tdmpc_replay_workspace_bytes.argtypes = [C.c_int64, C.c_int32]; lib.tdmpc_replay_workspace_bytes.restype = C.c_int64
+    lib.tdmpc_replay_sample.argtypes = [C.POINTER(ReplaySampleArgs), C.c_void_p]
+    lib.tdmpc_replay_gather.argtypes = [C.POINTER(ReplayGatherArgs), C.c_void_p]
+    got = (C.c_int32 * 9)()
+    lib.tdmpc_abi_sizes(got, 9)
     want = [C.sizeof(ModelCfg), C.sizeof(Weights), C.sizeof(PlanArgs), PlanArgs.obs.offset, PlanArgs.seed.offset,
-            PlanArgs.action.offset, PlanArgs.tap_z0.offset]
+            PlanArgs.action.offset, PlanArgs.tap_z0.offset, C.sizeof(ReplaySampleArgs), C.sizeof(ReplayGatherArgs)]
     if list(got) != want:
         raise RuntimeError(f"libtdmpc_b200.so ABI mismatch: library {list(got)} vs binding {want} (stale build?)")
     for name in EXPORTS:
-        if name not in ("tdmpc_last_error", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes"):
+        if name not in ("tdmpc_last_error", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes", "tdmpc_replay_workspace_bytes"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

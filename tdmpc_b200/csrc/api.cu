@@ -34,6 +34,7 @@ struct tdmpc_handle {
 };
 
 static std::string g_create_err;
+void tdmpc_set_global_error(const char* msg) { g_create_err = msg ? msg : ""; }   // handle-less entry points (replay.cu)
 
 #define FAIL(h, code, ...)                                   \
   do {                                                       \
@@ -151,13 +152,14 @@ extern "C" __attribute__((visibility("default"))) int tdmpc_debug_jobs(tdmpc_han
 extern "C" int32_t tdmpc_abi_sizes(int32_t* out, int32_t n) {
   const int32_t v[] = {(int32_t)sizeof(tdmpc_model_cfg), (int32_t)sizeof(tdmpc_weights), (int32_t)sizeof(tdmpc_plan_args),
                        (int32_t)offsetof(tdmpc_plan_args, obs), (int32_t)offsetof(tdmpc_plan_args, seed),
-                       (int32_t)offsetof(tdmpc_plan_args, action), (int32_t)offsetof(tdmpc_plan_args, tap_z0)};
+                       (int32_t)offsetof(tdmpc_plan_args, action), (int32_t)offsetof(tdmpc_plan_args, tap_z0),
+                       (int32_t)sizeof(tdmpc_replay_sample_args), (int32_t)sizeof(tdmpc_replay_gather_args)};
   const int32_t m = (int32_t)(sizeof(v) / sizeof(v[0]));
   for (int32_t i = 0; i < n && i < m; ++i) out[i] = v[i];
   return m;
 }
 extern "C" uint64_t tdmpc_launch_count(const tdmpc_handle* h) { return h ? h->launches : 0; }
-extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;dynamics=mlp,gru;select=bitonic"; }
+extern "C" const char* tdmpc_build_info(void) { return "tdmpc_b200;arch=sm_100a;rollout=tcgen05+tmem+bulk-tma|fp32-cuda-core;dynamics=mlp,gru;select=bitonic;replay=per-sampler"; }
 
 extern "C" int tdmpc_reserve(tdmpc_handle* h, int32_t batch, int32_t max_rows, int32_t max_horizon, int32_t max_elites) {
   if (!h) return TDMPC_ERR_INVALID;

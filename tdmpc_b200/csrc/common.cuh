@@ -37,7 +37,7 @@ struct ModelFp32 {
 // ------------------------------------------------------------------------------------------
 // Noise source: injected buffer (parity tests) or Philox4x32-10 keyed by (seed, call, stream).
 // Both are addressed by the same flat element index, see include/tdmpc_b200.h for the layouts.
-enum NoiseStream { NS_PI = 0, NS_CEM = 1, NS_TERM = 2, NS_OUT = 3, NS_PICK = 4, NS_SHIFT = 5 };
+enum NoiseStream { NS_PI = 0, NS_CEM = 1, NS_TERM = 2, NS_OUT = 3, NS_PICK = 4, NS_SHIFT = 5, NS_REPLAY = 6 };
 
 struct NoiseSrc {
   const float* inj;      // nullptr -> Philox

@@ -303,7 +303,53 @@ def run_drnn_case(name, cfg_name, steps=3, seed=0):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def run_replay_case(name, cfg_name, seed=0, draws=3):
+    """ReplayBuffer.sample of the reference (helper.py:506-534) on CPU: the buffer is filled through the reference's own
+    add / update_priorities with tests/synth.py data, np.random is seeded so that the uniforms it consumes are
+    synth.make_uniforms(seed).  Stored: the reference's outputs and its priority vector."""
+    from oracle import replay_oracle as RO
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self          # helper.py:530-532 moves the batch with .cuda()
+    cfg = synth.make_replay_cfg(cfg_name)
+    buf = ref_h.ReplayBuffer(cfg, latent_plan=True)
+    st = RO.ReplayState(cfg, latent_plan=True)
+    for obs, act, rew in synth.make_replay_episodes(cfg, seed):
+        ep = ref_h.Episode(cfg, obs[0])
+        for t in range(cfg.episode_length):
+            ep += (obs[t + 1], torch.from_numpy(act[t]), float(rew[t]), t == cfg.episode_length - 1)
+        buf += ep
+        st.add(torch.from_numpy(obs), torch.from_numpy(act), torch.from_numpy(rew))
+    n_valid = buf.capacity if buf._full else buf.idx
+    for idxs, pr in synth.make_priority_updates(cfg, n_valid, seed):
+        buf.update_priorities(torch.from_numpy(idxs), torch.from_numpy(pr))
+        st.update_priorities(torch.from_numpy(idxs), torch.from_numpy(pr))
+    assert torch.equal(buf._priorities, st["priorities"]) and torch.equal(buf._obs[:n_valid], st["obs"][:n_valid]) and buf.idx == st["idx"]
+    buf._obs[n_valid:] = 0          # torch.empty rows the reference never wrote (idx + t + 1 can touch row n_valid)
+    out = {"priorities": buf._priorities.numpy().copy(), "idx_full": np.array([buf.idx, int(buf._full)], dtype=np.int64)}
+    np.random.seed(seed)
+    uni = synth.make_uniforms(cfg.batch_size * 16 * draws, seed)
+    used = 0
+    for d in range(draws):
+        ref = buf.sample()
+        orc = RO.sample(st, uni[used:])
+        used += orc[6]
+        for k, (r, o) in enumerate(zip(ref, orc[:6])):
+            assert torch.equal(r, o) if k == 4 else torch.allclose(r, o, rtol=1e-6, atol=0), (name, d, k)
+        for key, v in zip(("obs", "next_obs", "action", "reward", "idxs", "weights"), ref):
+            out[f"d{d}_{key}"] = v.numpy().copy()
+        out[f"d{d}_used"] = np.array([orc[6]], dtype=np.int64)
+        print(f"[{name}] draw {d}: full={buf._full} uniforms used {orc[6]} (batch {cfg.batch_size}), "
+              f"distinct idx {len(set(ref[4].tolist()))}, oracle == reference")
+    assert abs(np.random.random_sample() - uni[used]) == 0.0        # the reference consumed exactly the same stream
+    out["meta"] = np.array([seed, draws], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "replay":
+        run_replay_case("replay_small", "small", seed=0)
+        run_replay_case("replay_full", "full", seed=1)
+        sys.exit(0)
     check_choice_replica()
     run_case("tdmpc_tiny", "tiny", steps=3)
     run_case("tdmpc_tiny_train", "tiny", steps=2, eval_mode=False, seed=3, std_floor=0.1)
@@ -314,4 +360,6 @@ if __name__ == "__main__":
     run_icem_case("icem_cfg4", "cfg4", steps=2, seed=5)
     run_drnn_case("drnn_tiny", "tiny_drnn", steps=3, seed=6)
     run_drnn_case("drnn_cfg5", "cfg5", steps=2, seed=7)
+    run_replay_case("replay_small", "small", seed=0)
+    run_replay_case("replay_full", "full", seed=1)
     print("golden fixtures written to", HERE)

@@ -192,3 +192,48 @@ def icem_noise_abi(n, sizes, H, A):
     if "shift" in n:
         out["shift"] = n["shift"].unsqueeze(0).contiguous()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Prioritised replay: deterministic buffer contents for the sampler tests.
+def make_replay_cfg(name="small", **over):
+    """cfg fields ReplayBuffer reads (helper.py:441-464,506-513)."""
+    base = dict(modality="state", device="cpu", per_alpha=0.6, per_beta=0.4, horizon=5, env_horizon=5, frame_stack=1)
+    base.update({
+        # not yet full -> np.random.choice(replace=True)
+        "small": dict(obs_shape=(6,), action_dim=2, episode_length=100, train_steps=4000, max_buffer_size=1000000,
+                      batch_size=128, n_episodes=13),
+        # wrapped around -> full -> replace=False, skewed priorities so that redraw rounds happen
+        "full": dict(obs_shape=(6,), action_dim=2, episode_length=50, train_steps=1000000, max_buffer_size=1500,
+                     batch_size=256, n_episodes=34),
+    }[name])
+    base.update(over)
+    return SimpleNamespace(**base)
+
+
+def make_replay_episodes(cfg, seed=0):
+    """[(obs [ep+1, D], action [ep, A], reward [ep])] * cfg.n_episodes, float32."""
+    rs = np.random.RandomState(1000 + seed)
+    ep, D, A = cfg.episode_length, cfg.obs_shape[0], cfg.action_dim
+    return [(rs.randn(ep + 1, D).astype(np.float32), rs.uniform(-1, 1, (ep, A)).astype(np.float32),
+             rs.randn(ep).astype(np.float32)) for _ in range(cfg.n_episodes)]
+
+
+def make_priority_updates(cfg, n_valid, seed=0, rounds=6, skew=3.0):
+    """[(idxs int64 [B], priorities float32 [B, 1])]: what TDMPC.update feeds update_priorities (tdmpc.py:231);
+    log-normal so a few transitions dominate.  Zero-priority (episode-tail) slots are left alone, as in training
+    (they are never sampled, so never updated)."""
+    rs = np.random.RandomState(2000 + seed)
+    ep, H = cfg.episode_length, cfg.horizon
+    out = []
+    for _ in range(rounds):
+        idxs = rs.randint(0, n_valid, size=cfg.batch_size)
+        idxs = np.unique(idxs[(idxs % ep) < ep - H])      # distinct: a scatter with repeated indices has no defined winner on a GPU
+        pr = np.exp(skew * rs.randn(len(idxs), 1)).astype(np.float32).clip(max=1e4)
+        out.append((idxs.astype(np.int64), pr))
+    return out
+
+
+def make_uniforms(n, seed=0):
+    """The float64 stream np.random.seed(seed); np.random.random_sample(n) would give."""
+    return np.random.RandomState(seed).random_sample(n)
