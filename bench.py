@@ -15,6 +15,7 @@ environments, no data-path collective, one all-gather of the planned actions per
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -134,6 +135,73 @@ def drnn_batched(dev, precision, B):
     flop = sum(T * (H * (f_gru + f_prior + f_rew) + f_pi + 2 * f_q) for T in rows) + sizes[0][2] * H * (f_pi + f_gru + f_prior)
     return {"workload": f"iCEM + GRU dynamics, {B} environments per launch, rows per iteration {rows}, precision {precision}",
             "ms_per_batched_plan": ms, "plans_per_sec": B / ms * 1e3, "flop_per_plan": flop, "tflops": B / ms * 1e3 * flop / 1e12}
+
+
+def replay_extra(dev, hbm_peak):
+    """ReplayBuffer.sample at the reference's full size (max_buffer_size 1e6 priorities, batch 512,
+    horizon 5, quadrotor dims).  Device time by CUDA events around tdmpc_replay_sample (+ gather), against the reference's
+    way of doing it restated on the host (oracle port: fp32 pow / sum, float64 cumsum + searchsorted, gathers)."""
+    from oracle import replay_oracle as RO
+    from tdmpc_b200 import ReplayBuffer
+    cfg = synth.make_replay_cfg("small", train_steps=1000000, episode_length=1000, batch_size=512, obs_shape=(18,), action_dim=4)
+    buf = ReplayBuffer(cfg, latent_plan=True)
+    rs = np.random.RandomState(7)
+    pri = np.exp(1.5 * rs.randn(buf.capacity)).astype(np.float32)
+    pri[(np.arange(buf.capacity) % 1000) >= 995] = 0
+    buf._priorities.copy_(torch.from_numpy(pri))
+    buf._obs.normal_(); buf._action.uniform_(-1, 1); buf._reward.normal_()
+    out = {"workload": "ReplayBuffer.sample: 1e6 priorities, batch 512, horizon 5, obs 18, act 4, per_alpha 0.6, per_beta 0.4"}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for full in (False, True):
+        buf.idx, buf._full = (0, True) if full else (buf.capacity - 1000, False)
+        total = buf.capacity if full else buf.idx
+        for _ in range(3):
+            buf.sample()
+        ms_w = []
+        for _ in range(10):
+            flush.zero_(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            buf.sample()
+            torch.cuda.synchronize()
+            ms_w.append((time.perf_counter() - t0) * 1e3)
+        # device time of the draw alone: 40 calls back to back over 40 different priority vectors (160 MB > L2, so every call
+        # reads HBM), one event pair around the lot; the host enqueues ahead of the GPU, no status read in between
+        many = torch.from_numpy(pri).to(dev).repeat(40, 1)
+        idxs = torch.empty(512, dtype=torch.int64, device=dev); wts = torch.empty(512, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        calls = [buf._sample_args(idxs, wts, priorities=many[i]) for i in range(40)]
+        ms_k = []
+        for _ in range(5):
+            flush.zero_(); torch.cuda.synchronize()
+            e0.record()
+            for a in calls:
+                assert buf._lib.tdmpc_replay_sample(ctypes.byref(a), stream) == 0
+            e1.record(); torch.cuda.synchronize()
+            ms_k.append(e0.elapsed_time(e1) / 40)
+        assert buf._status.tolist()[0] in (512,) or full
+        del many
+        rounds = buf.last_rounds
+        alg = rounds * (2 * 4 * total if not full else (4 + 1) * total) + 4 * total      # pass 1 once, then per round: block sums (+ mask)
+        k = float(np.median(ms_k))
+        key = "replace_false_full_buffer" if full else "replace_true"
+        out[key] = {"ms_sample_indices_device": k, "ms_sample_wall_incl_gather_and_status_read": float(np.median(ms_w)),
+                    "rounds": rounds, "launches": 1 + 2 * (-(-rounds // ReplayBuffer.ROUNDS_PER_CALL) * ReplayBuffer.ROUNDS_PER_CALL if full else 1) + 1,
+                    "algorithmic_bytes": alg, "achieved_gb_s": alg / (k * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": alg / (k * 1e-3) / 1e9 / hbm_peak, "hbm_peak_gb_s": hbm_peak}
+    st = RO.ReplayState(cfg, latent_plan=True)
+    st["priorities"] = torch.from_numpy(pri); st["idx"] = st["capacity"] - 1000
+    st["obs"].normal_()
+    t_cpu = []
+    for i in range(5):
+        uni = np.random.RandomState(i).random_sample(512)
+        t0 = time.perf_counter()
+        RO.sample(st, uni)
+        t_cpu.append((time.perf_counter() - t0) * 1e3)
+    out["cpu_port_ms"] = float(np.median(t_cpu))
+    out["cpu_port_note"] = (f"oracle/replay_oracle.sample on {torch.get_num_threads()} host threads, buffers already in host memory "
+                            "(the reference additionally copies the 4 MB priority vector device -> host per call, helper.py:511)")
+    return out
 
 
 def measured_peaks():
@@ -395,6 +463,8 @@ def main():
                                                  f"mixture 0.5, I=6, precision {prec}", "ms_per_plan_wall": ms1, "plans_per_sec": 1e3 / ms1}
             # BASELINE.json configs[4]: batched iCEM planning through the GRU latent dynamics (256 environments per launch here)
             extra["cfg5_b256"] = drnn_batched(dev, args.precision, 256)
+            if world == 1:
+                extra["replay_sample_1m"] = replay_extra(dev, measured_peaks()[2])
             # the batched environment-stepping loop (tdmpc_b200.PlanLoop): numpy observations in, numpy
             # actions out, one pinned H2D + one CUDA-graph replay of the whole plan + one D2H per step (wall clock, host included)
             from tdmpc_b200 import PlanLoop

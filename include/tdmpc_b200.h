@@ -242,15 +242,18 @@ typedef struct {
   float per_beta;            /* cfg.per_beta                                                                        */
   const double* uniforms;    /* device, optional: U[0,1) float64 draws in the order numpy's random_sample yields
                               * them (round r consumes batch - found_so_far values); NULL = built-in Philox stream  */
-  int64_t n_uniforms;        /* length of `uniforms`; round r is only run while batch*(r+1) values are available   */
+  int64_t n_uniforms;        /* length of `uniforms`; round r (counted over resumed calls) is only run while
+                              * batch*(r+1) values are available                                                    */
   uint64_t seed, call;       /* Philox key of the built-in stream                                                   */
-  int32_t max_rounds;        /* replace=0: upper bound on redraw rounds (0 = 8); see status                         */
-  int32_t _pad;
+  int32_t max_rounds;        /* replace=0: redraw rounds to enqueue in THIS call (0 = 8); see status                */
+  int32_t resume;            /* 0: fresh draw.  r > 0: continue the draw left in `workspace` by earlier calls that ran
+                              * r rounds in total (same arguments) -- lets a caller enqueue 2 rounds, read `status`,
+                              * and only pay for more when numpy's loop would really have gone on                   */
   void* workspace;           /* device, >= tdmpc_replay_workspace_bytes(total, batch)                               */
   int64_t workspace_bytes;
   int64_t* idxs;             /* out device [batch] int64 (torch.long); -1 where max_rounds was not enough           */
   float* weights;            /* out device [batch]                                                                   */
-  int32_t* status;           /* out device [2], optional: {indices found, rounds run}                               */
+  int32_t* status;           /* out device [2], optional: {indices found, rounds run so far}                        */
 } tdmpc_replay_sample_args;
 
 /* tdmpc_replay_gather replaces helper.py:515-528 (state modality): the horizon+1 step windows behind each index,

@@ -68,7 +68,7 @@ class ReplaySampleArgs(C.Structure):
     _fields_ = [
         ("priorities", _fp), ("total", C.c_int64), ("batch", C.c_int32), ("replace", C.c_int32),
         ("per_alpha", C.c_float), ("per_beta", C.c_float), ("uniforms", _fp), ("n_uniforms", C.c_int64),
-        ("seed", C.c_uint64), ("call", C.c_uint64), ("max_rounds", C.c_int32), ("_pad", C.c_int32),
+        ("seed", C.c_uint64), ("call", C.c_uint64), ("max_rounds", C.c_int32), ("resume", C.c_int32),
         ("workspace", _fp), ("workspace_bytes", C.c_int64), ("idxs", _fp), ("weights", _fp), ("status", _fp),
     ]
 

@@ -14,7 +14,8 @@
 // the block prefix and then re-walks ONE block with a warp scan.  Algorithmic bytes per sample call:
 // 2 x 4 x total (two passes over the priorities) + batch x RB_BLK x 4 for the walks (L2 hits).
 // HBM-bound, latency-scale: at total = 1 M that is 8 MB, about 1.3 us at the measured copy peak, so
-// the cost is the launches (7 for replace=True).
+// the cost is the launches: 3 kernels + 1 memset for replace=True (every stage's serial tail runs in the last block
+// to finish, instead of in a single-CTA kernel of its own), 2 more kernels per redraw round.
 #include "common.cuh"
 
 #include <cstdio>
@@ -29,23 +30,23 @@ constexpr int RB_THREADS = 256;
 constexpr int RB_MAX_PARTS = 1024;  // partial sums of pass 1
 constexpr int RB_MAX_BATCH = 4096;  // candidates of one round are de-duplicated in shared memory
 
-// control words at the head of the workspace
+// control words at the head of the workspace (zeroed by a memset at the start of every fresh draw)
 struct ReplayCtl {
   long long n_found;     // distinct indices committed so far (numpy: n_uniq)
   long long cursor;      // uniforms consumed so far
   long long rounds;      // draw rounds executed
   double cdf_total;      // cumsum(p)[-1] of the current round
   float prob_sum;        // probs.sum() in fp32 (the divisor of helper.py:508)
-  float _pad;
+  unsigned int done[3];  // "last block finishes the job" tickets of the three kernels
 };
 
 struct ReplayWs {
   ReplayCtl* ctl;
+  unsigned char* taken;      // [total] 1 = already drawn (replace = False); directly behind ctl: one memset clears both
   double* part;              // [RB_MAX_PARTS]
   double* bsum;              // [nb] block sums of the normalised probabilities
   double* bpre;              // [nb] exclusive prefix of bsum
   long long* cand;           // [batch] candidates of the current round
-  unsigned char* taken;      // [total] 1 = already drawn (replace = False)
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -56,12 +57,12 @@ size_t ws_layout(int64_t total, int32_t batch, void* base, ReplayWs* ws) {
   char* b = static_cast<char*>(base);
   auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : nullptr; };
   void* ctl = take(sizeof(ReplayCtl));
+  void* taken = take((size_t)total);
   void* part = take(sizeof(double) * RB_MAX_PARTS);
   void* bsum = take(sizeof(double) * nb);
   void* bpre = take(sizeof(double) * nb);
   void* cand = take(sizeof(long long) * (size_t)batch);
-  void* taken = take((size_t)total);
-  if (ws) *ws = ReplayWs{(ReplayCtl*)ctl, (double*)part, (double*)bsum, (double*)bpre, (long long*)cand, (unsigned char*)taken};
+  if (ws) *ws = ReplayWs{(ReplayCtl*)ctl, (unsigned char*)taken, (double*)part, (double*)bsum, (double*)bpre, (long long*)cand};
   return off;
 }
 
@@ -82,64 +83,58 @@ __device__ double block_sum(double v, double* sh /* [32] */) {
   return warp_sum(t);
 }
 
+// Every kernel below ends with "the last block to finish does the serial tail" (a ticket in ReplayCtl::done), which
+// saves the launch of a single-CTA kernel per stage: the whole draw is 3 launches instead of 7.
+__device__ bool last_block_done(unsigned int* ticket) {
+  __shared__ bool last;
+  __threadfence();                       // this block's global writes before the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *ticket = 0;               // ready for the next round
+  }
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
+}
+
 // priorities ** alpha in fp32 (torch: elementwise pow on a float32 tensor)
 __device__ __forceinline__ float pow_alpha(float p, float alpha) { return powf(p, alpha); }
 
-// pass 1: partial float64 sums of priorities ** alpha (grid-stride), then the last step folds them to fp32
-__global__ void replay_pow_partials(const float* __restrict__ pri, long long total, float alpha, double* __restrict__ part) {
+// launch 1: partial float64 sums of priorities ** alpha (grid-stride); the last block folds them into probs.sum()
+__global__ void replay_pow_sum(const float* __restrict__ pri, long long total, float alpha, double* part, ReplayCtl* ctl) {
   __shared__ double sh[32];
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     acc += (double)pow_alpha(__ldg(pri + i), alpha);
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
-}
-
-__global__ void replay_begin(const double* __restrict__ part, int nparts, ReplayCtl* ctl) {
-  __shared__ double sh[32];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += part[i];
+  if (!last_block_done(&ctl->done[0])) return;
+  acc = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(part + i);
   acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) {
-    ctl->n_found = 0; ctl->cursor = 0; ctl->rounds = 0; ctl->cdf_total = 0.0;
-    ctl->prob_sum = (float)acc;      // the sum is carried in float64 and rounded once (torch's own fp32 reduction order is unspecified)
-  }
+  // the sum is carried in float64 and rounded once (torch's own fp32 reduction order is unspecified)
+  if (threadIdx.x == 0) ctl->prob_sum = (float)acc;
 }
 
 // the float64 value numpy sees for element i: float32(p_i^alpha / sum), 0 once it has been drawn without replacement
-__device__ __forceinline__ double prob_at(const float* __restrict__ pri, const unsigned char* __restrict__ taken, long long i,
+__device__ __forceinline__ double prob_at(const float* __restrict__ pri, const unsigned char* taken, long long i,
                                           float alpha, float psum) {
   if (taken && taken[i]) return 0.0;
   return (double)(pow_alpha(__ldg(pri + i), alpha) / psum);
 }
 
-// pass 2: block sums of the (masked) normalised probabilities
-__global__ void replay_block_sums(const float* __restrict__ pri, const unsigned char* __restrict__ taken, long long total,
-                                  float alpha, int batch, const ReplayCtl* __restrict__ ctl, double* __restrict__ bsum) {
-  __shared__ double sh[32];
-  if (ctl->n_found >= batch) return;
-  const float psum = ctl->prob_sum;
-  const long long base = (long long)blockIdx.x * RB_BLK;
-  double acc = 0.0;
-  for (int k = threadIdx.x; k < RB_BLK; k += blockDim.x) {
-    const long long i = base + k;
-    if (i < total) acc += prob_at(pri, taken, i, alpha, psum);
-  }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) bsum[blockIdx.x] = acc;
-}
-
-// single CTA: exclusive scan of the block sums
-__global__ void replay_scan_blocks(const double* __restrict__ bsum, double* __restrict__ bpre, long long nb, int batch, ReplayCtl* ctl) {
+// exclusive scan of the block sums by one CTA
+__device__ void scan_block_sums(const double* bsum, double* bpre, long long nb, ReplayCtl* ctl) {
   __shared__ double wsum[32];
   __shared__ double carry_s;
-  if (ctl->n_found >= batch) return;
   if (threadIdx.x == 0) carry_s = 0.0;
   __syncthreads();
   const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (long long t0 = 0; t0 < nb; t0 += blockDim.x) {
     const long long i = t0 + threadIdx.x;
-    const double v = i < nb ? bsum[i] : 0.0;
+    const double v = i < nb ? __ldcg(bsum + i) : 0.0;
     double s = v;                                              // inclusive warp scan
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, s, o); if (l >= o) s += u; }
@@ -156,67 +151,48 @@ __global__ void replay_scan_blocks(const double* __restrict__ bsum, double* __re
   if (threadIdx.x == 0) ctl->cdf_total = carry_s;
 }
 
-// one warp per draw: first index with cdf[i] / cdf[-1] > u  (searchsorted side='right')
-__global__ void replay_search(const float* __restrict__ pri, const unsigned char* __restrict__ taken, long long total, float alpha,
-                              int batch, const double* __restrict__ uniforms, NoiseSrc rng, const ReplayCtl* __restrict__ ctl,
-                              const double* __restrict__ bsum, const double* __restrict__ bpre, long long nb,
-                              long long* __restrict__ cand) {
-  const long long found = ctl->n_found;
-  const int m = (int)(batch - found);
-  const int j = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= m) return;
-  const long long e = ctl->cursor + j;
-  const double u = uniforms ? uniforms[e] : philox_uniform64(rng, (uint64_t)e);
-  const double C = ctl->cdf_total;
+// launch 2 (per round): block sums of the (masked) normalised probabilities; the last block scans them
+__global__ void replay_block_sums(const float* __restrict__ pri, const unsigned char* taken, long long total,
+                                  float alpha, int batch, ReplayCtl* ctl, double* bsum, double* bpre) {
+  __shared__ double sh[32];
+  if (ctl->n_found >= batch) return;
   const float psum = ctl->prob_sum;
-  // smallest block whose inclusive prefix / C exceeds u
-  long long lo = 0, hi = nb - 1;
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if ((bpre[mid] + bsum[mid]) / C > u) hi = mid; else lo = mid + 1;
+  const long long base = (long long)blockIdx.x * RB_BLK;
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < RB_BLK; k += blockDim.x) {
+    const long long i = base + k;
+    if (i < total) acc += prob_at(pri, taken, i, alpha, psum);
   }
-  long long pick = -1, last_pos = -1;
-  for (long long b = lo; b < nb && pick < 0; ++b) {       // walks on past b = lo only if the re-summed block rounds differently
-    double run = bpre[b];
-    for (int c = 0; c < RB_BLK / 32 && pick < 0; ++c) {
-      const long long i = b * RB_BLK + c * 32 + lane;
-      const double q = i < total ? prob_at(pri, taken, i, alpha, psum) : 0.0;
-      double s = q;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-      const unsigned hit = __ballot_sync(0xffffffffu, q > 0.0 && (run + s) / C > u);
-      const unsigned pos = __ballot_sync(0xffffffffu, q > 0.0);
-      if (hit) pick = b * RB_BLK + c * 32 + (__ffs(hit) - 1);
-      if (pos) last_pos = b * RB_BLK + c * 32 + (31 - __clz(pos));
-      run += __shfl_sync(0xffffffffu, s, 31);
-    }
-  }
-  if (pick < 0) pick = last_pos >= 0 ? last_pos : total - 1;     // u beyond the re-summed total: the last drawable element
-  if (lane == 0) cand[j] = pick;
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = acc;
+  if (!last_block_done(&ctl->done[1])) return;
+  scan_block_sums(bsum, bpre, (long long)gridDim.x, ctl);
 }
 
-// single CTA: numpy's "keep the first occurrence, in draw order" + bookkeeping of the round
-__global__ void replay_commit(const long long* __restrict__ cand, int batch, int replace, ReplayCtl* ctl, unsigned char* taken,
-                              long long* __restrict__ idxs) {
-  __shared__ long long sc[RB_MAX_BATCH];
+// numpy's "keep the first occurrence, in draw order" + bookkeeping of the round (one CTA)
+__device__ void commit_round(const long long* cand, int batch, int replace, ReplayCtl* ctl, unsigned char* taken, long long* idxs,
+                             long long* sc /* shared [RB_MAX_BATCH] */) {
   __shared__ int wsum[32];
   __shared__ int carry_s;
   const long long found = ctl->n_found;
   const int m = (int)(batch - found);
-  if (m <= 0) return;
-  for (int j = threadIdx.x; j < m; j += blockDim.x) sc[j] = cand[j];
+  for (int j = threadIdx.x; j < m; j += blockDim.x) sc[j] = __ldcg(cand + j);
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int t0 = 0; t0 < m; t0 += blockDim.x) {
     const int j = t0 + threadIdx.x;
     int keep = 0;
-    if (j < m) {
+    if (j < m && sc[j] >= 0) {
       keep = 1;
       if (!replace) {
-        const long long v = sc[j];
-        for (int k = 0; k < j; ++k) if (sc[k] == v) { keep = 0; break; }
+        const long long v = sc[j];                           // branch-free sweep, two candidates per 16-byte shared load
+        const longlong2* sc2 = reinterpret_cast<const longlong2*>(sc);
+        int dup = 0;
+#pragma unroll 4
+        for (int k = 0; k < (j >> 1); ++k) { const longlong2 c = sc2[k]; dup |= (c.x == v) | (c.y == v); }
+        if ((j & 1) && sc[j - 1] == v) dup = 1;
+        keep = !dup;
       }
     }
     int s = keep;
@@ -236,12 +212,12 @@ __global__ void replay_commit(const long long* __restrict__ cand, int batch, int
     __syncthreads();
   }
   if (threadIdx.x == 0) { ctl->n_found = found + carry_s; ctl->cursor += m; ctl->rounds += 1; }
+  __syncthreads();
 }
 
-// single CTA: importance weights (helper.py:512-513) and the status words
-__global__ void replay_weights(const float* __restrict__ pri, long long total, float alpha, float beta, int batch,
-                               const ReplayCtl* __restrict__ ctl, long long* __restrict__ idxs, float* __restrict__ weights,
-                               int* __restrict__ status) {
+// importance weights (helper.py:512-513) and the status words (one CTA)
+__device__ void finish_weights(const float* __restrict__ pri, long long total, float alpha, float beta, int batch,
+                               const ReplayCtl* ctl, long long* idxs, float* weights, int* status) {
   __shared__ float sh[32];
   const int found = (int)ctl->n_found;
   const float psum = ctl->prob_sum;
@@ -264,8 +240,76 @@ __global__ void replay_weights(const float* __restrict__ pri, long long total, f
   mx = (threadIdx.x & 31) < (blockDim.x >> 5) ? sh[threadIdx.x & 31] : 0.0f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  for (int j = threadIdx.x; j < batch; j += blockDim.x) weights[j] = weights[j] / mx;
+  for (int j = threadIdx.x; j < batch; j += blockDim.x) weights[j] = weights[j] / mx;   // each thread re-reads its own writes
   if (threadIdx.x == 0 && status) { status[0] = found; status[1] = (int)ctl->rounds; }
+}
+
+// launch 3 (per round), one warp per draw: first index with cdf[i] / cdf[-1] > u  (searchsorted side='right');
+// the last block commits the round and, when the draw is complete or this was the last round enqueued, writes the weights
+__global__ void replay_search(const float* __restrict__ pri, unsigned char* taken, long long total, float alpha, float beta,
+                              int batch, int replace, int final_round, const double* __restrict__ uniforms, NoiseSrc rng,
+                              ReplayCtl* ctl, const double* __restrict__ bsum, const double* __restrict__ bpre, long long nb,
+                              long long* cand, long long* idxs, float* weights, int* status) {
+  __shared__ __align__(16) long long sc[RB_MAX_BATCH];
+  const long long found = ctl->n_found;
+  if (found >= batch) return;
+  const int m = (int)(batch - found);
+  const int j = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j < m) {
+    const long long e = ctl->cursor + j;
+    const double u = uniforms ? uniforms[e] : philox_uniform64(rng, (uint64_t)e);
+    const double C = ctl->cdf_total;
+    const float psum = ctl->prob_sum;
+    long long pick = -1;
+    if (C > 0.0) {           // else nothing drawable is left (numpy: "Fewer non-zero entries in p than size")
+      // smallest block whose inclusive prefix / C exceeds u
+      long long lo = 0, hi = nb - 1;
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((bpre[mid] + bsum[mid]) / C > u) hi = mid; else lo = mid + 1;
+      }
+      // two levels inside a block: every lane sums RB_BLK/32 = 32 consecutive elements, one warp scan finds the lane whose
+      // run crosses u, a second warp scan over that lane's 32 elements finds the element
+      long long last_chunk = -1;
+      for (long long b = lo; b < nb && pick < 0; ++b) {     // walks on past b = lo only if the re-summed block rounds differently
+        const long long base = b * RB_BLK;
+        double tot = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+          const long long i = base + lane * 32 + k;
+          if (i < total) tot += prob_at(pri, taken, i, alpha, psum);
+        }
+        double s = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        const double run = bpre[b];
+        const unsigned hit = __ballot_sync(0xffffffffu, tot > 0.0 && (run + s) / C > u);
+        const unsigned pos = __ballot_sync(0xffffffffu, tot > 0.0);
+        if (pos) last_chunk = base + (31 - __clz(pos)) * 32;
+        if (!hit) continue;
+        const int L = __ffs(hit) - 1;
+        const double excl = run + __shfl_sync(0xffffffffu, s - tot, L);
+        const long long i = base + L * 32 + lane;
+        const double q = i < total ? prob_at(pri, taken, i, alpha, psum) : 0.0;
+        double s2 = q;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += t; }
+        const unsigned hit2 = __ballot_sync(0xffffffffu, q > 0.0 && (excl + s2) / C > u);
+        const unsigned pos2 = __ballot_sync(0xffffffffu, q > 0.0);
+        pick = base + L * 32 + (hit2 ? __ffs(hit2) - 1 : 31 - __clz(pos2));   // no hit: the chunk re-summed one ulp lower -> its last drawable element
+      }
+      if (pick < 0 && last_chunk >= 0) {                     // u beyond the re-summed total: the last drawable element of the buffer
+        const long long i = last_chunk + lane;
+        const unsigned pos2 = __ballot_sync(0xffffffffu, i < total && prob_at(pri, taken, i, alpha, psum) > 0.0);
+        if (pos2) pick = last_chunk + (31 - __clz(pos2));
+      }
+    }
+    if (lane == 0) cand[j] = pick;
+  }
+  if (!last_block_done(&ctl->done[2])) return;
+  commit_round(cand, batch, replace, ctl, taken, idxs, sc);
+  if (final_round || ctl->n_found >= batch) finish_weights(pri, total, alpha, beta, batch, ctl, idxs, weights, status);
 }
 
 // grid (batch, horizon + 2): slice 0 is `obs`, slice s >= 1 is step t = s - 1 of next_obs / action / reward
@@ -316,21 +360,26 @@ extern "C" int tdmpc_replay_sample(const tdmpc_replay_sample_args* a, void* stre
   int nparts = (int)((total + RB_THREADS * 8 - 1) / (RB_THREADS * 8));
   nparts = nparts < 1 ? 1 : (nparts > RB_MAX_PARTS ? RB_MAX_PARTS : nparts);
   unsigned char* taken = a->replace ? nullptr : ws.taken;
-  if (taken && cudaMemsetAsync(taken, 0, (size_t)total, st) != cudaSuccess) return fail(TDMPC_ERR_CUDA, "replay_sample: memset failed");
   NoiseSrc rng{nullptr, a->seed, a->call, NS_REPLAY, nullptr};
-  replay_pow_partials<<<nparts, RB_THREADS, 0, st>>>(a->priorities, total, a->per_alpha, ws.part);
-  replay_begin<<<1, RB_THREADS, 0, st>>>(ws.part, nparts, ws.ctl);
+  if (!a->resume) {
+    // one memset clears the control words and (without replacement) the drawn-already mask that sits right behind them
+    const size_t clear = taken ? (size_t)((char*)ws.taken - (char*)ws.ctl) + (size_t)total : sizeof(ReplayCtl);
+    if (cudaMemsetAsync(ws.ctl, 0, clear, st) != cudaSuccess) return fail(TDMPC_ERR_CUDA, "replay_sample: memset failed");
+    replay_pow_sum<<<nparts, RB_THREADS, 0, st>>>(a->priorities, total, a->per_alpha, ws.part, ws.ctl);
+  }
   // injected uniforms: a round can only be run if the buffer still covers its draws (numpy consumes batch - n_found per round);
   // the caller sizes it (n_uniforms) and the status words tell how far the draw got
-  for (int r = 0; r < rounds; ++r) {
-    if (a->uniforms && r > 0 && a->n_uniforms < (int64_t)a->batch * (r + 1)) break;
-    replay_block_sums<<<(unsigned)nb, RB_THREADS, 0, st>>>(a->priorities, taken, total, a->per_alpha, a->batch, ws.ctl, ws.bsum);
-    replay_scan_blocks<<<1, 1024, 0, st>>>(ws.bsum, ws.bpre, nb, a->batch, ws.ctl);
+  int last = 0;
+  for (int r = 0; r < rounds; ++r)
+    if (!(a->uniforms && (r > 0 || a->resume) && a->n_uniforms < (int64_t)a->batch * (r + 1 + (a->resume > 0 ? a->resume : 0)))) last = r + 1;
+    else break;
+  if (last == 0) return fail(TDMPC_ERR_INVALID, "replay_sample: injected uniforms exhausted");
+  for (int r = 0; r < last; ++r) {
+    replay_block_sums<<<(unsigned)nb, RB_THREADS, 0, st>>>(a->priorities, taken, total, a->per_alpha, a->batch, ws.ctl, ws.bsum, ws.bpre);
     replay_search<<<(a->batch * 32 + RB_THREADS - 1) / RB_THREADS, RB_THREADS, 0, st>>>(
-        a->priorities, taken, total, a->per_alpha, a->batch, a->uniforms, rng, ws.ctl, ws.bsum, ws.bpre, nb, ws.cand);
-    replay_commit<<<1, 1024, 0, st>>>(ws.cand, a->batch, a->replace, ws.ctl, taken, reinterpret_cast<long long*>(a->idxs));
+        a->priorities, taken, total, a->per_alpha, a->per_beta, a->batch, a->replace, r == last - 1, a->uniforms, rng, ws.ctl,
+        ws.bsum, ws.bpre, nb, ws.cand, reinterpret_cast<long long*>(a->idxs), a->weights, a->status);
   }
-  replay_weights<<<1, 1024, 0, st>>>(a->priorities, total, a->per_alpha, a->per_beta, a->batch, ws.ctl, reinterpret_cast<long long*>(a->idxs), a->weights, a->status);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { char b[256]; snprintf(b, sizeof(b), "replay_sample: launch failed: %s", cudaGetErrorString(e)); return fail(TDMPC_ERR_CUDA, b); }
   return TDMPC_OK;

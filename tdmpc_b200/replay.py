@@ -22,7 +22,8 @@ class ReplayBuffer:
     (tests feed the one `np.random.seed(s)` would produce, which makes the indices those of the reference);
     without it a Philox stream keyed by (`seed`, number of sample() calls so far) is used."""
 
-    MAX_ROUNDS = 16
+    MAX_ROUNDS = 32          # numpy loops until done; beyond this the draw is reported as failed
+    ROUNDS_PER_CALL = 2      # redraw rounds enqueued before the status words are read
 
     def __init__(self, cfg, latent_plan=False, seed=0, device=None):
         if cfg.modality != 'state':
@@ -83,27 +84,42 @@ class ReplayBuffer:
         if rc != 0:
             raise RuntimeError(f"tdmpc_b200 replay: {self._lib.tdmpc_last_error(None).decode()} (status {rc})")
 
-    def sample_indices(self, uniforms=None):
-        """helper.py:507-513 on the device: (idxs int64 [batch], weights float32 [batch])."""
+    def _sample_args(self, idxs, weights, uniforms=None, priorities=None):
+        """tdmpc_replay_sample_args for the buffer's current fill state (keeps `uniforms` alive on the struct)."""
         total = self.capacity if self._full else self.idx
         if total <= 0:
             raise RuntimeError("tdmpc_b200 replay: sample() on an empty buffer")
-        idxs = torch.empty(self.batch_size, dtype=torch.int64, device=self.device)
-        weights = torch.empty(self.batch_size, dtype=torch.float32, device=self.device)
         a = _lib.ReplaySampleArgs()
-        a.priorities, a.total, a.batch = self._priorities.data_ptr(), total, self.batch_size
+        a.priorities = (self._priorities if priorities is None else priorities).data_ptr()
+        a.total, a.batch = total, self.batch_size
         a.replace = int(not self._full)                                                             # helper.py:511
         a.per_alpha, a.per_beta = float(self.cfg.per_alpha), float(self.cfg.per_beta)
         if uniforms is not None:
-            uniforms = torch.as_tensor(uniforms, dtype=torch.float64).to(self.device).contiguous()
+            a._keep = uniforms = torch.as_tensor(uniforms, dtype=torch.float64).to(self.device).contiguous()
             a.uniforms, a.n_uniforms = uniforms.data_ptr(), uniforms.numel()
         a.seed, a.call = self._seed, self._calls
-        a.max_rounds = self.MAX_ROUNDS
+        a.max_rounds = self.ROUNDS_PER_CALL
         a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         a.idxs, a.weights, a.status = idxs.data_ptr(), weights.data_ptr(), self._status.data_ptr()
-        self._check(self._lib.tdmpc_replay_sample(C.byref(a), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return a
+
+    def sample_indices(self, uniforms=None):
+        """helper.py:507-513 on the device: (idxs int64 [batch], weights float32 [batch])."""
+        idxs = torch.empty(self.batch_size, dtype=torch.int64, device=self.device)
+        weights = torch.empty(self.batch_size, dtype=torch.float32, device=self.device)
+        a = self._sample_args(idxs, weights, uniforms)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        found, rounds = 0, 0
+        while True:
+            a.resume = rounds
+            self._check(self._lib.tdmpc_replay_sample(C.byref(a), stream))
+            before = found
+            found, now = self._status.tolist()         # the one host read (the reference syncs on the whole vector here)
+            stuck = now == rounds or found == before   # out of injected uniforms / nothing drawable left
+            rounds = now
+            if found >= self.batch_size or stuck or rounds >= self.MAX_ROUNDS:
+                break
         self._calls += 1
-        found, rounds = self._status.tolist()          # the one host read (the reference syncs on the whole vector here)
         if found < self.batch_size:
             raise RuntimeError(f"tdmpc_b200 replay: {found} of {self.batch_size} distinct indices after {rounds} rounds "
                                "(fewer drawable transitions than batch_size, or too few uniforms supplied)")
