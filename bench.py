@@ -92,49 +92,67 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def drnn_batched(dev, precision, B):
-    """Batched TdICemSimDssm-style planning (cfg5 dims: obs 18, act 4, Hd=128, H=10, N=1024 decaying, K=32, mixture 0.5, I=6)
-    through Planner.plan: elite carry-over, single-beta colored noise, hidden state in/out."""
+def icem_batched(dev, precision, B, drnn, reps=3):
+    """Batched iCEM planning through Planner.plan (H=10, N=1024 decaying by 1.25, K=32, mixture 0.5, I=6, obs 18, act 4): elite
+    carry-over, colored noise, best-a.  drnn=False: TdICemSimMlp (BASELINE.json configs[3]: MLP dynamics, white/pink/brown mix);
+    drnn=True: TdICemSimDssm (configs[4]: GRU dynamics Hd=128, single-beta colored noise, hidden state in/out)."""
     from tdmpc_b200 import Planner
-    from tdmpc_b200.colored import synthesis_matrix
-    cfg = synth.make_cfg("cfg5")
+    from tdmpc_b200.colored import color_matrices, mix_split, synthesis_matrix
+    cfg = synth.make_cfg("cfg5" if drnn else "cfg4")
+    extra_kw = dict(dynamics="drnn", hidden_dim=cfg.hidden_dim) if drnn else {}
     pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, enc_layernorm=True, precision=precision,
-                 device=dev, dynamics="drnn", hidden_dim=cfg.hidden_dim)
-    pl.sync_weights({k: v.to(dev) for k, v in synth.make_drnn_weights(cfg, 0).items()})
+                 device=dev, **extra_kw)
+    sd = synth.make_drnn_weights(cfg, 0) if drnn else synth.make_told_weights(cfg, 0, enc_ln=True)
+    pl.sync_weights({k: v.to(dev) for k, v in sd.items()})
     H, K, I, A = cfg.horizon, cfg.num_elites, cfg.iterations, cfg.action_dim
     sizes, n = [], cfg.num_samples
     for i in range(I):
         if i > 0:
             n = max(2 * K, int(n / cfg.factor_decrease_num))
         sizes.append((n, int(cfg.fraction_elites_reused * K), int(0.5 * n)))
-    mats = np.zeros((3, H, H), dtype=np.float32)
-    mats[0] = mats[1] = mats[2] = synthesis_matrix(cfg.noise_beta, H)
-    color = {"len": H, "mats": torch.from_numpy(mats).to(dev), "n_white": [0] * I, "n_color1": [s[0] for s in sizes]}
+    if drnn:
+        mats = np.zeros((3, H, H), dtype=np.float32)
+        mats[0] = mats[1] = mats[2] = synthesis_matrix(cfg.noise_beta, H)
+        color = {"len": H, "mats": torch.from_numpy(mats).to(dev), "n_white": [0] * I, "n_color1": [s[0] for s in sizes]}
+    else:
+        splits = [mix_split(s[0]) for s in sizes]
+        color = {"len": H, "mats": torch.from_numpy(color_matrices(H, H, cfg.noise_beta)).to(dev),
+                 "n_white": [sp[0] for sp in splits], "n_color1": [sp[1] for sp in splits]}
     obs = torch.from_numpy(synth.make_obs(cfg, 1, batch=B)).to(dev)
-    hid = torch.zeros(B, cfg.hidden_dim, device=dev)
     kw = dict(horizon=H, num_samples=cfg.num_samples, num_pi_trajs=sizes[0][2], num_elites=K, iterations=I, discount=cfg.discount,
               temperature=cfg.temperature, momentum=cfg.momentum, min_std=cfg.min_std, std_floor=cfg.min_std, init_std=0.5, eval_mode=True,
               n_samples=[s[0] for s in sizes], n_reuse=[s[1] for s in sizes], n_pi=[s[2] for s in sizes],
               elite_actions=torch.zeros(B, K, H, A, device=dev), elite_horizon=H, warm_last=True, best_a_last=True, shift_elites=True,
-              color=color, hidden=hid, hidden_out=torch.empty_like(hid), prev_mean=torch.zeros(B, H, A, device=dev))
+              color=color, prev_mean=torch.zeros(B, H, A, device=dev))
+    if drnn:
+        hid = torch.zeros(B, cfg.hidden_dim, device=dev)
+        kw.update(hidden=hid, hidden_out=torch.empty_like(hid))
     for _ in range(2):
         pl.plan(obs, t0=False, has_prev=True, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
+    for _ in range(reps):
         pl.plan(obs, t0=False, has_prev=True, **kw)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    ms = e0.elapsed_time(e1) / reps
     rows = [sum(s) for s in sizes]
-    # algorithmic FLOPs (SURVEY 8d): DRNN row-step 0.976 MFLOP (GRU + prior + reward), terminal 1.73 MFLOP per row, policy rollout
-    # rows pay pi + GRU + prior per step
+    # algorithmic FLOPs (SURVEY 8d).  GRU: row-step 0.976 MFLOP (GRU + prior + reward), terminal 1.73 MFLOP per row, policy rollout
+    # rows pay pi + GRU + prior per step.  MLP: row-step F_dyn + F_rew, terminal F_pi + 2 F_Q, policy rollout rows pi + dynamics.
     L, M, Hd = cfg.latent_dim, cfg.mlp_dim, cfg.hidden_dim
-    f_gru = 2 * 3 * Hd * (L + A + Hd); f_prior = 2 * (Hd * M + M * L); f_rew = 2 * (Hd * M + M * M + M)
     f_pi = 2 * (L * M + M * M + M * A); f_q = 2 * ((L + A) * M + M * M + M)
-    flop = sum(T * (H * (f_gru + f_prior + f_rew) + f_pi + 2 * f_q) for T in rows) + sizes[0][2] * H * (f_pi + f_gru + f_prior)
-    return {"workload": f"iCEM + GRU dynamics, {B} environments per launch, rows per iteration {rows}, precision {precision}",
-            "ms_per_batched_plan": ms, "plans_per_sec": B / ms * 1e3, "flop_per_plan": flop, "tflops": B / ms * 1e3 * flop / 1e12}
+    if drnn:
+        f_step = 2 * 3 * Hd * (L + A + Hd) + 2 * (Hd * M + M * L); f_rew = 2 * (Hd * M + M * M + M)
+    else:
+        f_step = 2 * ((L + A) * M + M * M + M * L); f_rew = 2 * ((L + A) * M + M * M + M)
+    flop = sum(T * (H * (f_step + f_rew) + f_pi + 2 * f_q) for T in rows) + sizes[0][2] * H * (f_pi + f_step)
+    return {"workload": f"iCEM + {'GRU' if drnn else 'MLP'} dynamics, {B} environments per launch, rows per iteration {rows}, precision {precision}",
+            "ms_per_batched_plan": ms, "plans_per_sec": B / ms * 1e3, "sample_steps_per_sec": B / ms * 1e3 * (sum(rows) + sizes[0][2]) * H,
+            "flop_per_plan": flop, "tflops": B / ms * 1e3 * flop / 1e12}
+
+
+def drnn_batched(dev, precision, B):
+    return icem_batched(dev, precision, B, True)
 
 
 def replay_extra(dev, hbm_peak):
@@ -463,6 +481,8 @@ def main():
                                                  f"mixture 0.5, I=6, precision {prec}", "ms_per_plan_wall": ms1, "plans_per_sec": 1e3 / ms1}
             # BASELINE.json configs[4]: batched iCEM planning through the GRU latent dynamics (256 environments per launch here)
             extra["cfg5_b256"] = drnn_batched(dev, args.precision, 256)
+            # BASELINE.json configs[3]: the same batched through the MLP dynamics (TdICemSimMlp)
+            extra["cfg4_b256"] = icem_batched(dev, args.precision, 256, False)
             if world == 1:
                 extra["replay_sample_1m"] = replay_extra(dev, measured_peaks()[2])
             # the batched environment-stepping loop (tdmpc_b200.PlanLoop): numpy observations in, numpy
