@@ -448,8 +448,26 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     return sp;
   };
 
+  // With one CTA per problem a small batch leaves the sampling of N*H*A normals per iteration to a handful of SMs (B = 1, dog
+  // dims: 250 us per iteration): below two CTAs per SM the rows are drawn by sample_kernel, `nparts` CTAs per problem.
+  int nparts = 1;
+  if (B < 2 * h->num_sms) {
+    int most = 1;
+    for (int i = 0; i < I; ++i) most = a->n_samples[i] > most ? a->n_samples[i] : most;
+    const int want = (2 * h->num_sms + B - 1) / B, useful = (int)(((size_t)most * H * A + 1023) / 1024);
+    nparts = want < useful ? want : useful;
+    nparts = nparts > 64 ? 64 : (nparts < 8 ? 1 : nparts);     // under 8 k normals per iteration the extra launch costs more than it saves
+  }
+  auto sample_split = [&](const SampleSpec& s_, const float* reuse) -> int {
+    SampleParams q{};
+    q.B = B; q.H = H; q.A = A; q.Tcap = Tmax; q.spec = s_; q.mean = h->mean; q.std = h->std; q.actions = h->actions;
+    q.pi_actions = h->pi_actions; q.P0 = P0; q.reuse = reuse; q.reuse_rows = K;
+    launch_sample(q, nparts, st);
+    return check_launch(h, "sample");
+  };
+
   InitParams ip{};
-  ip.B = B; ip.H = H; ip.A = A; ip.Tcap = Tmax; ip.first = spec(0);
+  ip.B = B; ip.H = H; ip.A = A; ip.Tcap = Tmax; ip.first = spec(0); ip.skip_sample = nparts > 1;
   ip.init_std = a->init_std; ip.t0_all = a->t0_all; ip.t0 = a->t0; ip.has_prev = a->has_prev; ip.warm_last = a->warm_last;
   ip.prev_mean = a->prev_mean; ip.mean = h->mean; ip.std = h->std; ip.actions = h->actions;
   ip.pi_actions = h->pi_actions; ip.P0 = P0; ip.elite_actions = elites; ip.K = K; ip.shift_elites = a->shift_elites; ip.elite_h = eh;
@@ -457,6 +475,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
   ip.shift_mat = (CL > 0 && !a->noise_shift) ? a->color_mats + 2 * (size_t)CL * CL : nullptr;
   launch_init(ip, st);
   if (int r = check_launch(h, "init")) return r;
+  if (nparts > 1) if (int r = sample_split(ip.first, nullptr)) return r;
 
   for (int i = 0; i < I; ++i) {
     const int T = a->n_samples[i] + a->n_reuse[i] + a->n_pi[i];
@@ -476,7 +495,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     sp.elite_idx = h->elite_idx; sp.score = h->score;
     sp.elite_actions = (a->elite_actions || any_reuse) ? elites : nullptr;
     const bool last = i == I - 1;
-    sp.do_sample = !last; sp.do_output = last;
+    sp.do_sample = !last && nparts == 1; sp.do_output = last;
     if (!last) {
       sp.next = spec(i + 1);
       sp.pi_actions = h->pi_actions; sp.P0 = P0;
@@ -489,6 +508,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     sp.tap_elite_idx = a->tap_elite_idx; sp.tap_mean = a->tap_mean; sp.tap_std = a->tap_std;
     launch_select(sp, st);
     if (int r = check_launch(h, "select")) return r;
+    if (!last && nparts > 1) if (int r = sample_split(sp.next, sp.elite_actions)) return r;
   }
   if (h->cfg.dynamics == TDMPC_DYN_DRNN && a->hidden_out) {
     // step the model with the chosen action to get the next GRU state (tdmpc_icem_similarity_drnn.py:267)

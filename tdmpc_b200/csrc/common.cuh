@@ -197,9 +197,20 @@ struct SelectParams {
   int* tap_elite_idx; float* tap_mean; float* tap_std;
 };
 
+// Stand-alone sampling of one iteration's rows from (mean, std) in global memory (sample_kernel, grid (B, nparts)).
+struct SampleParams {
+  int B, H, A, Tcap;
+  SampleSpec spec;
+  const float* mean; const float* std;   // [B, H, A]
+  float* actions;
+  const float* pi_actions; int P0;
+  const float* reuse; int reuse_rows;    // reused elite rows [B, reuse_rows, H, A] or nullptr (already in place)
+};
+
 struct InitParams {
   int B, H, A;
   int Tcap;
+  int skip_sample;            // 1: iteration-0 rows are drawn by sample_kernel instead
   SampleSpec first;           // rows of iteration 0
   float init_std;
   int t0_all; const uint8_t* t0; int has_prev; int warm_last;
@@ -219,6 +230,7 @@ void launch_rollout_fp32(const ModelFp32& m, const RolloutParams& p, cudaStream_
 int  launch_rollout_tc(const struct TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st);
 void launch_select(const SelectParams& p, cudaStream_t st);
 void launch_init(const InitParams& p, cudaStream_t st);
+void launch_sample(const SampleParams& p, int nparts, cudaStream_t st);
 void launch_bump_counter(uint64_t* c, cudaStream_t st);     // *c += 1 (tdmpc_plan_args.call_dev)
 void launch_fill_noise(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out, cudaStream_t st);
 void launch_transpose_pack(const float* w, int N, int K, int Kp, int Kdst_off, float* wt, cudaStream_t st);

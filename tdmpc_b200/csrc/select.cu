@@ -94,15 +94,18 @@ __device__ __forceinline__ float sample_noise(const SampleSpec& sp, int b, int t
 // Rows of one iteration, in the reference's concatenation order [sampled | reused elites | pi]
 // (tdmpc.py:130-134; tdmpc_icem_similarity_mlp.py:230-233).  `reuse` rows must already be in place
 // (init_kernel writes the shifted elites itself) unless reuse != nullptr.
+// `part` of `nparts` CTAs share one problem's rows (element-interleaved); the single-CTA callers pass 0 of 1.
 __device__ void sample_rows(int b, const SampleSpec& sp, int Tcap, int H, int A, const float* mean_s, const float* std_s,
-                            float* actions, const float* pi_actions, int P0, const float* reuse, int reuse_rows) {
+                            float* actions, const float* pi_actions, int P0, const float* reuse, int reuse_rows,
+                            int part = 0, int nparts = 1) {
   const int HA = H * A;
+  const int first = part * NT + threadIdx.x, stride = nparts * NT;
   float* out = actions + (size_t)b * Tcap * HA;
   const uint64_t row0 = sp.cem_base + (uint64_t)b * sp.cem_bstride;
   if (!sp.cem.inj && sp.color_len == 0 && (A & 3) == 0 && (row0 & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     // white built-in noise, A a multiple of 4: the 4 actions of one (row, step, a..a+3) group are the 4 normals of ONE
     // Philox block -- one block and two Box-Muller pairs per 4 outputs instead of per output, one 16-byte store
-    for (int q = threadIdx.x; q < sp.N * HA / 4; q += NT) {
+    for (int q = first; q < sp.N * HA / 4; q += stride) {
       const int e = q * 4;
       const int n = e / HA, ta = e - n * HA;
       const int t = ta / A, a = ta - t * A;
@@ -117,7 +120,7 @@ __device__ void sample_rows(int b, const SampleSpec& sp, int Tcap, int H, int A,
       *reinterpret_cast<float4*>(out + e) = v;
     }
   } else
-  for (int e = threadIdx.x; e < sp.N * HA; e += NT) {
+  for (int e = first; e < sp.N * HA; e += stride) {
     const int n = e / HA, ta = e - n * HA;
     const int t = ta / A, a = ta - t * A;
     float v = mean_s[ta] + std_s[ta] * sample_noise(sp, b, t, n, a, A);   // mean + std * noise, clamp(-1, 1)  (tdmpc.py:130-132)
@@ -126,10 +129,21 @@ __device__ void sample_rows(int b, const SampleSpec& sp, int Tcap, int H, int A,
     out[e] = v;
   }
   if (reuse)
-    for (int e = threadIdx.x; e < sp.E * HA; e += NT)
+    for (int e = first; e < sp.E * HA; e += stride)
       out[(size_t)sp.N * HA + e] = reuse[(size_t)b * reuse_rows * HA + e];
-  for (int e = threadIdx.x; e < sp.P * HA; e += NT)
+  for (int e = first; e < sp.P * HA; e += stride)
     out[(size_t)(sp.N + sp.E) * HA + e] = pi_actions[(size_t)b * P0 * HA + e];
+}
+
+// Sampling alone, grid (B, nparts): used instead of the fused tail of select_kernel / init_kernel when there are too few
+// problems to fill the GPU with one CTA each (B = 1: a single CTA would draw all N*H*A normals of an iteration).
+// Same Philox addressing per element, so the rows are bit-identical to the fused path's.
+__global__ void __launch_bounds__(NT) sample_kernel(SampleParams p) {
+  __shared__ float mean_s[MAX_HA], std_s[MAX_HA];
+  const int b = blockIdx.x, HA = p.H * p.A;
+  for (int e = threadIdx.x; e < HA; e += NT) { mean_s[e] = p.mean[(size_t)b * HA + e]; std_s[e] = p.std[(size_t)b * HA + e]; }
+  __syncthreads();
+  sample_rows(b, p.spec, p.Tcap, p.H, p.A, mean_s, std_s, p.actions, p.pi_actions, p.P0, p.reuse, p.reuse_rows, blockIdx.y, gridDim.y);
 }
 
 __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
@@ -271,7 +285,7 @@ __global__ void __launch_bounds__(NT) init_kernel(InitParams p) {
       out[e] = v;
     }
   }
-  sample_rows(b, sp, p.Tcap, H, A, mean_s, std_s, p.actions, p.pi_actions, p.P0, nullptr, 0);
+  if (!p.skip_sample) sample_rows(b, sp, p.Tcap, H, A, mean_s, std_s, p.actions, p.pi_actions, p.P0, nullptr, 0);
 }
 
 __global__ void fill_noise_kernel(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out) {
@@ -317,6 +331,7 @@ void launch_select(const SelectParams& p, cudaStream_t st) {
 __global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }
 void launch_bump_counter(uint64_t* c, cudaStream_t st) { bump_counter_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(c)); }
 void launch_init(const InitParams& p, cudaStream_t st) { init_kernel<<<p.B, NT, 0, st>>>(p); }
+void launch_sample(const SampleParams& p, int nparts, cudaStream_t st) { sample_kernel<<<dim3(p.B, nparts), NT, 0, st>>>(p); }
 
 void launch_fill_noise(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out, cudaStream_t st) {
   const int blocks = (int)((count + 255) / 256 < 4096 ? (count + 255) / 256 : 4096);

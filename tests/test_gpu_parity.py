@@ -931,3 +931,27 @@ def test_drnn_estimate_value_with_per_row_hidden(precision):
         assert err.max().item() <= TOL_FP32 and abs(r_g - r_o) <= 1e-5 * max(1.0, abs(r_o))
     else:
         assert err.median().item() <= TOL_BF16 and (err <= TOL_BF16).float().mean().item() >= 0.75
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_split_sampling_small_batch_matches_fused(precision):
+    """B = 1 at dog-run dims draws its rows with sample_kernel (several CTAs per problem); a batch that fills the GPU keeps the
+    fused tail of select_kernel / init_kernel.  Same Philox addressing -> problem 0 must come out bit-identical, built-in noise."""
+    gu = _gu()
+    cfg = synth.make_cfg("cfg2s", iterations=3)
+    sd = synth.make_told_weights(cfg, 9)
+    pl = gu.make_planner(cfg, sd, precision)
+    Bbig = 2 * torch.cuda.get_device_properties(0).multi_processor_count
+    obs = torch.from_numpy(np.stack([synth.make_obs(cfg, 70)] * Bbig)).cuda()
+    kw = dict(**gu.plan_kwargs(cfg), eval_mode=False, t0=True, taps=True)
+    n0 = pl.launch_count
+    big = pl.plan(obs, seed=77, call=5, **kw)
+    n_big = pl.launch_count - n0
+    one = pl.plan(obs[:1], seed=77, call=5, **kw)
+    n_one = pl.launch_count - n0 - n_big
+    torch.cuda.synchronize()
+    assert n_one == n_big + cfg.iterations          # one sample_kernel per iteration on top of the fused path's launches
+    assert torch.equal(one["action"][0], big["action"][0])
+    assert torch.equal(one["taps"]["values"][:, 0], big["taps"]["values"][:, 0])
+    assert torch.equal(one["taps"]["elite_idx"][:, 0], big["taps"]["elite_idx"][:, 0])
+    assert torch.equal(one["prev_mean"][0], big["prev_mean"][0])
