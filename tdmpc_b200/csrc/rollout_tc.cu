@@ -936,8 +936,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             // Philox block when the stream offset is 4-aligned, e.g. A = 4)
             const bool terminal = (flags & F_TERMINAL) != 0;
             const uint64_t nbase = p.noise_base + (terminal ? 0 : (uint64_t)t * p.noise_tstride) + (uint64_t)pb * p.noise_bstride + (uint64_t)pj * A;
-            const bool nz4 = chain == CH_PI && !p.noise.inj && (nbase & 3) == 0 && p.min_std > 0.0f;
-            float zn[4] = {0.f, 0.f, 0.f, 0.f};
+            // Any stream offset: element nbase + a sits in Philox block (nbase + a) >> 2, lane (nbase + a) & 3, so the four actions
+            // a0..a0+3 take lanes r.. of block nbase/4 + a0/4 and lanes ..r-1 of the next one (r = nbase & 3; A = 38 gives r = 0 / 2
+            // on alternate rows).  One new block per group of four, carried over -- not one block + Box-Muller per element.
+            const bool nz4 = chain == CH_PI && !p.noise.inj && p.min_std > 0.0f;
+            const int nzr = (int)(nbase & 3);
+            float zn[4] = {0.f, 0.f, 0.f, 0.f}, zx[4] = {0.f, 0.f, 0.f, 0.f};
             if (nz4 && valid) philox_normal4(p.noise, nbase >> 2, zn);
             if (epi_only) { mbar_wait(d3_full, d3_phase, 15); d3_phase ^= 1; }
             else acc_wait();
@@ -984,7 +988,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int a0 = 0; a0 < A; a0 += 4) {
                 uint32_t v[4];
                 tmem_ld4(tlane + TM_ACC + b * 128 + a0, v);
-                if (nz4 && a0 > 0 && valid) philox_normal4(p.noise, (nbase + a0) >> 2, zn);
+                if (nz4 && valid && (nzr != 0 || a0 + 4 < A)) philox_normal4(p.noise, (nbase >> 2) + (a0 >> 2) + 1, zx);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -993,12 +997,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                     float x = 0.0f;
                     if (valid) {
                       const float mu = tanhf(__uint_as_float(v[i]) + __ldg(ch.b3 + a));
-                      x = policy_sample(mu, p.min_std, nz4 ? zn[i] : noise_at(p.noise, nbase + a));
+                      // lane nzr + i of the 8 normals {zn, zx} (compile-time i, run-time nzr: selects, no local array)
+                      const float w0 = i == 0 ? zn[0] : i == 1 ? zn[1] : i == 2 ? zn[2] : zn[3];
+                      const float w1 = i == 0 ? zn[1] : i == 1 ? zn[2] : i == 2 ? zn[3] : zx[0];
+                      const float w2 = i == 0 ? zn[2] : i == 1 ? zn[3] : i == 2 ? zx[0] : zx[1];
+                      const float w3 = i == 0 ? zn[3] : i == 1 ? zx[0] : i == 2 ? zx[1] : zx[2];
+                      const float zsel = nzr == 0 ? w0 : nzr == 1 ? w1 : nzr == 2 ? w2 : w3;
+                      x = policy_sample(mu, p.min_std, nz4 ? zsel : noise_at(p.noise, nbase + a));
                       if (!terminal) pi_row[(size_t)t * A + a] = x;
                     }
                     if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
                   }
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) zn[i] = zx[i];
               }
             }
             tcgen05_fence_before();

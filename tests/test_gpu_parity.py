@@ -399,11 +399,14 @@ def test_value_nan_guard():
         assert torch.equal(v.cpu(), torch.zeros(1, 40))
 
 
-def test_philox_stream_statistics_and_replay():
+@pytest.mark.parametrize("precision,cfg_name", [("fp32", "tiny"), ("bf16", "tiny"), ("bf16", "cfg2s")])
+def test_philox_stream_statistics_and_replay(precision, cfg_name):
+    """tiny has A = 3 and cfg2s A = 38: the per-row stream offsets take every alignment mod 4 (the tcgen05 policy-head epilogue
+    groups four actions per Philox block whatever the offset)."""
     gu = _gu()
-    cfg = synth.make_cfg("tiny")
+    cfg = synth.make_cfg(cfg_name, iterations=2) if cfg_name != "tiny" else synth.make_cfg(cfg_name)
     sd = synth.make_told_weights(cfg, 0)
-    pl = gu.make_planner(cfg, sd, "fp32")
+    pl = gu.make_planner(cfg, sd, precision)
     x = pl.fill_noise(1, 1 << 20, seed=123, call=7).cpu().double()
     assert abs(x.mean().item()) < 5e-3 and abs(x.std().item() - 1) < 5e-3
     assert abs((x ** 4).mean().item() - 3) < 0.05
