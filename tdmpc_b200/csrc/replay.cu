@@ -106,8 +106,14 @@ __device__ __forceinline__ float pow_alpha(float p, float alpha) { return powf(p
 __global__ void replay_pow_sum(const float* __restrict__ pri, long long total, float alpha, double* part, ReplayCtl* ctl) {
   __shared__ double sh[32];
   double acc = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    acc += (double)pow_alpha(__ldg(pri + i), alpha);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float v[4];                                   // four independent loads in flight before the first powf
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i0 + k * stride < total ? __ldg(pri + i0 + k * stride) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i0 + k * stride < total) acc += (double)pow_alpha(v[k], alpha);
+  }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
   if (!last_block_done(&ctl->done[0])) return;
@@ -159,10 +165,17 @@ __global__ void replay_block_sums(const float* __restrict__ pri, const unsigned 
   const float psum = ctl->prob_sum;
   const long long base = (long long)blockIdx.x * RB_BLK;
   double acc = 0.0;
-  for (int k = threadIdx.x; k < RB_BLK; k += blockDim.x) {
-    const long long i = base + k;
-    if (i < total) acc += prob_at(pri, taken, i, alpha, psum);
+  static_assert(RB_BLK == 4 * RB_THREADS, "one pass of four loads per thread");
+  float v[4];
+  bool live[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                    // loads first, arithmetic after
+    const long long i = base + threadIdx.x + k * RB_THREADS;
+    live[k] = i < total && !(taken && taken[i]);
+    v[k] = live[k] ? __ldg(pri + i) : 0.0f;
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (live[k]) acc += (double)(pow_alpha(v[k], alpha) / psum);
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) bsum[blockIdx.x] = acc;
   if (!last_block_done(&ctl->done[1])) return;
@@ -357,7 +370,7 @@ extern "C" int tdmpc_replay_sample(const tdmpc_replay_sample_args* a, void* stre
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const long long total = a->total;
   const long long nb = (total + RB_BLK - 1) / RB_BLK;
-  int nparts = (int)((total + RB_THREADS * 8 - 1) / (RB_THREADS * 8));
+  int nparts = (int)((total + RB_THREADS * 4 - 1) / (RB_THREADS * 4));
   nparts = nparts < 1 ? 1 : (nparts > RB_MAX_PARTS ? RB_MAX_PARTS : nparts);
   unsigned char* taken = a->replace ? nullptr : ws.taken;
   NoiseSrc rng{nullptr, a->seed, a->call, NS_REPLAY, nullptr};
