@@ -200,7 +200,7 @@ def replay_extra(dev, hbm_peak):
         assert buf._status.tolist()[0] in (512,) or full
         del many
         rounds = buf.last_rounds
-        alg = rounds * (2 * 4 * total if not full else (4 + 1) * total) + 4 * total      # pass 1 once, then per round: block sums (+ mask)
+        alg = 2 * 4 * total + rounds * (4 + int(full)) * total      # pass 1 reads the priorities and writes their powers; per round: block sums (+ mask)
         k = float(np.median(ms_k))
         key = "replace_false_full_buffer" if full else "replace_true"
         out[key] = {"ms_sample_indices_device": k, "ms_sample_wall_incl_gather_and_status_read": float(np.median(ms_w)),

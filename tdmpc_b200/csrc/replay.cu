@@ -11,9 +11,10 @@
 //
 // The cdf is never materialised: the priorities are cut into blocks of RB_BLK elements, one pass
 // gives the block sums (float64), a single CTA scans them, and every draw (one warp each) bisects
-// the block prefix and then re-walks ONE block with a warp scan.  Algorithmic bytes per sample call:
-// 2 x 4 x total (two passes over the priorities) + batch x RB_BLK x 4 for the walks (L2 hits).
-// HBM-bound, latency-scale: at total = 1 M that is 8 MB, about 1.3 us at the measured copy peak, so
+// the block prefix and then re-walks ONE block with a warp scan.  priorities ** alpha is evaluated once (pass 1 keeps it
+// in the workspace).  Algorithmic bytes per sample call: 3 x 4 x total (read priorities, write and re-read the powers)
+// + batch x RB_BLK x 4 for the walks (L2 hits).
+// HBM-bound, latency-scale: at total = 1 M that is 12 MB, about 1.9 us at the measured copy peak, so
 // the cost is the launches: 3 kernels + 1 memset for replace=True (every stage's serial tail runs in the last block
 // to finish, instead of in a single-CTA kernel of its own), 2 more kernels per redraw round.
 #include "common.cuh"
@@ -47,6 +48,7 @@ struct ReplayWs {
   double* bsum;              // [nb] block sums of the normalised probabilities
   double* bpre;              // [nb] exclusive prefix of bsum
   long long* cand;           // [batch] candidates of the current round
+  float* pw;                 // [total] priorities ** alpha, computed once by pass 1 (accurate powf is the expensive part of every sweep)
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -62,7 +64,8 @@ size_t ws_layout(int64_t total, int32_t batch, void* base, ReplayWs* ws) {
   void* bsum = take(sizeof(double) * nb);
   void* bpre = take(sizeof(double) * nb);
   void* cand = take(sizeof(long long) * (size_t)batch);
-  if (ws) *ws = ReplayWs{(ReplayCtl*)ctl, (unsigned char*)taken, (double*)part, (double*)bsum, (double*)bpre, (long long*)cand};
+  void* pw = take(sizeof(float) * (size_t)total);
+  if (ws) *ws = ReplayWs{(ReplayCtl*)ctl, (unsigned char*)taken, (double*)part, (double*)bsum, (double*)bpre, (long long*)cand, (float*)pw};
   return off;
 }
 
@@ -103,7 +106,7 @@ __device__ bool last_block_done(unsigned int* ticket) {
 __device__ __forceinline__ float pow_alpha(float p, float alpha) { return powf(p, alpha); }
 
 // launch 1: partial float64 sums of priorities ** alpha (grid-stride); the last block folds them into probs.sum()
-__global__ void replay_pow_sum(const float* __restrict__ pri, long long total, float alpha, double* part, ReplayCtl* ctl) {
+__global__ void replay_pow_sum(const float* __restrict__ pri, long long total, float alpha, float* __restrict__ pw, double* part, ReplayCtl* ctl) {
   __shared__ double sh[32];
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -112,7 +115,8 @@ __global__ void replay_pow_sum(const float* __restrict__ pri, long long total, f
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = i0 + k * stride < total ? __ldg(pri + i0 + k * stride) : 0.0f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (i0 + k * stride < total) acc += (double)pow_alpha(v[k], alpha);
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k * stride < total) { const float w = pow_alpha(v[k], alpha); pw[i0 + k * stride] = w; acc += (double)w; }
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
@@ -125,10 +129,9 @@ __global__ void replay_pow_sum(const float* __restrict__ pri, long long total, f
 }
 
 // the float64 value numpy sees for element i: float32(p_i^alpha / sum), 0 once it has been drawn without replacement
-__device__ __forceinline__ double prob_at(const float* __restrict__ pri, const unsigned char* taken, long long i,
-                                          float alpha, float psum) {
+__device__ __forceinline__ double prob_at(const float* __restrict__ pw, const unsigned char* taken, long long i, float psum) {
   if (taken && taken[i]) return 0.0;
-  return (double)(pow_alpha(__ldg(pri + i), alpha) / psum);
+  return (double)(__ldg(pw + i) / psum);
 }
 
 // exclusive scan of the block sums by one CTA
@@ -158,8 +161,8 @@ __device__ void scan_block_sums(const double* bsum, double* bpre, long long nb, 
 }
 
 // launch 2 (per round): block sums of the (masked) normalised probabilities; the last block scans them
-__global__ void replay_block_sums(const float* __restrict__ pri, const unsigned char* taken, long long total,
-                                  float alpha, int batch, ReplayCtl* ctl, double* bsum, double* bpre) {
+__global__ void replay_block_sums(const float* __restrict__ pw, const unsigned char* taken, long long total,
+                                  int batch, ReplayCtl* ctl, double* bsum, double* bpre) {
   __shared__ double sh[32];
   if (ctl->n_found >= batch) return;
   const float psum = ctl->prob_sum;
@@ -172,10 +175,10 @@ __global__ void replay_block_sums(const float* __restrict__ pri, const unsigned 
   for (int k = 0; k < 4; ++k) {                    // loads first, arithmetic after
     const long long i = base + threadIdx.x + k * RB_THREADS;
     live[k] = i < total && !(taken && taken[i]);
-    v[k] = live[k] ? __ldg(pri + i) : 0.0f;
+    v[k] = live[k] ? __ldg(pw + i) : 0.0f;
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) if (live[k]) acc += (double)(pow_alpha(v[k], alpha) / psum);
+  for (int k = 0; k < 4; ++k) if (live[k]) acc += (double)(v[k] / psum);
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) bsum[blockIdx.x] = acc;
   if (!last_block_done(&ctl->done[1])) return;
@@ -229,7 +232,7 @@ __device__ void commit_round(const long long* cand, int batch, int replace, Repl
 }
 
 // importance weights (helper.py:512-513) and the status words (one CTA)
-__device__ void finish_weights(const float* __restrict__ pri, long long total, float alpha, float beta, int batch,
+__device__ void finish_weights(const float* __restrict__ pw, long long total, float beta, int batch,
                                const ReplayCtl* ctl, long long* idxs, float* weights, int* status) {
   __shared__ float sh[32];
   const int found = (int)ctl->n_found;
@@ -238,7 +241,7 @@ __device__ void finish_weights(const float* __restrict__ pri, long long total, f
   for (int j = threadIdx.x; j < batch; j += blockDim.x) {
     float wgt = 0.0f;
     if (j < found) {
-      const float p = pow_alpha(__ldg(pri + idxs[j]), alpha) / psum;
+      const float p = __ldg(pw + idxs[j]) / psum;
       wgt = powf((float)total * p, -beta);
     } else {
       idxs[j] = -1;
@@ -259,7 +262,7 @@ __device__ void finish_weights(const float* __restrict__ pri, long long total, f
 
 // launch 3 (per round), one warp per draw: first index with cdf[i] / cdf[-1] > u  (searchsorted side='right');
 // the last block commits the round and, when the draw is complete or this was the last round enqueued, writes the weights
-__global__ void replay_search(const float* __restrict__ pri, unsigned char* taken, long long total, float alpha, float beta,
+__global__ void replay_search(const float* __restrict__ pw, unsigned char* taken, long long total, float beta,
                               int batch, int replace, int final_round, const double* __restrict__ uniforms, NoiseSrc rng,
                               ReplayCtl* ctl, const double* __restrict__ bsum, const double* __restrict__ bpre, long long nb,
                               long long* cand, long long* idxs, float* weights, int* status) {
@@ -291,7 +294,7 @@ __global__ void replay_search(const float* __restrict__ pri, unsigned char* take
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) {
           const long long i = base + lane * 32 + k;
-          if (i < total) tot += prob_at(pri, taken, i, alpha, psum);
+          if (i < total) tot += prob_at(pw, taken, i, psum);
         }
         double s = tot;
 #pragma unroll
@@ -304,7 +307,7 @@ __global__ void replay_search(const float* __restrict__ pri, unsigned char* take
         const int L = __ffs(hit) - 1;
         const double excl = run + __shfl_sync(0xffffffffu, s - tot, L);
         const long long i = base + L * 32 + lane;
-        const double q = i < total ? prob_at(pri, taken, i, alpha, psum) : 0.0;
+        const double q = i < total ? prob_at(pw, taken, i, psum) : 0.0;
         double s2 = q;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += t; }
@@ -314,7 +317,7 @@ __global__ void replay_search(const float* __restrict__ pri, unsigned char* take
       }
       if (pick < 0 && last_chunk >= 0) {                     // u beyond the re-summed total: the last drawable element of the buffer
         const long long i = last_chunk + lane;
-        const unsigned pos2 = __ballot_sync(0xffffffffu, i < total && prob_at(pri, taken, i, alpha, psum) > 0.0);
+        const unsigned pos2 = __ballot_sync(0xffffffffu, i < total && prob_at(pw, taken, i, psum) > 0.0);
         if (pos2) pick = last_chunk + (31 - __clz(pos2));
       }
     }
@@ -322,7 +325,7 @@ __global__ void replay_search(const float* __restrict__ pri, unsigned char* take
   }
   if (!last_block_done(&ctl->done[2])) return;
   commit_round(cand, batch, replace, ctl, taken, idxs, sc);
-  if (final_round || ctl->n_found >= batch) finish_weights(pri, total, alpha, beta, batch, ctl, idxs, weights, status);
+  if (final_round || ctl->n_found >= batch) finish_weights(pw, total, beta, batch, ctl, idxs, weights, status);
 }
 
 // grid (batch, horizon + 2): slice 0 is `obs`, slice s >= 1 is step t = s - 1 of next_obs / action / reward
@@ -378,7 +381,7 @@ extern "C" int tdmpc_replay_sample(const tdmpc_replay_sample_args* a, void* stre
     // one memset clears the control words and (without replacement) the drawn-already mask that sits right behind them
     const size_t clear = taken ? (size_t)((char*)ws.taken - (char*)ws.ctl) + (size_t)total : sizeof(ReplayCtl);
     if (cudaMemsetAsync(ws.ctl, 0, clear, st) != cudaSuccess) return fail(TDMPC_ERR_CUDA, "replay_sample: memset failed");
-    replay_pow_sum<<<nparts, RB_THREADS, 0, st>>>(a->priorities, total, a->per_alpha, ws.part, ws.ctl);
+    replay_pow_sum<<<nparts, RB_THREADS, 0, st>>>(a->priorities, total, a->per_alpha, ws.pw, ws.part, ws.ctl);
   }
   // injected uniforms: a round can only be run if the buffer still covers its draws (numpy consumes batch - n_found per round);
   // the caller sizes it (n_uniforms) and the status words tell how far the draw got
@@ -388,9 +391,9 @@ extern "C" int tdmpc_replay_sample(const tdmpc_replay_sample_args* a, void* stre
     else break;
   if (last == 0) return fail(TDMPC_ERR_INVALID, "replay_sample: injected uniforms exhausted");
   for (int r = 0; r < last; ++r) {
-    replay_block_sums<<<(unsigned)nb, RB_THREADS, 0, st>>>(a->priorities, taken, total, a->per_alpha, a->batch, ws.ctl, ws.bsum, ws.bpre);
+    replay_block_sums<<<(unsigned)nb, RB_THREADS, 0, st>>>(ws.pw, taken, total, a->batch, ws.ctl, ws.bsum, ws.bpre);
     replay_search<<<(a->batch * 32 + RB_THREADS - 1) / RB_THREADS, RB_THREADS, 0, st>>>(
-        a->priorities, taken, total, a->per_alpha, a->per_beta, a->batch, a->replace, r == last - 1, a->uniforms, rng, ws.ctl,
+        ws.pw, taken, total, a->per_beta, a->batch, a->replace, r == last - 1, a->uniforms, rng, ws.ctl,
         ws.bsum, ws.bpre, nb, ws.cand, reinterpret_cast<long long*>(a->idxs), a->weights, a->status);
   }
   const cudaError_t e = cudaGetLastError();
