@@ -115,14 +115,26 @@ __device__ __forceinline__ uint32_t job_first_tile(const TcModel& m, uint32_t jo
 }
 
 // bf16 store of one element of the [z,a] operand (128B-swizzled k-blocks of 64); explicit shared-space stores
-__device__ __forceinline__ void za_store1(uint8_t* za, int row, int k, float v) {
-  const uint32_t a = smem_u32(za) + (k >> 6) * TILE_BYTES + sw128_offset(row, k & 63);
+// (ckb: index of the compact last k-block, see tc_prims.cuh umma_desc_k16, or -1)
+__device__ __forceinline__ uint32_t za_offset(int row, int k, int ckb) {
+  const int kb = k >> 6;
+  return kb == ckb ? kb * TILE_BYTES + k16_offset(row, k & 63) : kb * TILE_BYTES + sw128_offset(row, k & 63);
+}
+__device__ __forceinline__ void za_store1(uint8_t* za, int row, int k, float v, int ckb) {
+  const uint32_t a = smem_u32(za) + za_offset(row, k, ckb);
   const unsigned short b = __bfloat16_as_ushort(__float2bfloat16(v));
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(b) : "memory");
 }
 // 8 consecutive k (k0 % 8 == 0) as one 16-byte store
 __device__ __forceinline__ void sw_store8(uint8_t* base, int row, int k0, const float* v) {
   const uint32_t a = smem_u32(base) + (k0 >> 6) * TILE_BYTES + sw128_offset(row, k0 & 63);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
+               "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
+}
+
+// the same for the [z,a] operand, whose last k-block may be compact
+__device__ __forceinline__ void za_store8(uint8_t* za, int row, int k0, const float* v, int ckb) {
+  const uint32_t a = smem_u32(za) + za_offset(row, k0, ckb);
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
                "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
 }
@@ -138,7 +150,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* xs = smem;
   uint8_t* za = xs + XS_BYTES;
-  uint8_t* wring = za + m.nkb1 * TILE_BYTES;
+  uint8_t* wring = za + m.za_bytes;
+  const int ckb = m.za_compact ? m.nkb1 - 1 : -1;       // compact last k-block of [z,a]
   float* xch = reinterpret_cast<float*>(wring + S * TILE_BYTES);     // [3][2 groups][128 rows] epilogue-group exchange
   float* qcs = xch + XCH_FLOATS;                                       // [4][512] Q-head layer constants (16-byte aligned)
   uint32_t* sjobs = reinterpret_cast<uint32_t*>(qcs + QC_FLOATS);
@@ -275,6 +288,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           if (ks < nks) umma_ss_p(d, umma_desc_make(alo + 2 * ks), umma_desc_make(blo + 2 * ks), idesc, (first && ks == 0) ? 0u : 1u, lead);
       };
 
+      // k-block kb of the [z,a] operand against the weight tile at b_addr
+      auto kblock_za = [&](uint32_t d, int kb, uint32_t b_addr, uint32_t idesc, bool first) {
+        if (kb == ckb) umma_ss_p(d, umma_desc_k16(za_addr + kb * TILE_BYTES), umma_desc_make(umma_desc_lo(b_addr)), idesc, first ? 0u : 1u, lead);
+        else kblock_ss(d, za_addr + kb * TILE_BYTES, b_addr, idesc, min(4, ks1_total - kb * 4), first);
+      };
+
       for (int it = 0; it < my_tiles; ++it)
         for (int j = 0; j < kp.njobs; ++j) {
           const uint32_t job = kp.jw[j];
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             } else {
               for (int kb = 0; kb < m.nkb1; ++kb) {
                 const uint32_t wt = tile_acquire();
-                kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+                kblock_za(d, kb, wt, idesc128, kb == 0);
                 tile_release();
               }
             }
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             const uint32_t d = tmem + TM_ACC + b * 128;
             for (int kb = 0; kb < m.nkb1; ++kb) {
               const uint32_t wt = tile_acquire();
-              kblock_ss(d, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+              kblock_za(d, kb, wt, idesc128, kb == 0);
               tile_release();
             }
             for (int kb = 0; kb < 2; ++kb) {
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             // gi_n = [z,a] W_ih[newval]^T -> Y; the n-gate epilogue forms gi_n + r * gh_n in registers (rnns.py:27)
             for (int kb = 0; kb < m.nkb1; ++kb) {
               const uint32_t wt = tile_acquire();
-              kblock_ss(tmem + TM_Y, za_addr + kb * TILE_BYTES, wt, idesc128, min(4, ks1_total - kb * 4), kb == 0);
+              kblock_za(tmem + TM_Y, kb, wt, idesc128, kb == 0);
               tile_release();
             }
             for (int i = 0; i < m.gi_pad; ++i) { tile_acquire(); tile_release(); }     // padding tiles keep the ring aligned
@@ -517,8 +536,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               for (int kb = 0; kb < nkb; ++kb) {
                 if (!first && c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
                 const uint32_t wt = tile_acquire();
-                kblock_ss(tmem + c * 128, (first ? za_addr : xs_addr) + kb * TILE_BYTES, wt, idesc128,
-                            first ? min(4, ks1_total - kb * 4) : 4, kb == 0);
+                if (first) kblock_za(tmem + c * 128, kb, wt, idesc128, kb == 0);
+                else kblock_ss(tmem + c * 128, xs_addr + kb * TILE_BYTES, wt, idesc128, 4, kb == 0);
                 tile_release();
               }
               umma_commit_p(&q_full[c], lead);
@@ -599,7 +618,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       // initial [z0, a0, 0...] row (group 0)
       if (grp == 0) {
         const float* zr = p.z0 + (size_t)pb * L;
-        for (int k0 = 0; k0 < m.nkb1 * 64; k0 += 8) {
+        for (int k0 = 0; k0 < (ckb >= 0 ? m.K1p : m.nkb1 * 64); k0 += 8) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -611,7 +630,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             v[i] = x;
           }
-          sw_store8(za, row, k0, v);
+          za_store8(za, row, k0, v, ckb);
         }
         fence_proxy_async_smem();
         mbar_arrive(za_full);
@@ -901,7 +920,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                         x = policy_sample(mu, p.min_std, noise_at(p.noise, nbase + a));
                         pi_row[(size_t)t * A + a] = x;
                       }
-                      if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
+                      if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x, ckb);
                     }
                   if (!(flags & F_LAST_STEP)) { fence_proxy_async_smem(); mbar_arrive(za_full); }
                 }
@@ -968,19 +987,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                       const float4 bb = bz[c8 * 2 + (i >> 2)];
                       o[i] = __uint_as_float(v[c8 * 8 + i]) + ((i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w);
                     }
-                    if (kk + 8 <= L) sw_store8(za, row, kk, o);
+                    if (kk + 8 <= L) za_store8(za, row, kk, o, ckb);
                     else {
                       // the 8-column group that also holds action columns: z elements only
 #pragma unroll
-                      for (int i = 0; i < 8; ++i) if (kk + i < L) za_store1(za, row, kk + i, o[i]);
+                      for (int i = 0; i < 8; ++i) if (kk + i < L) za_store1(za, row, kk + i, o[i], ckb);
                     }
                   }
                 }
               }
               if (next_act) {
 #pragma unroll
-                for (int a = 0; a < 8; ++a) if (a < A) za_store1(za, row, L + a, an[a]);
-                for (int a = 8; a < A; ++a) za_store1(za, row, L + a, valid ? __ldg(act_row + (size_t)(t + 1) * A + a) : 0.0f);
+                for (int a = 0; a < 8; ++a) if (a < A) za_store1(za, row, L + a, an[a], ckb);
+                for (int a = 8; a < A; ++a) za_store1(za, row, L + a, valid ? __ldg(act_row + (size_t)(t + 1) * A + a) : 0.0f, ckb);
               }
             } else {
               // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
@@ -1006,7 +1025,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                       x = policy_sample(mu, p.min_std, nz4 ? zsel : noise_at(p.noise, nbase + a));
                       if (!terminal) pi_row[(size_t)t * A + a] = x;
                     }
-                    if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x);
+                    if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x, ckb);
                   }
                 }
 #pragma unroll
@@ -1436,7 +1455,11 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
 
   // shared-memory budget -> weight ring depth
-  const int fixed = XS_BYTES + nkb1 * TILE_BYTES + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 22) * 8 + 16 + 1024;
+  // a last k-block that holds a single k-step is stored unswizzled in 4 KB (tc_prims.cuh: umma_desc_k16); at dog-run dims
+  // (K = 138 -> 128 + 16) that is the difference between a 2-slot and a 3-slot weight ring
+  m.za_compact = (!drnn && nkb1 >= 2 && m.K1p - 64 * (nkb1 - 1) == 16 && !getenv("TDMPC_TC_NO_COMPACT")) ? 1 : 0;
+  m.za_bytes = m.za_compact ? (nkb1 - 1) * TILE_BYTES + K16_BLOCK_BYTES : nkb1 * TILE_BYTES;
+  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 22) * 8 + 16 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly

@@ -62,6 +62,8 @@ struct TcModel {
   int L, A;
   int K1p;                     // L+A rounded up to 16 (UMMA_K)
   int nkb1;                    // 64-wide k-blocks of the [z,a] operand
+  int za_compact;              // 1: the last k-block holds ONE k-step (16 columns) and is stored unswizzled in 4 KB instead of 16 KB
+  int za_bytes;                // shared-memory size of the [z,a] operand
   int n3p[CH_COUNT];           // L3 MMA N (multiple of 16) for dyn / pi
   int l3rows[CH_COUNT];        // rows per L3 weight k-block tile: 64 or 128
   const uint32_t* jobs[2][TDMPC_MAX_H + 1];   // [mode][H] device job lists

@@ -239,6 +239,18 @@ constexpr uint32_t UMMA_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr_bytes) { return ((saddr_bytes & 0x3FFFF) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t umma_desc_make(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | lo; }
 
+// Compact k-block: 128 rows x 16 bf16 (one UMMA_K step), K-major WITHOUT swizzle ("interleave"): core matrices of 8 rows x 16 B,
+// the two along K 128 B apart (LBO), 8-row groups 256 B apart (SBO) -> 4 KB instead of the 16 KB of a swizzled 64-wide block.
+// Used for the last k-block of the [z,a] operand when it holds only 16 columns (dog-run dims: K = 138 -> 128 + 16).
+constexpr uint32_t UMMA_DESC_HI_K16 = (256u >> 4) | (1u << 14);                        // SBO, version 1, layout 0 (no swizzle)
+__device__ __forceinline__ uint64_t umma_desc_k16(uint32_t saddr_bytes) {
+  return ((uint64_t)UMMA_DESC_HI_K16 << 32) | (((saddr_bytes & 0x3FFFF) >> 4) | ((128u >> 4) << 16));
+}
+__host__ __device__ __forceinline__ uint32_t k16_offset(int row, int kk) {              // kk in [0, 16)
+  return (uint32_t)((row >> 3) * 256 + (kk >> 3) * 128 + (row & 7) * 16 + (kk & 7) * 2);
+}
+constexpr int K16_BLOCK_BYTES = 4096;
+
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 // [4,6) D fmt=1 (f32) | [7,10) A fmt=1 (bf16) | [10,13) B fmt=1 (bf16) | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
