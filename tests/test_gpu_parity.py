@@ -958,3 +958,21 @@ def test_split_sampling_small_batch_matches_fused(precision):
     assert torch.equal(one["taps"]["values"][:, 0], big["taps"]["values"][:, 0])
     assert torch.equal(one["taps"]["elite_idx"][:, 0], big["taps"]["elite_idx"][:, 0])
     assert torch.equal(one["prev_mean"][0], big["prev_mean"][0])
+
+
+def test_compact_last_kblock_is_bit_identical(monkeypatch):
+    """Dog-run dims (K = 138): the third k-block of the [z,a] operand is stored unswizzled in 4 KB (one k-step) to make room for
+    a third weight-ring slot.  Same arithmetic, different shared-memory layout and ring depth: a whole plan must equal, bit for
+    bit, the plan computed with the swizzled 16 KB block (TDMPC_TC_NO_COMPACT=1)."""
+    gu = _gu()
+    cfg = synth.make_cfg("cfg2", iterations=2)
+    sd = synth.make_told_weights(cfg, 4)
+    obs = torch.from_numpy(np.stack([synth.make_obs(cfg, 80 + b) for b in range(3)])).cuda()
+    kw = dict(**gu.plan_kwargs(cfg), eval_mode=False, t0=True, seed=21, call=2, taps=True)
+    a = gu.make_planner(cfg, sd, "bf16").plan(obs, **kw)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("TDMPC_TC_NO_COMPACT", "1")             # read when the weights are packed
+    b = gu.make_planner(cfg, sd, "bf16").plan(obs, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(a["taps"]["values"], b["taps"]["values"]) and torch.equal(a["action"], b["action"])
+    assert torch.equal(a["taps"]["elite_idx"], b["taps"]["elite_idx"]) and torch.equal(a["prev_mean"], b["prev_mean"])
