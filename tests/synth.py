@@ -30,6 +30,7 @@ def make_cfg(name="cfg1", **over):
         "cfg2": dict(obs_shape=(223,), action_dim=38, latent_dim=100, iterations=8),  # dog-run (cfgs/tasks/dog.yaml)
         "cfg2s": dict(obs_shape=(223,), action_dim=38),                   # dog-run with L=50, I=6
         "cfg3": dict(obs_shape=(18,), action_dim=4),                      # quadrotor xyz_vxyz_R_omega
+        "k80": dict(obs_shape=(18,), action_dim=6, latent_dim=64, iterations=2),   # L+A = 70 -> 64 + 16: compact SECOND k-block
         "cfg4": dict(obs_shape=(18,), action_dim=4, horizon=10, num_samples=1024, num_elites=32,
                      mixture_coef=0.5, horizon_schedule="linear(2, 10, 25000, 0)", normalize=True),
         "tiny": dict(obs_shape=(7,), action_dim=3, latent_dim=24, horizon=3, num_samples=96,

@@ -227,7 +227,7 @@ def _integer_model(cfg, seed):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-@pytest.mark.parametrize("cfg_name", ["tiny", "cfg3", "cfg2"])
+@pytest.mark.parametrize("cfg_name", ["tiny", "cfg3", "cfg2", "k80"])
 def test_integer_exact_rollout(cfg_name, precision):
     """Known-answer test: bit-exact trajectory values through H steps of dynamics + reward."""
     gu = _gu()
@@ -960,12 +960,13 @@ def test_split_sampling_small_batch_matches_fused(precision):
     assert torch.equal(one["prev_mean"][0], big["prev_mean"][0])
 
 
-def test_compact_last_kblock_is_bit_identical(monkeypatch):
-    """Dog-run dims (K = 138): the third k-block of the [z,a] operand is stored unswizzled in 4 KB (one k-step) to make room for
-    a third weight-ring slot.  Same arithmetic, different shared-memory layout and ring depth: a whole plan must equal, bit for
+@pytest.mark.parametrize("cfg_name", ["cfg2", "k80"])
+def test_compact_last_kblock_is_bit_identical(cfg_name, monkeypatch):
+    """Dog-run dims (K = 138; and K = 70, where it is the second block): the last k-block of the [z,a] operand is stored
+    unswizzled in 4 KB (one k-step) to make room for another weight-ring slot.  Same arithmetic, different shared-memory layout and ring depth: a whole plan must equal, bit for
     bit, the plan computed with the swizzled 16 KB block (TDMPC_TC_NO_COMPACT=1)."""
     gu = _gu()
-    cfg = synth.make_cfg("cfg2", iterations=2)
+    cfg = synth.make_cfg(cfg_name, iterations=2)
     sd = synth.make_told_weights(cfg, 4)
     obs = torch.from_numpy(np.stack([synth.make_obs(cfg, 80 + b) for b in range(3)])).cuda()
     kw = dict(**gu.plan_kwargs(cfg), eval_mode=False, t0=True, seed=21, call=2, taps=True)
