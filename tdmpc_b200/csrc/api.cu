@@ -131,6 +131,7 @@ extern "C" int tdmpc_destroy(tdmpc_handle* h) {
   free_scratch(h);
   cudaFree(h->arena32);
   cudaFree(h->arena_tc);
+  tc_release_host(&h->tc);
   delete h;
   return TDMPC_OK;
 }

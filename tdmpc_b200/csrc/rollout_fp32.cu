@@ -327,10 +327,13 @@ void launch_rollout_fp32(const ModelFp32& m, const RolloutParams& p, cudaStream_
   const int ldz = m.pi[0].Kp, ldn = (p.L + 3) & ~3;
   const size_t smem = sizeof(float) * ((size_t)2 * R * p.M + (size_t)R * ldz + (size_t)R * ldn + (size_t)R * p.A + 4 * R +
                                        (m.drnn ? (size_t)R * m.Hd : 0));
-  static size_t configured = 0;
-  if (smem > configured) {
+  // per function AND per device: remember what each device of this process was raised to
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
     cudaFuncSetAttribute(rollout_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   rollout_fp32_kernel<<<tiles, NT, smem, st>>>(m, p);
 }

@@ -22,6 +22,7 @@
 // All three roles walk the same job list (tc_model.cuh), which keeps the mbarrier phases aligned.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "tc_model.cuh"
@@ -1453,6 +1454,16 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
     }
   // pageable-host source: the runtime stages the bytes before returning, so `all` may die here
   if (cudaMemcpyAsync(jdst, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+  // host copy for the launches (the MMA warp reads its program from the kernel-parameter bank)
+  {
+    uint32_t* hj = static_cast<uint32_t*>(malloc(all.size() * sizeof(uint32_t) + 4));
+    if (!hj) return -1;
+    memcpy(hj, all.data(), all.size() * sizeof(uint32_t));
+    free(const_cast<uint32_t*>(out->jobs_host));          // re-pack of the same handle
+    m.jobs_host = hj;
+    for (int mode = 0; mode < 2; ++mode)
+      for (int H = 1; H <= TDMPC_MAX_H; ++H) m.jobs_off[mode][H] = (int)(m.jobs[mode][H] - jdst);
+  }
 
   // shared-memory budget -> weight ring depth
   // a last k-block that holds a single k-step is stored unswizzled in 4 KB (tc_prims.cuh: umma_desc_k16); at dog-run dims
@@ -1466,10 +1477,19 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (stages < 2) return -1;
   m.stages = stages;
   m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem_bytes) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem_bytes) != cudaSuccess) return -1;
+  // The attribute is per function AND per device, not per handle: always raise it to the fixed maximum, so handles with
+  // different shapes (or on different GPUs of one process) cannot shrink each other's limit.
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  { const char* e = getenv("TDMPC_TC_DEBUG"); m.debug = e ? atoi(e) : 0; }
+  m.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
+  if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) m.producers = v; }
   *out = m;
   return launches;
+}
+
+void tc_release_host(TcModel* m) {
+  if (m) { free(const_cast<uint32_t*>(m->jobs_host)); m->jobs_host = nullptr; }
 }
 
 static unsigned long long* g_tc_trace = nullptr;
@@ -1487,16 +1507,11 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
   kp.trace = g_tc_trace;
   kp.one = 1;
-  { const char* e = getenv("TDMPC_TC_DEBUG"); kp.debug = e ? atoi(e) : 0; }
-  kp.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
-  if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) kp.producers = v; }
+  kp.debug = m.debug;
+  kp.producers = m.producers;
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
-  if (kp.njobs <= 0) return -1;
-  {
-    const std::vector<uint32_t> jl = build_jobs(p.mode, p.H, m.drnn != 0, m.A);
-    if ((int)jl.size() != kp.njobs || kp.njobs > MAX_JOBS) return -1;
-    for (int i = 0; i < kp.njobs; ++i) kp.jw[i] = jl[i];
-  }
+  if (kp.njobs <= 0 || kp.njobs > MAX_JOBS || !m.jobs_host) return -1;
+  memcpy(kp.jw, m.jobs_host + m.jobs_off[p.mode][p.H], sizeof(uint32_t) * kp.njobs);
   if (m.drnn) rollout_tc_kernel<true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   else rollout_tc_kernel<false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   return 1;

@@ -70,6 +70,11 @@ struct TcModel {
   int njobs[2][TDMPC_MAX_H + 1];
   int stages;                  // weight ring depth that fits in shared memory
   size_t smem_bytes;
+  // host-side launch state, fixed when the weights are packed (environment switches are read THERE, not per launch)
+  const uint32_t* jobs_host;   // host copy of every job program (owned by the handle: tc_release_host)
+  int jobs_off[2][TDMPC_MAX_H + 1];
+  int debug;                   // TDMPC_TC_DEBUG (experiments only)
+  int producers;               // producer threads of the weight ring (divides `stages`)
   // DRNN (TDMPC_DYN_DRNN): chain CH_DYN is the prior MLP (layer 1: K = hidden_dim, layer 3 slot = its second Linear),
   // chain CH_REW's layer 1 reads the hidden state; gate weights live in their own tiles.
   int drnn;
@@ -86,3 +91,4 @@ const char* tc_supported(const tdmpc_model_cfg& c);     // nullptr when the shap
 size_t tc_arena_bytes(const tdmpc_model_cfg& c);
 // returns number of kernels launched (>= 0) or -1
 int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m32, void* arena, TcModel* out, cudaStream_t st);
+void tc_release_host(TcModel* m);    // frees jobs_host

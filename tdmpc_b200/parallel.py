@@ -15,18 +15,20 @@ def shard_range(total, rank, world):
 
 
 def broadcast_weights(model, src=0):
-    """After agent.update() on the trainer rank: one flat broadcast of every TOLD parameter
-    (about 6 MB fp32), then each rank re-packs locally (Planner.sync_weights)."""
+    """After agent.update() on the trainer rank: one flat broadcast of every TOLD parameter AND floating-point buffer
+    (about 6 MB fp32), then each rank re-packs locally (Planner.sync_weights).  Buffers matter: the GRU agent's prior MLP
+    carries BatchNorm running statistics (`_dynamics.prior_mlp.1.running_mean / running_var`) that update() moves in
+    train mode and the planner folds into its packed weights."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
-    params = list(model.parameters())
+    tensors = list(model.parameters()) + [b for b in model.buffers() if b.is_floating_point()]
     with torch.no_grad():
-        flat = torch.cat([p.reshape(-1) for p in params])
+        flat = torch.cat([p.reshape(-1).float() for p in tensors])
         dist.broadcast(flat, src=src)
         off = 0
-        for p in params:
+        for p in tensors:
             n = p.numel()
-            p.copy_(flat[off:off + n].view_as(p))     # on the parameter itself (not .data): bumps Tensor._version -> planner re-packs
+            p.copy_(flat[off:off + n].view_as(p))     # on the tensor itself (not .data): bumps Tensor._version -> planner re-packs
             off += n
 
 
@@ -54,6 +56,11 @@ class ShardedPlanner:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.lo, self.hi = shard_range(total, self.rank, self.world)
+        # every rank would otherwise draw the SAME Philox stream for its local problem i: fold the global offset of this
+        # shard into the seed (a 64-bit odd multiplier keeps distinct shards on distinct keys)
+        self.base_seed = int(getattr(planner, "seed", 0))
+        if hasattr(planner, "seed") and self.world > 1:
+            planner.seed = (self.base_seed + 0x9E3779B97F4A7C15 * (self.lo + 1)) & 0xFFFFFFFFFFFFFFFF
 
     def plan(self, obs_all_or_local, gather=True, **kw):
         obs = obs_all_or_local

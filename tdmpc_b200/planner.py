@@ -318,7 +318,9 @@ def _fast_plan(self, obs, eval_mode=False, step=None, t0=True):
     num_pi_trajs = int(cfg.mixture_coef * cfg.num_samples)
     obs_t = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.device, non_blocking=True).reshape(1, -1)
     prev = getattr(self, "_prev_mean", None)
-    has_prev = prev is not None
+    # the reference only reads _prev_mean when `not t0` (tdmpc.py:124): at an episode start the horizon may have grown
+    # (horizon_schedule) and the stale, shorter history must be ignored, not shape-checked
+    has_prev = prev is not None and not t0
     if has_prev and prev.shape[0] != horizon:
         # the reference relies on broadcasting `mean[:-1] = prev[1:]`; only an equal-length (or
         # length-2, i.e. broadcastable) history is meaningful -- emulate it, else fail like torch would
@@ -380,6 +382,10 @@ def _fast_plan_icem(self, obs, eval_mode=False, step=None, t0=True):
     if have and not shift and sizes[0][1] > 0:
         raise RuntimeError("fraction_elites_reused > 0 without shift_elites_over_time leaves `reused_actions` "
                            "undefined in the reference (tdmpc_icem_similarity_mlp.py:217-231)")
+    if cfg.fraction_elites_reused > 0 and not cfg.keep_previous_elites:
+        # the reference then keeps feeding iteration 0's `reused_actions` to the later iterations (:224-231); this path
+        # always reuses the previous iteration's elites, so refuse rather than diverge silently (as the DRNN path does)
+        raise NotImplementedError("fraction_elites_reused > 0 needs keep_previous_elites")
     ebuf = torch.zeros(1, K, H, A, device=self.device)
     eh = H
     if have:
@@ -490,17 +496,75 @@ def _fast_plan_icem_drnn(self, obs, hidden, eval_mode=False, step=None, t0=True)
     return res["action"][0], hid_out, plan_metrics
 
 
-def accelerate(agent, precision="bf16"):
+def _fast_plan_sim(self, obs, eval_mode=False, step=None, t0=True, fine_tuning=False):
+    """Drop-in for TDMPCSIM.plan (src/algorithm/tdmpc_similarity.py:135-200) -- the agent the quadrotor scripts build
+    (train_dyna_episode.py:86,144, train_dyna_episode_multi_agent.py:19).  Differences from TDMPC.plan that are reproduced:
+    returns the bare action tensor (no metrics), `fine_tuning` disables the seed-step early return, the planning horizon
+    `self.plan_horizon` only moves at an episode start (:151-152), the number of policy trajectories follows
+    `regularization_schedule` (:153-154) and may be zero."""
+    cfg = self.cfg
+    if step < cfg.seed_steps and not eval_mode and not fine_tuning:
+        return torch.empty(cfg.action_dim, dtype=torch.float32, device=self.device).uniform_(-1, 1)
+    pl = self._planner
+    pl.sync_weights(self.model)
+    horizon = int(min(cfg.horizon, linear_schedule(cfg.horizon_schedule, step)))
+    if horizon != self.plan_horizon and t0:
+        self.plan_horizon = horizon
+    H = self.plan_horizon
+    self.mixture_coef = linear_schedule(cfg.regularization_schedule, step)
+    num_pi_trajs = int(self.mixture_coef * cfg.num_samples)
+    prev = getattr(self, "_prev_mean", None)
+    has_prev = prev is not None and not t0
+    if has_prev and prev.shape[0] != H:       # `mean[:-1] = self._prev_mean[1:]` (:165) would fail the same way
+        raise RuntimeError(f"shape mismatch: _prev_mean has horizon {prev.shape[0]}, plan horizon is {H}")
+    buf = prev.reshape(1, H, cfg.action_dim).contiguous().clone() if has_prev else None
+    obs_t = torch.as_tensor(np.asarray(obs), dtype=torch.float32).to(self.device, non_blocking=True).reshape(1, -1)
+    res = pl.plan(obs_t, horizon=H, num_samples=cfg.num_samples, num_pi_trajs=num_pi_trajs, num_elites=cfg.num_elites,
+                  iterations=cfg.iterations, discount=cfg.discount, temperature=cfg.temperature, momentum=cfg.momentum,
+                  min_std=cfg.min_std, std_floor=self.std, eval_mode=eval_mode, t0=bool(t0), prev_mean=buf, has_prev=has_prev,
+                  noise=getattr(self, "_inject_noise", None), taps=getattr(self, "_want_taps", False))
+    self._prev_mean = res["prev_mean"][0]
+    self._last_taps = res["taps"]
+    return res["action"][0]
+
+
+_PLAN_KINDS = {"tdmpc": _fast_plan, "sim": _fast_plan_sim, "icem": _fast_plan_icem, "drnn": _fast_plan_icem_drnn}
+
+
+def agent_kind(agent):
+    """Which of the reference's four planner shapes an agent object has:
+    'drnn'  TdICemSimDssm  (GRU dynamics; plan(obs, hidden, ...) -> (a, hidden', metrics))   tdmpc_icem_similarity_drnn.py:81
+    'icem'  TdICemSimMlp   (sample_mix_action_sequence; plan -> (a, metrics))                tdmpc_icem_similarity_mlp.py:77
+    'sim'   TDMPCSIM       (plan_horizon + fine_tuning; plan -> a)                           tdmpc_similarity.py:74
+    'tdmpc' TDMPC          (plan -> (a, metrics))                                            tdmpc.py:53"""
+    if hasattr(agent.model._dynamics, "gru_cell"):
+        return "drnn"
+    if hasattr(type(agent), "sample_mix_action_sequence") or type(agent).__name__ == "TdICemSimMlp":
+        return "icem"
+    if hasattr(agent, "plan_horizon"):
+        return "sim"
+    return "tdmpc"
+
+
+def accelerate(agent, precision="bf16", kind=None):
     """Give an existing reference-style agent (attributes cfg, model, std, device) the CUDA `plan`.
-    The agent's nn.Module keeps owning the parameters; they are re-packed whenever they change."""
+    The agent's nn.Module keeps owning the parameters; they are re-packed whenever they change.
+    `kind` overrides the class detection of agent_kind()."""
     cfg = agent.cfg
-    sd = agent.model.state_dict()
-    drnn = hasattr(agent.model._dynamics, "gru_cell")
+    kind = agent_kind(agent) if kind is None else kind
+    if kind not in _PLAN_KINDS:
+        raise ValueError(f"accelerate: unknown agent kind {kind!r}")
+    drnn = kind == "drnn"
+    enc = agent.model._encoder
+    # helper.enc: Linear, ELU, Linear; helper.dmlab_enc_norm: Linear, <norm>, ELU, Linear with the norm chosen by
+    # cfg.norm_type (helper.py:161-165) -- only LayerNorm is implemented; anything else must not be packed as one
+    enc_ln = len(enc) == 4
+    if enc_ln and not isinstance(enc[1], torch.nn.LayerNorm):
+        raise NotImplementedError(f"accelerate: encoder normalisation {type(enc[1]).__name__} is not supported (LayerNorm only)")
     agent._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
-                             enc_layernorm="_encoder.3.weight" in sd, precision=precision, device=agent.device,
+                             enc_layernorm=enc_ln, precision=precision, device=agent.device,
                              dynamics="drnn" if drnn else "mlp", hidden_dim=cfg.hidden_dim if drnn else 0)
-    icem = hasattr(agent, "plan_horizon") and hasattr(cfg, "factor_decrease_num")
-    agent.plan = types.MethodType(_fast_plan_icem_drnn if drnn else _fast_plan_icem if icem else _fast_plan, agent)
+    agent.plan = types.MethodType(_PLAN_KINDS[kind], agent)
     return agent
 
 
@@ -539,7 +603,9 @@ class TDMPC:
         self._planner.sync_weights(self.model)
         # one "problem" per trajectory so every row may start from its own latent
         acts = actions[:horizon].permute(1, 0, 2).unsqueeze(1).contiguous()      # [T, 1, H, A]
-        v, r = self._planner.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std)
+        pl = self._planner
+        pl.call += 1                    # fresh terminal-policy noise per call, like the reference's _standard_normal draw
+        v, r = pl.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std, seed=pl.seed, call=pl.call)
         return v, float(r.mean().item())
 
     def update(self, replay_buffer, step):
@@ -598,5 +664,35 @@ class TdICemSimDssm(TDMPC):
         self._planner.sync_weights(self.model)
         H = self.plan_horizon
         acts = actions[:H].permute(1, 0, 2).unsqueeze(1).contiguous()      # one "problem" per trajectory: [T, 1, H, A]
-        v, r = self._planner.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std, hidden=hidden)
+        pl = self._planner
+        pl.call += 1
+        v, r = pl.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std, hidden=hidden, seed=pl.seed, call=pl.call)
         return v, float(r.mean().item())
+
+
+class TDMPCSIM(TDMPC):
+    """Planning half of the reference's TDMPCSIM agent (src/algorithm/tdmpc_similarity.py:74-200) on the B200 planner:
+    `plan(obs, eval_mode, step, t0, fine_tuning) -> action`."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        dev = getattr(cfg, "device", "cuda")
+        self.device = torch.device(dev if dev != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        self.std = linear_schedule(cfg.std_schedule, 0)
+        self.mixture_coef = linear_schedule(cfg.regularization_schedule, 0)
+        self.model = DSSM(cfg).to(self.device)            # same sub-modules / state_dict keys as tdmpc_similarity.TOLD
+        self.model_target = deepcopy(self.model)
+        self.model.eval()
+        self.model_target.eval()
+        self.plan_horizon = 1
+        self.batch_size = getattr(cfg, "batch_size", None)
+        self._planner = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
+                                enc_layernorm=bool(cfg.normalize), precision=getattr(cfg, "precision", "bf16"),
+                                device=self.device)
+
+    plan = _fast_plan_sim
+
+    @torch.no_grad()
+    def estimate_value(self, z, actions, horizon):
+        """Reference signature (tdmpc_similarity.py:124-133): returns G [T,1] only."""
+        return TDMPC.estimate_value(self, z, actions, horizon)[0]

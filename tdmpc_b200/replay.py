@@ -46,6 +46,11 @@ class ReplayBuffer:
         self.idx = 0
         self.batch_size = cfg.batch_size
         self.horizon = cfg.horizon if latent_plan else cfg.env_horizon                              # helper.py:459-464
+        if self.horizon > cfg.horizon:
+            # only the last cfg.horizon transitions of an episode get priority 0 (helper.py:479-480): a longer window can
+            # start close enough to the end of the buffer to run past it.  The reference then dies with an IndexError in
+            # sample(); the gather kernel would read out of bounds silently, so refuse up front.
+            raise ValueError(f"ReplayBuffer: sampling window {self.horizon} exceeds cfg.horizon {cfg.horizon}")
         self._seed, self._calls = int(seed), 0
         self._ws = torch.empty(int(self._lib.tdmpc_replay_workspace_bytes(self.capacity, self.batch_size)),
                                dtype=torch.uint8, device=self.device)

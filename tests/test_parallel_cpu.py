@@ -21,6 +21,7 @@ def test_shard_range_partitions_exactly():
 
 class _FakePlanner:
     """Stands in for the CUDA planner: the 'action' of problem i is a function of its observation only."""
+    seed = 7
 
     def plan(self, obs, **kw):
         return {"action": torch.stack([obs.sum(1), obs[:, 0] * 2], 1), "metrics": torch.zeros(obs.shape[0], 2)}
@@ -45,6 +46,18 @@ def _worker(rank, world, port, total):
         v0 = m.weight._version
         broadcast_weights(m, src=0)
         assert torch.all(m.weight == 1.0) and torch.all(m.bias == 10.0) and m.weight._version > v0
+        # buffers travel too: the GRU agent's prior MLP folds BatchNorm running statistics into the packed weights
+        bn = torch.nn.BatchNorm1d(5)
+        with torch.no_grad():
+            bn.running_mean.fill_(float(rank + 2)); bn.running_var.fill_(float(3 * rank + 4))
+        vb = bn.running_var._version
+        broadcast_weights(bn, src=0)
+        assert torch.all(bn.running_mean == 2.0) and torch.all(bn.running_var == 4.0) and bn.running_var._version > vb
+        assert bn.num_batches_tracked.dtype == torch.int64                      # integer buffers are left alone
+        # each rank plans its shard with its own Philox key (same key => local problem i repeats rank 0's noise)
+        seeds = [None] * world
+        dist.all_gather_object(seeds, sp.planner.seed)
+        assert len(set(seeds)) == world and sp.base_seed == 7
     finally:
         dist.destroy_process_group()
 
