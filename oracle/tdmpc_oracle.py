@@ -20,6 +20,7 @@ Reference lines followed (all under /root/reference/src):
   algorithm/helper.py:71-96    TruncatedNormal.sample
   algorithm/helper.py:119-133,156-176,197-201   enc / dmlab_enc_norm / mlp / q layer stacks
   algorithm/helper.py:639-652  linear_schedule
+  algorithm/tdmpc_similarity.py:124-200   TDMPCSIM.estimate_value / plan
   algorithm/tdmpc_icem_similarity_mlp.py:115-265   iCEM estimate_value / sampling / plan
   algorithm/tdmpc_icem_similarity_drnn.py:56-59,124-146,168-272  DRNN next / plan
   models/gru_dyna.py:25-29, models/rnns.py:19-29, algorithm/helper.py:179-184  DGruDyna / NormGRUCell / mlp_norm
@@ -248,11 +249,12 @@ def plan_tdmpc(sd, cfg, obs, *, eval_mode, step, t0, prev_mean, std_floor, noise
     std = 2 * torch.ones(H, A)
     if not t0 and prev_mean is not None:
         mean[:-1] = prev_mean[1:]
-    taps = {"values": [], "elite_idx": [], "mean": [], "std": [], "z0": z[0].clone()}
+    taps = {"values": [], "elite_idx": [], "mean": [], "std": [], "z0": z[0].clone(), "actions": [], "mean_in": []}
     for i in range(cfg.iterations):
         actions = torch.clamp(mean.unsqueeze(1) + std.unsqueeze(1) * noise["cem"][i], -1, 1)
         if P > 0:
             actions = torch.cat([actions, pi_actions], dim=1)
+        taps["actions"].append(actions.clone()); taps["mean_in"].append(mean.clone())      # teacher-forcing inputs (tests)
         value, reward_mean = estimate_value(sd, z, actions, H, cfg.discount, cfg.min_std,
                                             noise["term"][i], quant)
         elite_idxs = topk_desc(value.squeeze(1), K)
@@ -269,6 +271,59 @@ def plan_tdmpc(sd, cfg, obs, *, eval_mode, step, t0, prev_mean, std_floor, noise
     taps["pick"] = j
     taps["score"] = score.squeeze(1).clone()
     return a, metrics, mean, taps
+
+
+# ----------------------------------------------------------------------------- TDMPCSIM.plan
+
+
+def plan_tdmpcsim(sd, cfg, obs, *, eval_mode, step, t0, state, noise, quant=False, fine_tuning=False):
+    """TDMPCSIM.plan (tdmpc_similarity.py:135-200) with every random draw injected -- the agent the quadrotor scripts
+    build (train_dyna_episode.py:86,144).  Against TDMPC.plan: returns the bare action; `fine_tuning` disables the
+    seed-step early return (:144); the horizon lives in state['plan_horizon'] and only moves when t0 (:151-152); the
+    number of policy trajectories follows regularization_schedule (:153-154); estimate_value returns G only (:124-133).
+    state: plan_horizon, std, _prev_mean.  noise: as plan_tdmpc with shapes for (plan_horizon, P).  Returns (a, taps)."""
+    if step < cfg.seed_steps and not eval_mode and not fine_tuning:
+        return noise["seed_uniform"].clone(), {}
+    A = cfg.action_dim
+    obs = torch.as_tensor(obs, dtype=torch.float32).unsqueeze(0)
+    horizon = int(min(cfg.horizon, linear_schedule(cfg.horizon_schedule, step)))
+    if horizon != state["plan_horizon"] and t0:
+        state["plan_horizon"] = horizon
+    H = state["plan_horizon"]
+    mix = linear_schedule(cfg.regularization_schedule, step)
+    state["mixture_coef"] = mix
+    N, K = cfg.num_samples, cfg.num_elites
+    P = int(mix * N)
+    if P > 0:
+        pi_actions = torch.empty(H, P, A)
+        z = told_h(sd, obs).repeat(P, 1)
+        for t in range(H):
+            pi_actions[t] = told_pi(sd, z, cfg.min_std, noise["pi"][t], quant)
+            z, _ = told_next(sd, z, pi_actions[t], quant)
+    z = told_h(sd, obs).repeat(N + P, 1)
+    mean = torch.zeros(H, A)
+    std = 2 * torch.ones(H, A)
+    pm = state.get("_prev_mean")
+    if not t0 and pm is not None:
+        mean[:-1] = pm[1:]
+    taps = {"values": [], "elite_idx": [], "mean": [], "std": []}
+    for i in range(cfg.iterations):
+        actions = torch.clamp(mean.unsqueeze(1) + std.unsqueeze(1) * noise["cem"][i], -1, 1)
+        if P > 0:
+            actions = torch.cat([actions, pi_actions], dim=1)
+        value, _ = estimate_value(sd, z, actions, H, cfg.discount, cfg.min_std, noise["term"][i], quant)
+        elite_idxs = topk_desc(value.squeeze(1), K)
+        elite_value, elite_actions = value[elite_idxs], actions[:, elite_idxs]
+        mean, std, score = cem_update(elite_value, elite_actions, mean, cfg.temperature, cfg.momentum, state["std"])
+        taps["values"].append(value.squeeze(1).clone()); taps["elite_idx"].append(elite_idxs.clone())
+        taps["mean"].append(mean.clone()); taps["std"].append(std.clone())
+    j = categorical_pick(score, noise["u"])
+    state["_prev_mean"] = mean
+    a = elite_actions[0, j].clone()
+    if not eval_mode:
+        a = a + std[0] * noise["out"]
+    taps["pick"] = j
+    return a, taps
 
 
 # ----------------------------------------------------------------------------- iCEM (MLP dynamics)
@@ -349,6 +404,7 @@ def plan_icem_mlp(sd, cfg, obs, *, eval_mode, step, t0, state, noise, quant=Fals
             actions = torch.cat([actions_sampled, reused, pi_actions[:, :P]], dim=1)
         else:
             actions = torch.cat([actions_sampled, pi_actions[:, :P]], dim=1)
+        taps.setdefault("actions", []).append(actions.clone()); taps.setdefault("mean_in", []).append(mean.clone())
         value, reward_mean = estimate_value(sd, zs_plan, actions, H, cfg.discount, cfg.min_std,
                                             noise["term"][i], quant)
         elite_idxs = topk_desc(value.squeeze(1), cfg.num_elites)
@@ -365,6 +421,7 @@ def plan_icem_mlp(sd, cfg, obs, *, eval_mode, step, t0, state, noise, quant=Fals
         a = a + std[0] * noise["out"]
     metrics = {"external_reward_mean": reward_mean, "current_std": std[0].mean().item()}
     taps["pick"] = j
+    taps["score"] = score.squeeze(1).clone()
     return a, metrics, taps
 
 
@@ -437,6 +494,7 @@ def plan_icem_drnn(sd, cfg, obs, hidden, *, eval_mode, step, t0, state, noise, q
         if i > 0 and cfg.keep_previous_elites:
             reused = state["_elite_actions"][:, :E]
         actions = torch.cat([actions_sampled, reused, pi_actions[:, :P]], dim=1) if E > 0 else torch.cat([actions_sampled, pi_actions[:, :P]], dim=1)
+        taps.setdefault("actions", []).append(actions.clone()); taps.setdefault("mean_in", []).append(mean.clone())
         value, reward_mean = estimate_value(sd, z.repeat(T, 1), actions, H, cfg.discount, cfg.min_std, noise["term"][i], quant,
                                             hidden=hidden.repeat(T, 1))
         elite_idxs = topk_desc(value.squeeze(1), cfg.num_elites)
@@ -453,6 +511,7 @@ def plan_icem_drnn(sd, cfg, obs, hidden, *, eval_mode, step, t0, state, noise, q
     _, hidden_next, _ = dssm_next(sd, z[0:1], a.unsqueeze(0), hidden, quant)
     metrics = {"external_reward_mean": reward_mean, "current_std": std[0].mean().item()}
     taps["pick"] = j
+    taps["score"] = score.squeeze(1).clone()
     return a, hidden_next, metrics, taps
 
 

@@ -131,6 +131,71 @@ def run_case(name, cfg_name, steps=3, eval_mode=True, seed=0, std_floor=None, **
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def run_sim_case(name, cfg_name, plan, seed=0, eval_mode=True, **over):
+    """TDMPCSIM.plan (tdmpc_similarity.py:135-200), the unmodified reference class -- the agent the quadrotor scripts
+    build.  `plan`: list of (step, t0) calls; chosen so that the horizon schedule moves between calls (plan_horizon must
+    follow it only at t0) and the policy-trajectory count follows regularization_schedule."""
+    from src.algorithm.tdmpc_similarity import TDMPCSIM
+    import src.algorithm.helper as ref_h2
+    cfg = synth.make_cfg(cfg_name, batch_size=8, **over)
+    torch.manual_seed(0)
+    agent = TDMPCSIM(cfg)
+    agent.device = torch.device("cpu")
+    sd = synth.make_told_weights(cfg, seed, enc_ln=bool(cfg.normalize))
+    missing = agent.model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("_predictor") for k in missing.missing_keys) and not missing.unexpected_keys
+    agent.std = 0.1
+    out = {}
+    state = {"plan_horizon": 1, "std": agent.std}
+    for s, (step, t0) in enumerate(plan):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        horizon = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, step)))
+        H = horizon if t0 else agent.plan_horizon
+        P = int(O.linear_schedule(cfg.regularization_schedule, step) * cfg.num_samples)
+        nz = synth.make_noise_hp(cfg, seed * 100 + s, H, P)
+        inj = Injector()
+        for t in range(H):
+            if P > 0:
+                inj.stdn_q.append(nz["pi"][t])
+        for i in range(cfg.iterations):
+            inj.randn_q.append(nz["cem"][i])
+            inj.stdn_q.append(nz["term"][i])
+        inj.randn_q.append(nz["out"])
+        inj.u = nz["u"]
+        ev = agent.estimate_value
+
+        def ev_logged(z, actions, horizon, _ev=ev, _inj=inj):
+            v = _ev(z, actions, horizon)
+            _inj.value_log.append(v.squeeze(1).clone())
+            return v
+
+        agent.estimate_value = ev_logged
+        ref_std = ref_h2._standard_normal
+        with inj:
+            ref_h2._standard_normal = ref_h._standard_normal      # same patched queue for both import names
+            a = agent.plan(obs, eval_mode=eval_mode, step=step, t0=t0)
+        ref_h2._standard_normal = ref_std
+        agent.estimate_value = ev
+        assert isinstance(a, torch.Tensor) and not inj.stdn_q and (eval_mode or not inj.randn_q)
+        out[f"s{s}_action"] = a.numpy().copy()
+        out[f"s{s}_prev_mean"] = agent._prev_mean.numpy().copy()
+        out[f"s{s}_values"] = torch.stack(inj.value_log).numpy()
+        out[f"s{s}_elite_idx"] = torch.stack(inj.topk_log).numpy().astype(np.int32)
+        out[f"s{s}_hp"] = np.array([agent.plan_horizon, P], dtype=np.int64)
+        a_o, taps = O.plan_tdmpcsim(sd, cfg, obs, eval_mode=eval_mode, step=step, t0=t0, state=state, noise=nz)
+        dv = (torch.stack(taps["values"]) - torch.stack(inj.value_log)).abs().max().item()
+        da = (a_o - a).abs().max().item()
+        dm = (state["_prev_mean"] - agent._prev_mean).abs().max().item()
+        print(f"[{name}] call {s} (step {step}, t0 {t0}): H={agent.plan_horizon} P={P} |dvalue|={dv:.3e} |daction|={da:.3e} |dmean|={dm:.3e}")
+        assert dv < 1e-5 and da < 1e-5 and dm < 1e-5 and state["plan_horizon"] == agent.plan_horizon
+    out["plan"] = np.array([[st, int(t)] for st, t in plan], dtype=np.int64)
+    out["meta"] = np.array([seed, len(plan), int(eval_mode)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
+SIM_PLAN = [(9000, True), (9001, False), (17000, False), (17001, True), (17002, False)]     # horizon schedule: 3, 3, (4 ignored), 4, 4
+
+
 def run_icem_case(name, cfg_name, steps=3, seed=0):
     """TdICemSimMlp.plan (tdmpc_icem_similarity_mlp.py:159-265), the unmodified reference class."""
     import colorednoise
@@ -350,6 +415,10 @@ if __name__ == "__main__":
         run_replay_case("replay_small", "small", seed=0)
         run_replay_case("replay_full", "full", seed=1)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sim":
+        run_sim_case("tdmpcsim_tiny", "tiny", SIM_PLAN, seed=8, horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)
+        run_sim_case("tdmpcsim_cfg3", "cfg3", SIM_PLAN[:4], seed=9, eval_mode=False)
+        sys.exit(0)
     check_choice_replica()
     run_case("tdmpc_tiny", "tiny", steps=3)
     run_case("tdmpc_tiny_train", "tiny", steps=2, eval_mode=False, seed=3, std_floor=0.1)
@@ -362,4 +431,6 @@ if __name__ == "__main__":
     run_drnn_case("drnn_cfg5", "cfg5", steps=2, seed=7)
     run_replay_case("replay_small", "small", seed=0)
     run_replay_case("replay_full", "full", seed=1)
+    run_sim_case("tdmpcsim_tiny", "tiny", SIM_PLAN, seed=8, horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)
+    run_sim_case("tdmpcsim_cfg3", "cfg3", SIM_PLAN[:4], seed=9, eval_mode=False)
     print("golden fixtures written to", HERE)

@@ -39,6 +39,7 @@ def install():
     _mod("rlpyt.utils.tensor", infer_leading_dims=_Dummy, restore_leading_dims=_Dummy)
     _mod("rlpyt.ul.algos"); _mod("rlpyt.ul.algos.utils")
     _mod("rlpyt.ul.algos.utils.optim_factory", create_optimizer=lambda *a, **k: None)
+    _mod("rlpyt.ul.algos.utils.scheduler_factory", create_scheduler=lambda *a, **k: (None, None))     # tdmpc_similarity.py:8
 
     class RunningMeanStd:
         def __init__(self, *a, **k):

@@ -145,6 +145,22 @@ def make_noise(cfg, seed=0, step=10 ** 6, batch=None):
     return n
 
 
+def make_noise_hp(cfg, seed, H, P):
+    """make_noise with the plan horizon and the number of policy trajectories given explicitly: TDMPCSIM takes them from
+    `plan_horizon` (moved only at an episode start) and `regularization_schedule` (tdmpc_similarity.py:150-154)."""
+    rs = np.random.RandomState(2500 + seed)
+    A, I, N = cfg.action_dim, cfg.iterations, cfg.num_samples
+    n = {
+        "pi": _t(rs.standard_normal((H, P, A))),
+        "cem": _t(rs.standard_normal((I, H, N, A))),
+        "term": _t(rs.standard_normal((I, N + P, A))),
+        "out": _t(rs.standard_normal((A,))),
+        "seed_uniform": _t(rs.uniform(-1, 1, (A,))),
+    }
+    n["u"] = float(rs.random_sample())
+    return n
+
+
 def make_icem_noise(cfg, seed, sizes, H, have_elites, single_beta=False):
     """Draws of one TdICemSimMlp.plan call in consumption order (tdmpc_icem_similarity_mlp.py:139-157,
     188-239): per iteration white randn + two colored blocks (series of length cfg.horizon, truncated to

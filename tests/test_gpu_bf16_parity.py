@@ -1,0 +1,264 @@
+"""bf16-operand mode (the tcgen05 path every headline number uses) against the oracle run with the SAME quantised
+operands, at the tolerance north_star / BASELINE.md section 5 state: per iteration, TEACHER-FORCED -- iteration i of the
+CUDA planner sees the oracle's own action rows, incoming mean and std floor -- so one legitimate near-tie elite flip
+cannot compound:
+
+  * values: median, p90 and max relative error gated at ~10x what the kernel achieves (see GATES);
+  * wherever the K-th / (K+1)-th value gap resolves the elite set, the sets must be IDENTICAL and then the new mean, the
+    new std and (last iteration) the picked action must agree to 1e-3;
+  * the Q-head LayerNorm / tanh path on its own, with non-zero head weights (the integer-exact known-answer model of
+    test_gpu_parity.py zeroes `_Q*.6`, so it cannot see that path).
+
+Everything goes through the C ABI (Planner.estimate_value / select_update -> tdmpc_estimate_value[_drnn] /
+tdmpc_select_update)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tdmpc_oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+# Statistical gates on the per-trajectory relative value error |v_cuda - v_oracle| / max|v_oracle| (same bf16 operands on
+# both sides).  Measured on B200 (profiles/r2_bf16_parity_errors.txt): median 2e-7 .. 1e-6 and p90 below 1e-5 for every
+# configuration; a single flipped bf16 rounding of an activation (fp32 summation order differs from MKL's) moves an
+# individual trajectory by up to ~1e-2 of max|value|, which is why the max is gated against the mode's own quantisation
+# noise (quantised oracle vs fp32 oracle) and not against 1e-3.
+GATE_MEDIAN = 1e-5
+GATE_P90 = 1e-3
+TOL_DIST = 1e-3          # north_star: action / mean / std within 1e-3 given identical elite sets
+
+
+def _gu():
+    from tests import gpu_util
+    return gpu_util
+
+
+def _value_gates(err, qn, label):
+    med, p90, mx = err.median().item(), err.quantile(0.9).item(), err.max().item()
+    print(f"{label}: value rel err median {med:.2e} p90 {p90:.2e} max {mx:.2e}" + (f" | quantisation noise max {qn:.2e}" if qn is not None else ""))
+    assert med <= GATE_MEDIAN, f"{label}: median {med:.3e}"
+    assert p90 <= GATE_P90, f"{label}: p90 {p90:.3e}"
+    if qn is not None:
+        assert mx <= max(qn, 5e-3), f"{label}: max {mx:.3e} above the mode's quantisation noise {qn:.3e}"
+    return med, p90, mx
+
+
+def _teacher_forced_iterations(pl, cfg, z0, taps_o, term_noise, std_floor, hidden=None, u=None, a_o=None, eval_mode=True, label=""):
+    """For every CEM iteration: CUDA values of the oracle's action rows, then the CUDA selection / distribution update from
+    the CUDA values and the oracle's incoming mean.  Returns (#iterations whose elite set was resolvable and identical,
+    list of per-iteration error summaries)."""
+    K, I = cfg.num_elites, cfg.iterations
+    resolved, stats = 0, []
+    for i in range(I):
+        acts = taps_o["actions"][i]                       # [H, T, A] exactly what the oracle evaluated
+        H, T, A = acts.shape
+        v_o = taps_o["values"][i]
+        kw = dict(discount=cfg.discount, min_std=cfg.min_std, noise_term=term_noise[i].unsqueeze(0))
+        if hidden is not None:
+            kw["hidden"] = hidden.cuda().repeat(1, 1)
+        a_dev = acts.permute(1, 0, 2).unsqueeze(0).contiguous().cuda()
+        v_g, _ = pl.estimate_value(z0.cuda(), a_dev, **kw)
+        mean_g = taps_o["mean_in"][i].unsqueeze(0).contiguous().cuda()
+        std_g = torch.zeros_like(mean_g)
+        idx_g, score_g = pl.select_update(v_g, a_dev, mean_g, std_g, num_elites=K, temperature=cfg.temperature,
+                                          momentum=cfg.momentum, std_floor=std_floor)
+        torch.cuda.synchronize()
+        scale = v_o.abs().max().item()
+        err = (v_g[0].cpu() - v_o).abs() / scale
+        stats.append((err.median().item(), err.quantile(0.9).item(), err.max().item()))
+        # is the elite set resolvable?  K-th / (K+1)-th gap of the oracle's values against the error actually seen near it
+        srt, order = torch.sort(v_o, descending=True)
+        gap = (srt[K - 1] - srt[K]).item()
+        near = err[order[max(0, K - 4):K + 4]].max().item() * scale
+        e_o, e_g = set(taps_o["elite_idx"][i].tolist()), set(idx_g[0].cpu().tolist())
+        if gap > 2.5 * near and gap > 1e-6 * scale:
+            assert e_o == e_g, f"{label} iter {i}: elite sets differ although the K/K+1 gap {gap:.3e} resolves them (err {near:.3e})"
+        if e_o != e_g:
+            continue                                      # a legitimate near-tie flip: nothing further to compare here
+        resolved += 1
+        m_o, s_o = taps_o["mean"][i], taps_o["std"][i]
+        dm = (mean_g[0].cpu() - m_o).abs().max().item()
+        ds = ((std_g[0].cpu() - s_o).abs() / s_o.abs().clamp_min(1e-6)).max().item()
+        assert dm <= TOL_DIST, f"{label} iter {i}: |dmean| {dm:.3e}"
+        assert ds <= TOL_DIST, f"{label} iter {i}: std rel err {ds:.3e}"
+        if i == I - 1 and u is not None:
+            # categorical pick on the CUDA scores with the oracle's uniform (numpy's inverse-CDF walk), then the action
+            j_g = O.categorical_pick(score_g[0].cpu().unsqueeze(1), u)
+            el_g = acts[:, idx_g[0].cpu().long()]                               # [H, K, A] in the CUDA elite order
+            a_g = el_g[0, j_g].clone()
+            cdf = np.cumsum(taps_o["score"].numpy().astype(np.float64)); cdf /= cdf[-1]
+            if np.abs(cdf - u).min() > 1e-3:                                    # u is not sitting on a cdf step
+                assert idx_g[0, j_g].item() == taps_o["elite_idx"][i][taps_o["pick"]].item(), f"{label}: picked elite differs"
+                if eval_mode:
+                    assert (a_g - a_o).abs().max().item() <= TOL_DIST
+    return resolved, stats
+
+
+# ------------------------------------------------------------------------------------------------- TDMPC.plan
+@pytest.mark.parametrize("cfg_name,seed", [("cfg1", 0), ("cfg3", 1), ("cfg2", 4), ("tiny", 0)])
+def test_bf16_teacher_forced_plan(cfg_name, seed):
+    """cfg1 (cartpole), cfg3 (quadrotor), cfg2 (dog-run: L = 100, A = 38, I = 8): two planning steps (the second one
+    warm-started from the oracle's `_prev_mean`), every iteration teacher-forced."""
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    prev_o = None
+    total_resolved = 0
+    for s in range(2):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise(cfg, seed * 100 + s)
+        a_o, m_o, mean_o, taps_o = gu.oracle_plan(sd, cfg, obs, nz, t0=(s == 0), prev_mean=prev_o, quant=True)
+        z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
+        zg = pl.encode(torch.from_numpy(obs).cuda().unsqueeze(0))
+        np.testing.assert_allclose(zg.cpu().numpy(), z0.numpy(), rtol=1e-5, atol=1e-5)
+        res, stats = _teacher_forced_iterations(pl, cfg, z0, taps_o, nz["term"], cfg.min_std, u=nz["u"], a_o=a_o,
+                                                label=f"{cfg_name} step {s}")
+        total_resolved += res
+        allv = torch.tensor(stats)
+        print(f"bf16 teacher-forced {cfg_name} step {s}: per-iteration median {allv[:, 0].max().item():.2e} p90 {allv[:, 1].max().item():.2e} "
+              f"max {allv[:, 2].max().item():.2e}; elite sets identical in {res}/{cfg.iterations} iterations")
+        assert allv[:, 0].max().item() <= GATE_MEDIAN and allv[:, 1].max().item() <= GATE_P90
+        prev_o = mean_o
+    assert total_resolved >= cfg.iterations           # the mean / std / action comparison is not vacuous
+
+
+@pytest.mark.parametrize("cfg_name,seed", [("tiny", 0), ("cfg1", 1), ("cfg3", 2), ("cfg2s", 3), ("cfg2", 4)])
+def test_bf16_value_error_distribution(cfg_name, seed):
+    """estimate_value on random action rows: the tightened statistical gate (median 1e-5, p90 1e-3, max below the mode's
+    own quantisation noise) plus the policy-rollout actions."""
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    H, N, P, T = synth.plan_dims(cfg)
+    rs = np.random.RandomState(seed + 7)
+    z0 = O.told_h(sd, torch.from_numpy(synth.make_obs(cfg, seed)).unsqueeze(0))
+    eps_pi = torch.from_numpy(rs.standard_normal((H, P, cfg.action_dim)).astype(np.float32))
+    pi_o = torch.empty(H, P, cfg.action_dim)
+    z = z0.repeat(P, 1)
+    for t in range(H):
+        pi_o[t] = O.told_pi(sd, z, cfg.min_std, eps_pi[t], True)
+        z, _ = O.told_next(sd, z, pi_o[t], True)
+    pi_g = pl.pi_rollout(z0.cuda(), P, H, min_std=cfg.min_std, noise_pi=eps_pi.unsqueeze(0))
+    err_pi = (pi_g[0].permute(1, 0, 2).cpu() - pi_o).abs().flatten()
+    actions = torch.from_numpy(rs.uniform(-1, 1, (H, T, cfg.action_dim)).astype(np.float32))
+    eps_t = torch.from_numpy(rs.standard_normal((T, cfg.action_dim)).astype(np.float32))
+    v_o, _ = O.estimate_value(sd, z0.repeat(T, 1), actions, H, cfg.discount, cfg.min_std, eps_t, True)
+    v_f, _ = O.estimate_value(sd, z0.repeat(T, 1), actions, H, cfg.discount, cfg.min_std, eps_t, False)
+    v_g, _ = pl.estimate_value(z0.cuda(), actions.permute(1, 0, 2).unsqueeze(0).contiguous(), discount=cfg.discount,
+                               min_std=cfg.min_std, noise_term=eps_t.unsqueeze(0))
+    torch.cuda.synchronize()
+    scale = v_o.abs().max().item()
+    err = (v_g[0].cpu() - v_o.squeeze(1)).abs() / scale
+    qn = ((v_f - v_o).abs().squeeze(1) / scale).max().item()
+    _value_gates(err, qn, f"bf16 {cfg_name}")
+    print(f"bf16 {cfg_name}: pi action abs err median {err_pi.median().item():.2e} p90 {err_pi.quantile(0.9).item():.2e} max {err_pi.max().item():.2e}")
+    assert err_pi.median().item() <= GATE_MEDIAN and err_pi.quantile(0.9).item() <= GATE_P90
+
+
+# ------------------------------------------------------------------------------------------------- Q heads alone
+def _q_only_model(cfg, seed):
+    """Integer-exact dynamics (every dot product exact in fp32, ELU = identity: test_gpu_parity._integer_model), reward
+    head zero, policy and Q heads as synth draws them (non-zero `_Q*.6`): the trajectory value is gamma^H *
+    min(Q1, Q2)(z_H, pi(z_H)) with z_H bit-identical on both sides, so the error is that of the policy + Q-head path alone
+    (Linear -> LayerNorm -> tanh -> Linear -> LayerNorm -> ELU -> fp32 dot)."""
+    from tests.test_gpu_parity import _integer_model
+    sd = _integer_model(cfg, seed)
+    fresh = synth.make_told_weights(cfg, seed)
+    for q in ("_Q1", "_Q2"):
+        sd[q + ".6.weight"], sd[q + ".6.bias"] = fresh[q + ".6.weight"].clone(), fresh[q + ".6.bias"].clone()
+    sd["_reward.4.weight"] = torch.zeros_like(sd["_reward.4.weight"])
+    sd["_reward.4.bias"] = torch.zeros_like(sd["_reward.4.bias"])
+    return sd
+
+
+@pytest.mark.parametrize("cfg_name", ["cfg3", "cfg2", "tiny"])
+def test_bf16_q_head_path(cfg_name):
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = _q_only_model(cfg, 11)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    H, L, A = 2, cfg.latent_dim, cfg.action_dim
+    rs = np.random.RandomState(5)
+    B, T = 2, 700                                                         # ragged tiles, tiles straddling problems
+    z0 = torch.from_numpy(rs.randint(-2, 3, (B, L)).astype(np.float32))
+    actions = torch.from_numpy(rs.randint(-1, 2, (B, T, H, A)).astype(np.float32))
+    eps = torch.from_numpy(rs.standard_normal((B, T, A)).astype(np.float32))
+    v_g, r_g = pl.estimate_value(z0, actions, discount=cfg.discount, min_std=cfg.min_std, noise_term=eps)
+    torch.cuda.synchronize()
+    errs = []
+    for b in range(B):
+        v_o, _ = O.estimate_value(sd, z0[b:b + 1].repeat(T, 1), actions[b].permute(1, 0, 2), H, cfg.discount, cfg.min_std, eps[b], quant=True)
+        assert v_o.abs().max() > 1e-2 and v_o.std() > 1e-3                # the Q heads really produce the value
+        errs.append((v_g[b].cpu() - v_o.squeeze(1)).abs() / v_o.abs().max())
+    err = torch.cat(errs)
+    print(f"bf16 Q-head path {cfg_name}: rel err median {err.median().item():.2e} p90 {err.quantile(0.9).item():.2e} "
+          f"p99 {err.quantile(0.99).item():.2e} max {err.max().item():.2e}")
+    assert (r_g == 0).all()
+    assert err.median().item() <= GATE_MEDIAN and err.quantile(0.9).item() <= 1e-4 and err.quantile(0.99).item() <= 5e-3
+
+
+# ------------------------------------------------------------------------------------------------- iCEM (cfg4)
+@pytest.mark.parametrize("cfg_name,seed", [("cfg4", 5), ("tiny_icem", 4)])
+def test_bf16_teacher_forced_icem(cfg_name, seed):
+    """TdICemSimMlp.plan's iterations (sample-count decay, carried + shifted elites, best-a row) on the tcgen05 path:
+    two planning steps, every iteration teacher-forced with the oracle's rows."""
+    gu = _gu()
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_told_weights(cfg, seed, enc_ln=True)
+    pl = gu.make_planner(cfg, sd, "bf16")
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    total = 0
+    for s in range(2):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_sizes(cfg, O.linear_schedule(cfg.regularization_schedule, 10 ** 6), have)
+        H = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, 10 ** 6)))
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have)
+        a_o, m_o, taps_o = O.plan_icem_mlp(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(s == 0), state=state, noise=nz, quant=True)
+        z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
+        res, stats = _teacher_forced_iterations(pl, cfg, z0, taps_o, nz["term"], cfg.min_std, u=nz["u"], a_o=a_o,
+                                                label=f"icem {cfg_name} step {s}")
+        allv = torch.tensor(stats)
+        print(f"bf16 teacher-forced iCEM {cfg_name} step {s}: median {allv[:, 0].max().item():.2e} p90 {allv[:, 1].max().item():.2e} "
+              f"max {allv[:, 2].max().item():.2e}; elite sets identical in {res}/{cfg.iterations} iterations")
+        assert allv[:, 0].max().item() <= GATE_MEDIAN and allv[:, 1].max().item() <= GATE_P90
+        total += res
+    assert total >= cfg.iterations
+
+
+# ------------------------------------------------------------------------------------------------- DRNN (cfg5)
+@pytest.mark.parametrize("cfg_name,seed", [("cfg5", 7), ("tiny_drnn", 6)])
+def test_bf16_teacher_forced_drnn(cfg_name, seed):
+    """TdICemSimDssm.plan's iterations through the GRU latent dynamics (rollout_tc_kernel<true>): two planning steps with a
+    non-zero hidden state on the second, every iteration teacher-forced."""
+    from tdmpc_b200 import Planner
+    cfg = synth.make_cfg(cfg_name)
+    sd = synth.make_drnn_weights(cfg, seed)
+    pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, enc_layernorm=True, precision="bf16",
+                 dynamics="drnn", hidden_dim=cfg.hidden_dim)
+    pl.sync_weights({k: v.cuda() for k, v in sd.items()})
+    state = {"plan_horizon": 1, "std": cfg.min_std}
+    hidden_o = torch.zeros(1, cfg.hidden_dim)
+    total = 0
+    for s in range(2):
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        t0 = s == 0
+        have = state.get("_elite_actions") is not None
+        sizes = O.icem_drnn_sizes(cfg, O.linear_schedule(cfg.regularization_schedule, 10 ** 6), have, t0)
+        H = int(min(cfg.horizon, O.linear_schedule(cfg.horizon_schedule, 10 ** 6)))
+        nz = synth.make_icem_noise(cfg, seed * 100 + s, sizes, H, have and not t0, single_beta=True)
+        hidden_in = hidden_o.clone()
+        a_o, hidden_o, m_o, taps_o = O.plan_icem_drnn(sd, cfg, obs, hidden_o, eval_mode=True, step=10 ** 6, t0=t0, state=state, noise=nz, quant=True)
+        z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
+        res, stats = _teacher_forced_iterations(pl, cfg, z0, taps_o, nz["term"], cfg.min_std, hidden=hidden_in, u=nz["u"], a_o=a_o,
+                                                label=f"drnn {cfg_name} step {s}")
+        allv = torch.tensor(stats)
+        print(f"bf16 teacher-forced DRNN {cfg_name} step {s}: median {allv[:, 0].max().item():.2e} p90 {allv[:, 1].max().item():.2e} "
+              f"max {allv[:, 2].max().item():.2e}; elite sets identical in {res}/{cfg.iterations} iterations")
+        assert allv[:, 0].max().item() <= GATE_MEDIAN and allv[:, 1].max().item() <= GATE_P90
+        total += res
+    assert total >= cfg.iterations

@@ -977,3 +977,101 @@ def test_compact_last_kblock_is_bit_identical(cfg_name, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(a["taps"]["values"], b["taps"]["values"]) and torch.equal(a["action"], b["action"])
     assert torch.equal(a["taps"]["elite_idx"], b["taps"]["elite_idx"]) and torch.equal(a["prev_mean"], b["prev_mean"])
+
+
+# ------------------------------------------------------------------------------------------------- TDMPCSIM
+@pytest.mark.parametrize("name,cfg_name,over", [("tdmpcsim_tiny", "tiny", dict(horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)),
+                                                 ("tdmpcsim_cfg3", "cfg3", {})])
+def test_tdmpcsim_dropin_matches_reference_golden(golden_dir, name, cfg_name, over):
+    """The TDMPCSIM drop-in (the agent the quadrotor scripts build: train_dyna_episode.py:86,144) in fp32 mode against what the
+    unmodified TDMPCSIM.plan (tdmpc_similarity.py:135-200) produced: bare action return, plan_horizon that moves only at an
+    episode start, policy-trajectory count from regularization_schedule, `_prev_mean` side effect, exploration noise."""
+    from tdmpc_b200 import TDMPCSIM
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, ncalls, eval_mode = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name, batch_size=8, device="cuda", precision="fp32", **over)
+    sd = synth.make_told_weights(cfg, seed, enc_ln=bool(cfg.normalize))
+    agent = TDMPCSIM(cfg)
+    missing = agent.model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("_predictor") for k in missing.missing_keys) and not missing.unexpected_keys
+    agent.std = 0.1
+    K = cfg.num_elites
+    for s, (step, t0) in enumerate(g["plan"].tolist()):
+        H, P = [int(x) for x in g[f"s{s}_hp"]]
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise_hp(cfg, seed * 100 + s, H, P)
+        agent._inject_noise = {"pi": nz["pi"].unsqueeze(0).cuda(), "cem": nz["cem"].unsqueeze(0).cuda(), "term": nz["term"].unsqueeze(0).cuda(),
+                               "out": nz["out"].unsqueeze(0).cuda(), "u": np.array([nz["u"]])}
+        agent._want_taps = True
+        a = agent.plan(obs, eval_mode=bool(eval_mode), step=step, t0=bool(t0))
+        torch.cuda.synchronize()
+        assert isinstance(a, torch.Tensor) and a.shape == (cfg.action_dim,) and a.is_cuda          # bare tensor, no metrics
+        assert agent.plan_horizon == H and int(agent.mixture_coef * cfg.num_samples) == P
+        ref_vals = g[f"s{s}_values"]
+        scale = np.abs(ref_vals).max()
+        same = True
+        for i in range(cfg.iterations):
+            v = agent._last_taps["values"][i, 0, :ref_vals.shape[1]].cpu().numpy()
+            assert np.abs(v - ref_vals[i]).max() <= 2e-5 * scale, (s, i)
+            srt = np.sort(ref_vals[i])[::-1]
+            if srt[K - 1] - srt[K] > 1e-4 * scale:
+                assert set(agent._last_taps["elite_idx"][i, 0].cpu().tolist()) == set(g[f"s{s}_elite_idx"][i].tolist())
+            else:
+                same = False
+                break
+        if not same:
+            agent._prev_mean = torch.from_numpy(g[f"s{s}_prev_mean"]).cuda()      # teacher-force the carried state and go on
+            continue
+        np.testing.assert_allclose(agent._prev_mean.cpu().numpy(), g[f"s{s}_prev_mean"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(a.cpu().numpy(), g[f"s{s}_action"], rtol=0, atol=1e-4)
+    # seed steps: uniform action unless fine_tuning (tdmpc_similarity.py:144-145)
+    n_before = agent._planner.launch_count
+    a = agent.plan(obs, eval_mode=False, step=0, t0=True)
+    assert agent._planner.launch_count == n_before and a.abs().max() <= 1.0
+    agent._inject_noise = None
+    a = agent.plan(obs, eval_mode=False, step=0, t0=True, fine_tuning=True)
+    torch.cuda.synchronize()
+    assert agent._planner.launch_count > n_before and torch.isfinite(a).all()
+
+
+def test_accelerate_on_reference_style_agents():
+    """`accelerate()` (INTEGRATION.md option 1) on attribute-compatible stand-ins of the reference's four agent classes:
+    dispatch, a real plan through the C ABI, return arity, side effects -- and that the planner follows in-place weight
+    updates of the agent's own nn.Module."""
+    from tdmpc_b200 import accelerate, agent_kind
+    from tests.test_dropin_cpu import _agent
+    for kind in ("tdmpc", "sim", "icem", "drnn"):
+        over = dict(normalize=True, horizon=5, horizon_schedule="linear(2, 5, 25000, 0)") if kind == "sim" else {}
+        ag = _agent(kind, **over)
+        ag.model = ag.model.cuda().eval()
+        ag.device = torch.device("cuda", torch.cuda.current_device())
+        with torch.no_grad():                         # the reference zero-initialises these heads (tdmpc.py:21-23): all values would tie
+            for m in (ag.model._reward, ag.model._Q1, ag.model._Q2):
+                m[-1].weight.normal_(0, 0.05)
+        accelerate(ag, precision="bf16" if kind != "drnn" else "fp32")
+        assert agent_kind(ag) == kind
+        obs = synth.make_obs(ag.cfg, 3)
+        A = ag.cfg.action_dim
+        if kind == "drnn":
+            hid = torch.zeros(1, ag.cfg.hidden_dim, device="cuda")
+            for t in range(3):
+                a, hid, m = ag.plan(obs, hid, eval_mode=(t > 0), step=10 ** 6, t0=(t == 0))
+                assert a.shape == (A,) and tuple(hid.shape) == (1, ag.cfg.hidden_dim) and torch.isfinite(hid).all() and m["current_std"] > 0
+        elif kind == "sim":
+            for t in range(3):
+                a = ag.plan(obs, eval_mode=(t > 0), step=10 ** 6, t0=(t == 0))
+                assert isinstance(a, torch.Tensor) and a.shape == (A,) and torch.isfinite(a).all()
+            assert tuple(ag._prev_mean.shape) == (ag.plan_horizon, A)
+        else:
+            for t in range(3):
+                a, m = ag.plan(obs, eval_mode=(t > 0), step=10 ** 6, t0=(t == 0))
+                assert a.shape == (A,) and torch.isfinite(a).all() and m["current_std"] > 0
+            assert tuple(ag._prev_mean.shape)[1] == A
+        r0 = ag._planner.launch_count
+        with torch.no_grad():
+            ag.model._pi[-1].bias.add_(0.1)           # what update() does: in place -> the next plan re-packs
+        if kind == "drnn":
+            ag.plan(obs, hid, eval_mode=True, step=10 ** 6, t0=False)
+        else:
+            ag.plan(obs, eval_mode=True, step=10 ** 6, t0=False)
+        assert ag._planner._wver is not None and ag._planner.launch_count > r0

@@ -169,3 +169,33 @@ def test_colored_noise_matrix_is_the_generator():
     m = color_matrices(10, 7, 2.5)
     assert m.shape == (3, 10, 10) and np.all(m[2, 7:] == 0) and np.all(m[2, :, 7:] == 0)
     assert mix_split(1024) == (341, 342, 341) and mix_split(819) == (273, 273, 273) and mix_split(335) == (111, 112, 112)
+
+
+SIM_CASES = [("tdmpcsim_tiny", "tiny", dict(horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)),
+             ("tdmpcsim_cfg3", "cfg3", {})]
+
+
+@pytest.mark.parametrize("name,cfg_name,over", SIM_CASES)
+def test_oracle_matches_tdmpcsim_fixture(golden_dir, name, cfg_name, over):
+    """plan_tdmpcsim against what the unmodified TDMPCSIM.plan (tdmpc_similarity.py:135-200) produced: plan_horizon moves
+    only at t0, P follows regularization_schedule, bare action return, exploration noise (cfg3 case)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, ncalls, eval_mode = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name, batch_size=8, **over)
+    sd = synth.make_told_weights(cfg, seed, enc_ln=bool(cfg.normalize))
+    state = {"plan_horizon": 1, "std": 0.1}
+    for s, (step, t0) in enumerate(g["plan"].tolist()):
+        H, P = [int(x) for x in g[f"s{s}_hp"]]
+        obs = synth.make_obs(cfg, seed * 100 + s)
+        nz = synth.make_noise_hp(cfg, seed * 100 + s, H, P)
+        a, taps = O.plan_tdmpcsim(sd, cfg, obs, eval_mode=bool(eval_mode), step=step, t0=bool(t0), state=state, noise=nz)
+        assert state["plan_horizon"] == H and int(state["mixture_coef"] * cfg.num_samples) == P
+        vals, ref_vals = torch.stack(taps["values"]).numpy(), g[f"s{s}_values"]
+        scale = np.abs(ref_vals).max()
+        assert np.abs(vals - ref_vals).max() <= TOL * scale
+        for i in range(cfg.iterations):
+            srt = np.sort(ref_vals[i])[::-1]
+            if srt[cfg.num_elites - 1] - srt[cfg.num_elites] > 4 * TOL * scale:
+                assert set(taps["elite_idx"][i].tolist()) == set(g[f"s{s}_elite_idx"][i].tolist())
+        np.testing.assert_allclose(state["_prev_mean"].numpy(), g[f"s{s}_prev_mean"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(a.numpy(), g[f"s{s}_action"], rtol=0, atol=1e-4)
