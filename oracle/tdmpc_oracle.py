@@ -27,7 +27,7 @@ Reference lines followed (all under /root/reference/src):
 
 `quant=True` selects the "bf16-weight / fp32-accumulate" numerics of the tensor-core
 kernel: every operand of a tensor-core GEMM (the Linear layers of dynamics, reward, pi,
-Q1, Q2 with out_features > 1, GRU gate GEMMs, prior MLP) is rounded to bf16
+Q1, Q2 except the scalar reward / Q heads, GRU gate GEMMs, prior MLP) is rounded to bf16
 (round-to-nearest-even) -- weights AND layer inputs -- products are accumulated in fp32,
 biases / LayerNorm / activations / the N=1 reward and Q heads / the encoder stay fp32.
 """
@@ -115,7 +115,9 @@ def told_next(sd, z, a, quant=False):
 def told_pi(sd, z, std=0.0, eps=None, quant=False):
     """TOLD.pi (tdmpc.py:39-45) + TruncatedNormal.sample(clip=0.3) (helper.py:86-96).
     `eps` is the standard-normal draw the reference takes from _standard_normal."""
-    mu = torch.tanh(mlp3(sd, "_pi", z, quant))
+    # the policy head is a tensor-core GEMM in the kernel for every action_dim (N padded to 16), so its operands are
+    # quantised even when action_dim == 1 (cartpole, BASELINE configs[0]); only the reward / Q heads are fp32 dot products
+    mu = torch.tanh(mlp3(sd, "_pi", z, quant, head_quant=quant))
     if std > 0:
         e = eps * (torch.ones_like(mu) * std)
         e = torch.clamp(e, -0.3, 0.3)

@@ -74,14 +74,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
   const float e = ex2_approx(x * 2.8853900817779268f);       // exp(2x)
   return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
-// tanh of a value that is rounded to bf16 right afterwards (Q-head layer 1 -> operand of layer 2): one MUFU instead of two.
-// tanh.approx.f32 is good to 2^-11 relative, a quarter of the bf16 rounding step that follows; measured effect on the plan
-// values: 4e-5 median relative (gate: 1e-3).  -DTDMPC_TANH_PRECISE restores the two-MUFU form.
+// tanh of the Q-head layer-1 activation (rounded to bf16 right afterwards).  The one-MUFU tanh.approx.f32 (2^-11 relative) was
+// measured 3 % faster on the whole kernel, but it is a DENSE perturbation -- one activation in eight changes its bf16
+// rounding -- that lifts the median value error against the quantised oracle from 4e-7 to 1.5e-5 at dog-run dims
+// (profiles/r2_bf16_error_probe.txt).  Parity comes first: the two-MUFU form is the default, -DTDMPC_TANH_APPROX selects
+// the fast one.
 __device__ __forceinline__ float tanh_bf16(float x) {
-#ifdef TDMPC_TANH_PRECISE
-  return tanh_fast(x);
-#else
+#ifdef TDMPC_TANH_APPROX
   float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+  return tanh_fast(x);
 #endif
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
