@@ -57,7 +57,8 @@ struct KParams {
   int producers;               // producer threads (warps 0, 2, 3); divides the ring depth
   int debug;                   // experiments only (TDMPC_TC_DEBUG; wrong results): bit0 = producers skip the weight copies, bit1 = accumulators
                                //   are released after the activation math, bit2 = the activation math of the MLP layers is skipped
-  unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py)
+  unsigned long long* trace;   // optional [3 roles][MAX_JOBS][2] clock64 stamps of block 0's third tile (tools/trace_rollout.py), then 128
+                               //   end-of-tile clock64 + 128 globaltimer stamps of block 0, then per block {clock64 start, end, tiles, smid}
   // The job program again, in the kernel-parameter (constant) bank: the MMA warp reads it with uniform loads, which keeps its
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
   uint32_t jw[MAX_JOBS];
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   if (*tmem_slot != 0) asm volatile("trap;");   // all 512 columns of the SM are ours: the base is 0, so TMEM addresses are immediates
   constexpr uint32_t tmem = 0;
   const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long t_start = kp.trace ? clock64() : 0;
 
   if (warp < 4) {
     // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
@@ -1153,6 +1155,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 
   tcgen05_fence_before();
   __syncthreads();
+  if (kp.trace && threadIdx.x == 128 && blockIdx.x < 256) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* bs = kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * blockIdx.x;
+    bs[0] = (unsigned long long)t_start; bs[1] = (unsigned long long)clock64(); bs[2] = (unsigned long long)my_tiles; bs[3] = smid;
+  }
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
@@ -1496,7 +1504,7 @@ void tc_release_host(TcModel* m) {
 
 static unsigned long long* g_tc_trace = nullptr;
 void tc_set_trace(unsigned long long* dev_buf) { g_tc_trace = dev_buf; }
-int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256; }      // + end-of-tile stamps of block 0's first 128 tiles
+int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256 + 4 * 256; }      // + end-of-tile stamps of block 0's first 128 tiles + per-block stats
 
 int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st) {
   if (p.H < 1 || p.H > TDMPC_MAX_H) return -1;

@@ -24,6 +24,7 @@ lib.tdmpc_debug_set_trace(C.c_void_p(buf.data_ptr()))
 pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
 torch.cuda.synchronize(); lib.tdmpc_debug_set_trace(None)
 raw = buf.cpu().numpy()
+blk = raw[-1024:].reshape(256, 4); raw = raw[:-1024]
 ends = raw[-256:-128]; ns = raw[-128:][ends > 0]; ends = ends[ends > 0]
 tr = raw[:-256].reshape(3, -1, 2)
 # the job list the kernel walked (word layout: tc_model.cuh)
@@ -43,3 +44,10 @@ for j, (ty, chn, c, t) in enumerate(jobs):
 print("tile total cycles:", tr[:, :len(jobs), 1].max() - t0)
 print("tile periods of block 0 (cycles):", " ".join(str(int(x)) for x in np.diff(ends)))
 if len(ends) > 1: print(f"SM clock from globaltimer: {(ends[-1] - ends[0]) / max(1, ns[-1] - ns[0]) * 1e3:.0f} MHz over {len(ends) - 1} tiles")
+used = blk[blk[:, 2] > 0]
+if len(used):
+    per = (used[:, 1] - used[:, 0]) / used[:, 2]
+    print(f"per-block cycles per tile over {len(used)} blocks: min {per.min():.0f} median {np.median(per):.0f} max {per.max():.0f}; "
+          f"block cycles min {(used[:, 1] - used[:, 0]).min()} max {(used[:, 1] - used[:, 0]).max()}; tiles per block {used[:, 2].min()}..{used[:, 2].max()}")
+    slow = np.argsort(-per)[:8]
+    print("slowest blocks (block, smid, cycles/tile):", [(int(i), int(used[i, 3]), int(per[i])) for i in slow])
