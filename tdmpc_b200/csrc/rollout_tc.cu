@@ -63,6 +63,7 @@ struct KParams {
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
   uint32_t jw[MAX_JOBS];
   int one;                     // always 1 (an opaque branch condition: tc_prims.cuh, tmem_drain_aux)
+  unsigned int* tile_counter;  // dynamic tile scheduler: tickets handed out so far in this launch (zero between launches)
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter space");
 
@@ -174,7 +175,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint64_t* r_ready = x_full + 1;
   uint64_t* u_ready = r_ready + 1;
   uint64_t* d3_full = u_ready + 1;       // parked layer-3 accumulator complete (and the [z,a] tile no longer read)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_full + 1);
+  // Dynamic tile scheduler.  The first tile of a CTA is blockIdx.x; every further one is a ticket from a global counter, so that
+  // SMs that run their tiles faster (the per-tile time differs by +-2.5 % across the chip: profiles/r2_tile_stats.txt) take more of
+  // them instead of idling at the end.  Producer thread 0 -- the role that runs furthest ahead -- draws the ticket for tile n + 1
+  // when it starts on tile n and publishes it through a 4-entry ring (tq_full: one arrival per entry use); all roles read the
+  // ring in order.  They stay within a tile of each other (weight ring, accumulator and operand barriers), so an entry is
+  // never overwritten before its last reader is done.
+  uint64_t* tq_full = d3_full + 1;
+  uint32_t* tile_q = reinterpret_cast<uint32_t*>(tq_full + 4);
+  uint32_t* tmem_slot = tile_q + 4;
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
   // holds the GRU state: fp32 [column][row] (conflict-free for thread = row) and the bf16 K-major operand HS (2 k-blocks).
   float* hf = reinterpret_cast<float*>(xs);
@@ -192,6 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
     mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(r_ready, 128); mbar_init(u_ready, 128);
     mbar_init(d3_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&tq_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -200,7 +210,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   tcgen05_fence_after();
   if (*tmem_slot != 0) asm volatile("trap;");   // all 512 columns of the SM are ours: the base is 0, so TMEM addresses are immediates
   constexpr uint32_t tmem = 0;
-  const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // n-th tile of this CTA (n = 0, 1, ...) or -1 when the launch has no more tiles; every role calls it once per tile, in order
+  uint32_t tq_n = 0;
+  auto next_tile = [&]() -> int {
+    const uint32_t e = tq_n & 3u;
+    mbar_wait(&tq_full[e], (tq_n >> 2) & 1u, 16);
+    const uint32_t t = *reinterpret_cast<volatile uint32_t*>(&tile_q[e]);
+    ++tq_n;
+    return t < (uint32_t)kp.num_tiles ? (int)t : -1;
+  };
+  int tiles_done = 0;
   const long long t_start = kp.trace ? clock64() : 0;
 
   if (warp < 4) {
@@ -217,7 +236,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const int pk = warp == 0 ? 0 : warp - 1;
       if (lane == 0 && pk < P) {
         uint32_t stage = 0, phase = 0, mine = 0;    // mine: tile counter mod P
-        for (int it = 0; it < my_tiles; ++it)
+        if (pk == 0) { tile_q[0] = blockIdx.x; mbar_arrive(&tq_full[0]); }
+        for (uint32_t n = 0; next_tile() >= 0; ++n) {
+          if (pk == 0) {
+            // the ticket for tile n + 1, drawn now so that the weight stream never waits for it.  Exactly num_tiles tickets are
+            // drawn per launch (one per tile started, CTA-first tiles included through the failing last draw of every CTA), so
+            // the holder of the last one puts the counter back to zero for the next launch.
+            const unsigned ticket = atomicAdd(kp.tile_counter, 1u);
+            if (ticket == (unsigned)kp.num_tiles - 1u) atomicExch(kp.tile_counter, 0u);
+            tile_q[(n + 1) & 3u] = ticket + gridDim.x;
+            mbar_arrive(&tq_full[(n + 1) & 3u]);
+          }
           for (int j = 0; j < kp.njobs; ++j) {
             const uint32_t job = sjobs[j];
             const int nt = job_tiles(m, job);
@@ -236,6 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
             }
           }
+        }
       }
     } else if (warp == 1) {
       // ============================== MMA issuer ==============================
@@ -299,7 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         else kblock_ss(d, za_addr + kb * TILE_BYTES, b_addr, idesc, min(4, ks1_total - kb * 4), first);
       };
 
-      for (int it = 0; it < my_tiles; ++it)
+      for (int it = 0; next_tile() >= 0; ++it)
         for (int j = 0; j < kp.njobs; ++j) {
           const uint32_t job = kp.jw[j];
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
@@ -593,8 +623,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       for (int i = 0; i < 8; ++i) x[i] = ldg4(ptr, idx * 8 + i);
     };
 
-    for (int it = 0; it < my_tiles; ++it) {
-      const long long g = ((long long)blockIdx.x + (long long)it * gridDim.x) * TILE_ROWS + row;
+    int tile_idx;
+    for (int it = 0; (tile_idx = next_tile()) >= 0; ++it, ++tiles_done) {
+      const long long g = (long long)tile_idx * TILE_ROWS + row;
       const bool valid = g < total;
       const long long pb = valid ? g / p.T : 0;
       const long long pj = valid ? g - pb * p.T : 0;
@@ -1159,7 +1190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     unsigned long long* bs = kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * blockIdx.x;
-    bs[0] = (unsigned long long)t_start; bs[1] = (unsigned long long)clock64(); bs[2] = (unsigned long long)my_tiles; bs[3] = smid;
+    bs[0] = (unsigned long long)t_start; bs[1] = (unsigned long long)clock64(); bs[2] = (unsigned long long)tiles_done; bs[3] = smid;
   }
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
@@ -1449,6 +1480,9 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
     m.pi_w3q = w3q;
   }
   if ((int)tile != tiles) return -1;
+  // ticket counter of the dynamic tile scheduler: in the arena's tail, zero between launches (the kernel resets it itself)
+  m.tile_counter = reinterpret_cast<unsigned int*>(base + (size_t)tiles * TILE_BYTES + jobs_bytes_total() + (512 + 8 * 512) * sizeof(float));
+  if (cudaMemsetAsync(m.tile_counter, 0, 16, st) != cudaSuccess) return -1;
   // job programs for every (mode, horizon)
   uint32_t* jdst = reinterpret_cast<uint32_t*>(base + (size_t)tiles * TILE_BYTES);
   std::vector<uint32_t> all;
@@ -1480,7 +1514,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   // (K = 138 -> 128 + 16) that is the difference between a 2-slot and a 3-slot weight ring
   m.za_compact = (!drnn && nkb1 >= 2 && m.K1p - 64 * (nkb1 - 1) == 16 && !getenv("TDMPC_TC_NO_COMPACT")) ? 1 : 0;
   m.za_bytes = m.za_compact ? (nkb1 - 1) * TILE_BYTES + K16_BLOCK_BYTES : nkb1 * TILE_BYTES;
-  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 22) * 8 + 16 + 1024;
+  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 26) * 8 + 32 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
@@ -1517,6 +1551,7 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
   kp.trace = g_tc_trace;
   kp.one = 1;
+  kp.tile_counter = m.tile_counter;
   kp.debug = m.debug;
   kp.producers = m.producers;
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
