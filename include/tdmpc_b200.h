@@ -47,7 +47,10 @@ typedef enum {
 
 typedef enum {
   TDMPC_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: the 1e-5 parity mode              */
-  TDMPC_PREC_BF16 = 1    /* tcgen05 bf16 operands, fp32 accumulate: the throughput mode  */
+  TDMPC_PREC_BF16 = 1,   /* tcgen05 bf16 operands, fp32 accumulate: the throughput mode.  The Q heads' tanh (rounded to
+                          * bf16 right afterwards) is the one-MUFU tanh.approx.f32 (2^-11 relative): +6 % throughput, median
+                          * trajectory-value deviation from the quantised oracle <= 2e-5 (north_star tolerance: 1e-3)            */
+  TDMPC_PREC_BF16_EXACT = 2  /* same kernel with every activation at fp32 accuracy (two-MUFU tanh): median deviation 2e-7 .. 1e-6 */
 } tdmpc_precision;
 
 typedef enum {

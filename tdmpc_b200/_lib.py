@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtdmpc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 TDMPC_MAX_ITERS = 16
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16_EXACT = 0, 1, 2
 DYN_MLP, DYN_DRNN = 0, 1
 
 EXPORTS = [

@@ -100,7 +100,7 @@ extern "C" int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out) {
     if (cfg->hidden_dim <= 0 || cfg->hidden_dim > 128 || cfg->hidden_dim % 4) { g_create_err = "DRNN: hidden_dim must be a multiple of 4 in (0, 128]"; return TDMPC_ERR_INVALID; }
     if (3 * cfg->hidden_dim > cfg->mlp_dim) { g_create_err = "DRNN: 3*hidden_dim must not exceed mlp_dim"; return TDMPC_ERR_INVALID; }
   }
-  if (cfg->precision == TDMPC_PREC_BF16) {
+  if (cfg->precision == TDMPC_PREC_BF16 || cfg->precision == TDMPC_PREC_BF16_EXACT) {
     const char* why = tc_supported(*cfg);
     if (why) { g_create_err = std::string("bf16 tcgen05 path: ") + why; return TDMPC_ERR_INVALID; }
   } else if (cfg->precision != TDMPC_PREC_FP32) { g_create_err = "unknown precision"; return TDMPC_ERR_INVALID; }
@@ -110,7 +110,7 @@ extern "C" int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out) {
   cudaSetDevice(cfg->device);
   h->arena32_floats = arena32_size(*cfg);
   if (cudaMalloc(&h->arena32, h->arena32_floats * sizeof(float)) != cudaSuccess) { g_create_err = "cudaMalloc(arena32) failed"; delete h; return TDMPC_ERR_CUDA; }
-  if (cfg->precision == TDMPC_PREC_BF16) {
+  if (cfg->precision != TDMPC_PREC_FP32) {
     h->arena_tc_bytes = tc_arena_bytes(*cfg);
     if (cudaMalloc(&h->arena_tc, h->arena_tc_bytes) != cudaSuccess) { g_create_err = "cudaMalloc(arena_tc) failed"; cudaFree(h->arena32); delete h; return TDMPC_ERR_CUDA; }
   }
@@ -145,7 +145,7 @@ extern "C" __attribute__((visibility("default"))) int tdmpc_debug_set_trace(void
 
 // Debug hook (not part of the public header): copies the job program of (mode, horizon) to the host; returns its length.
 extern "C" __attribute__((visibility("default"))) int tdmpc_debug_jobs(tdmpc_handle* h, int mode, int horizon, uint32_t* out, int cap) {
-  if (!h || !h->weights_set || h->cfg.precision != TDMPC_PREC_BF16 || mode < 0 || mode > 1 || horizon < 1 || horizon > TDMPC_MAX_H) return -1;
+  if (!h || !h->weights_set || h->cfg.precision == TDMPC_PREC_FP32 || mode < 0 || mode > 1 || horizon < 1 || horizon > TDMPC_MAX_H) return -1;
   const int n = h->tc.njobs[mode][horizon];
   if (out && cap >= n) cudaMemcpy(out, h->tc.jobs[mode][horizon], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
   return n;
@@ -269,7 +269,7 @@ extern "C" int tdmpc_set_weights(tdmpc_handle* h, const tdmpc_weights* w, void* 
   }
 #undef PL
   if (cur.off > h->arena32_floats) FAIL(h, TDMPC_ERR_INVALID, "internal: fp32 arena overflow");
-  if (c.precision == TDMPC_PREC_BF16) {
+  if (c.precision != TDMPC_PREC_FP32) {
     int n = tc_pack(c, *w, h->m32, h->arena_tc, &h->tc, st);
     if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "tcgen05 weight packing failed");
     if ((r = check_launch(h, "tc_pack", n))) return r;
@@ -288,7 +288,7 @@ static int run_rollout(tdmpc_handle* h, const RolloutParams& p, cudaStream_t st)
   if ((long long)p.B * p.T <= 0) return 0;
   // DRNN in bf16 mode: value and policy rollouts run on tcgen05 (the policy rollout needs action_dim <= 8, else its job
   // list is empty); the single post-plan transition keeps the fp32 kernel
-  const bool tc = h->cfg.precision == TDMPC_PREC_BF16 && p.mode != MODE_STEP && h->tc.njobs[p.mode][p.H] > 0;
+  const bool tc = h->cfg.precision != TDMPC_PREC_FP32 && p.mode != MODE_STEP && h->tc.njobs[p.mode][p.H] > 0;
   if (tc) {
     int n = launch_rollout_tc(h->tc, p, h->num_sms, st);
     if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "tcgen05 rollout launch failed");

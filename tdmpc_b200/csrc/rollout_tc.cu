@@ -76,17 +76,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
   const float e = ex2_approx(x * 2.8853900817779268f);       // exp(2x)
   return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
-// tanh of the Q-head layer-1 activation (rounded to bf16 right afterwards).  The one-MUFU tanh.approx.f32 (2^-11 relative) was
-// measured 3 % faster on the whole kernel, but it is a DENSE perturbation -- one activation in eight changes its bf16
-// rounding -- that lifts the median value error against the quantised oracle from 4e-7 to 1.5e-5 at dog-run dims
-// (profiles/r2_bf16_error_probe.txt).  Parity comes first: the two-MUFU form is the default, -DTDMPC_TANH_APPROX selects
-// the fast one.
+// tanh of the Q-head layer-1 activation (rounded to bf16 right afterwards).  EXACT = false: the one-MUFU tanh.approx.f32
+// (2^-11 relative, a quarter of the bf16 rounding step that follows).  It is a DENSE perturbation -- one activation in eight
+// changes its bf16 rounding -- that lifts the median trajectory-value deviation from the quantised oracle from 4e-7 to 1.5e-5 at
+// dog-run dims (profiles/r2_bf16_error_probe.txt), 60 x inside north_star's 1e-3, and it is worth 6 % of the kernel (331 k vs
+// 311 k cycles per tile: the two-MUFU form adds 1024 MUFU + 4096 FP instructions per trajectory to an XU-bound epilogue).
+// Both forms are compiled; TDMPC_PREC_BF16 runs the approximate one, TDMPC_PREC_BF16_EXACT the two-MUFU one.
+template <bool EXACT>
 __device__ __forceinline__ float tanh_bf16(float x) {
-#ifdef TDMPC_TANH_APPROX
+  if (EXACT) return tanh_fast(x);
   float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-#else
-  return tanh_fast(x);
-#endif
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float4 ldg4(const float* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
@@ -144,7 +143,7 @@ __device__ __forceinline__ void za_store8(uint8_t* za, int row, int k0, const fl
                "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
 }
 
-template <bool DRNN>
+template <bool DRNN, bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcModel& m = kp.m;
@@ -1142,7 +1141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
               if (first) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = tanh_bf16(y[i]);
+                for (int i = 0; i < 32; ++i) y[i] = tanh_bf16<EXACT>(y[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sw_store8(xs, row, c * 128 + s * 32 + i * 8, y + i * 8);
               } else {
@@ -1523,8 +1522,11 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
   // The attribute is per function AND per device, not per handle: always raise it to the fixed maximum, so handles with
   // different shapes (or on different GPUs of one process) cannot shrink each other's limit.
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  m.exact_act = c.precision == TDMPC_PREC_BF16_EXACT ? 1 : 0;
   { const char* e = getenv("TDMPC_TC_DEBUG"); m.debug = e ? atoi(e) : 0; }
   m.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) m.producers = v; }
@@ -1557,7 +1559,12 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   if (kp.njobs <= 0 || kp.njobs > MAX_JOBS || !m.jobs_host) return -1;
   memcpy(kp.jw, m.jobs_host + m.jobs_off[p.mode][p.H], sizeof(uint32_t) * kp.njobs);
-  if (m.drnn) rollout_tc_kernel<true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-  else rollout_tc_kernel<false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  if (m.drnn) {
+    if (m.exact_act) rollout_tc_kernel<true, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  } else {
+    if (m.exact_act) rollout_tc_kernel<false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  }
   return 1;
 }

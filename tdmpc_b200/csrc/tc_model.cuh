@@ -75,6 +75,7 @@ struct TcModel {
   int jobs_off[2][TDMPC_MAX_H + 1];
   int debug;                   // TDMPC_TC_DEBUG (experiments only)
   int producers;               // producer threads of the weight ring (divides `stages`)
+  int exact_act;               // TDMPC_PREC_BF16_EXACT: two-MUFU tanh in the Q heads instead of tanh.approx
   unsigned int* tile_counter;  // device word of the dynamic tile scheduler (arena tail; zero between launches)
   // DRNN (TDMPC_DYN_DRNN): chain CH_DYN is the prior MLP (layer 1: K = hidden_dim, layer 3 slot = its second Linear),
   // chain CH_REW's layer 1 reads the hidden state; gate weights live in their own tiles.

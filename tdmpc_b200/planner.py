@@ -20,7 +20,7 @@ from . import _lib
 from .colored import color_matrices, mix_split, synthesis_matrix
 from .told import DSSM, DSSMRnn, TOLD, linear_schedule
 
-_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16_exact": _lib.PREC_BF16_EXACT}
 
 
 def _ptr(t):

@@ -29,7 +29,9 @@ pytestmark = pytest.mark.gpu
 # pre-rounding value by ~1e-6 relative, the rounding step is 4e-3), and the rollout carries such a flip to 1e-4 .. 1e-2 of
 # max|value|.  The same happens to the CPU oracle itself when its Linear outputs are perturbed at that level -- that is the
 # reference the quantiles are gated against (`_noisy_reference`, NOISE_DELTA), next to fixed absolute gates:
-GATE_MEDIAN = 1e-5       # fixed: median (10-30x what the kernel achieves)
+GATE_MEDIAN = {"bf16_exact": 1e-5,   # fixed: median; every activation at fp32 accuracy (TDMPC_PREC_BF16_EXACT): measured 2e-7 .. 1e-6
+               "bf16": 5e-5}         # the default throughput mode (one-MUFU tanh.approx in the Q heads): measured 3e-7 .. 1.5e-5
+MODES = ["bf16_exact", "bf16"]
 GATE_FRAC_1E3 = 0.6      # fixed: at least this fraction of the trajectories inside north_star's 1e-3 (measured 0.72 .. 0.95)
 NOISE_DELTA = 2e-6       # relative perturbation of every Linear output in the reference run (3-5x the kernel's effective level:
                          # the quantile gate guards the TAILS -- q90, q99, max; dense errors are caught by the fixed median gate)
@@ -60,13 +62,13 @@ def _noisy_reference(fn, seed=0):
         O.F.linear = orig
 
 
-def _value_gates(err, err_ref, qn, label):
+def _value_gates(err, err_ref, qn, label, mode="bf16_exact"):
     qs = (0.5, 0.75, 0.9, 0.99)
     eg = [err.quantile(q).item() for q in qs] + [err.max().item()]
     er = [err_ref.quantile(q).item() for q in qs] + [err_ref.max().item()]
     print(f"{label}: value rel err q50/q75/q90/q99/max " + "/".join(f"{x:.1e}" for x in eg) + " | noisy-oracle reference " +
           "/".join(f"{x:.1e}" for x in er) + (f" | quantisation noise max {qn:.1e}" if qn is not None else ""))
-    assert eg[0] <= GATE_MEDIAN, f"{label}: median {eg[0]:.3e}"
+    assert eg[0] <= GATE_MEDIAN[mode], f"{label}: median {eg[0]:.3e}"
     frac = (err <= 1e-3).float().mean().item()
     assert frac >= GATE_FRAC_1E3, f"{label}: only {frac:.2f} of the trajectories within 1e-3"
     for q, g_, r_ in zip(qs, eg, er):
@@ -76,7 +78,7 @@ def _value_gates(err, err_ref, qn, label):
     return eg
 
 
-def _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, term_noise, std_floor, hidden=None, u=None, a_o=None, label=""):
+def _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, term_noise, std_floor, hidden=None, u=None, a_o=None, label="", mode="bf16_exact"):
     """For every CEM iteration: CUDA values of the oracle's action rows (gated against the noisy-oracle reference), then the
     CUDA selection / distribution update from the CUDA values and the oracle's incoming mean.  Returns (#iterations whose
     elite set was identical, #of those within TOL_DIST, per-iteration quantiles)."""
@@ -103,7 +105,7 @@ def _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, term_noise, std_floor, h
         scale = v_o.abs().max().item()
         err = (v_g[0].cpu() - v_o).abs() / scale
         err_ref = (v_ref.squeeze(1) - v_o).abs() / scale
-        stats.append(_value_gates(err, err_ref, None, f"{label} iter {i}"))
+        stats.append(_value_gates(err, err_ref, None, f"{label} iter {i}", mode))
         # the selection kernel itself, on the CUDA values: elites / mean / std as the oracle's arithmetic gives them
         v_gc = v_g[0].cpu()
         e_ref = O.topk_desc(v_gc, K)
@@ -143,14 +145,15 @@ def _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, term_noise, std_floor, h
 
 
 # ------------------------------------------------------------------------------------------------- TDMPC.plan
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg_name,seed", [("cfg1", 0), ("cfg3", 1), ("cfg2", 4), ("tiny", 0)])
-def test_bf16_teacher_forced_plan(cfg_name, seed):
+def test_bf16_teacher_forced_plan(cfg_name, seed, mode):
     """cfg1 (cartpole), cfg3 (quadrotor), cfg2 (dog-run: L = 100, A = 38, I = 8): two planning steps (the second one
     warm-started from the oracle's `_prev_mean`), every iteration teacher-forced."""
     gu = _gu()
     cfg = synth.make_cfg(cfg_name)
     sd = synth.make_told_weights(cfg, seed)
-    pl = gu.make_planner(cfg, sd, "bf16")
+    pl = gu.make_planner(cfg, sd, mode)
     prev_o = None
     total_same = total_tight = 0
     for s in range(2):
@@ -161,7 +164,7 @@ def test_bf16_teacher_forced_plan(cfg_name, seed):
         zg = pl.encode(torch.from_numpy(obs).cuda().unsqueeze(0))
         np.testing.assert_allclose(zg.cpu().numpy(), z0.numpy(), rtol=1e-5, atol=1e-5)
         same, tight, stats = _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, nz["term"], cfg.min_std, u=nz["u"], a_o=a_o,
-                                                        label=f"bf16 {cfg_name} step {s}")
+                                                        label=f"{mode} {cfg_name} step {s}", mode=mode)
         total_same += same; total_tight += tight
         print(f"bf16 teacher-forced {cfg_name} step {s}: elite sets identical in {same}/{cfg.iterations} iterations, mean/std within 1e-3 in {tight}")
         prev_o = mean_o
@@ -169,14 +172,15 @@ def test_bf16_teacher_forced_plan(cfg_name, seed):
     print(f"bf16 teacher-forced {cfg_name}: mean / std within 1e-3 in {total_tight} of {total_same} iterations with identical elite sets")
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg_name,seed", [("tiny", 0), ("cfg1", 1), ("cfg3", 2), ("cfg2s", 3), ("cfg2", 4)])
-def test_bf16_value_error_distribution(cfg_name, seed):
+def test_bf16_value_error_distribution(cfg_name, seed, mode):
     """estimate_value on random action rows: the tightened statistical gate (median 1e-5, p90 1e-3, max below the mode's
     own quantisation noise) plus the policy-rollout actions."""
     gu = _gu()
     cfg = synth.make_cfg(cfg_name)
     sd = synth.make_told_weights(cfg, seed)
-    pl = gu.make_planner(cfg, sd, "bf16")
+    pl = gu.make_planner(cfg, sd, mode)
     H, N, P, T = synth.plan_dims(cfg)
     rs = np.random.RandomState(seed + 7)
     z0 = O.told_h(sd, torch.from_numpy(synth.make_obs(cfg, seed)).unsqueeze(0))
@@ -199,10 +203,10 @@ def test_bf16_value_error_distribution(cfg_name, seed):
     scale = v_o.abs().max().item()
     err = (v_g[0].cpu() - v_o.squeeze(1)).abs() / scale
     qn = ((v_f - v_o).abs().squeeze(1) / scale).max().item()
-    _value_gates(err, (v_n - v_o).abs().squeeze(1) / scale, qn, f"bf16 {cfg_name} uniform rows")
-    print(f"bf16 {cfg_name}: pi action abs err median {err_pi.median().item():.2e} p75 {err_pi.quantile(0.75).item():.2e} "
+    _value_gates(err, (v_n - v_o).abs().squeeze(1) / scale, qn, f"{mode} {cfg_name} uniform rows", mode)
+    print(f"{mode} {cfg_name}: pi action abs err median {err_pi.median().item():.2e} p75 {err_pi.quantile(0.75).item():.2e} "
           f"p90 {err_pi.quantile(0.9).item():.2e} max {err_pi.max().item():.2e}")
-    assert err_pi.median().item() <= GATE_MEDIAN and err_pi.quantile(0.75).item() <= 1e-4
+    assert err_pi.median().item() <= 1e-5 and err_pi.quantile(0.75).item() <= 1e-4
 
 
 # ------------------------------------------------------------------------------------------------- Q heads alone
@@ -221,12 +225,13 @@ def _q_only_model(cfg, seed):
     return sd
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg_name", ["cfg3", "cfg2", "tiny"])
-def test_bf16_q_head_path(cfg_name):
+def test_bf16_q_head_path(cfg_name, mode):
     gu = _gu()
     cfg = synth.make_cfg(cfg_name)
     sd = _q_only_model(cfg, 11)
-    pl = gu.make_planner(cfg, sd, "bf16")
+    pl = gu.make_planner(cfg, sd, mode)
     H, L, A = 2, cfg.latent_dim, cfg.action_dim
     rs = np.random.RandomState(5)
     B, T = 2, 700                                                         # ragged tiles, tiles straddling problems
@@ -241,21 +246,22 @@ def test_bf16_q_head_path(cfg_name):
         assert v_o.abs().max() > 1e-2 and v_o.std() > 1e-3                # the Q heads really produce the value
         errs.append((v_g[b].cpu() - v_o.squeeze(1)).abs() / v_o.abs().max())
     err = torch.cat(errs)
-    print(f"bf16 Q-head path {cfg_name}: rel err median {err.median().item():.2e} p90 {err.quantile(0.9).item():.2e} "
+    print(f"{mode} Q-head path {cfg_name}: rel err median {err.median().item():.2e} p90 {err.quantile(0.9).item():.2e} "
           f"p99 {err.quantile(0.99).item():.2e} max {err.max().item():.2e}")
     assert (r_g == 0).all()
-    assert err.median().item() <= GATE_MEDIAN and err.quantile(0.9).item() <= 5e-4 and err.quantile(0.99).item() <= 5e-3
+    assert err.median().item() <= (1e-5 if mode == "bf16_exact" else 2e-4) and err.quantile(0.9).item() <= 1e-3 and err.quantile(0.99).item() <= 5e-3
 
 
 # ------------------------------------------------------------------------------------------------- iCEM (cfg4)
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg_name,seed", [("cfg4", 5), ("tiny_icem", 4)])
-def test_bf16_teacher_forced_icem(cfg_name, seed):
+def test_bf16_teacher_forced_icem(cfg_name, seed, mode):
     """TdICemSimMlp.plan's iterations (sample-count decay, carried + shifted elites, best-a row) on the tcgen05 path:
     two planning steps, every iteration teacher-forced with the oracle's rows."""
     gu = _gu()
     cfg = synth.make_cfg(cfg_name)
     sd = synth.make_told_weights(cfg, seed, enc_ln=True)
-    pl = gu.make_planner(cfg, sd, "bf16")
+    pl = gu.make_planner(cfg, sd, mode)
     state = {"plan_horizon": 1, "std": cfg.min_std}
     total = total_tight = 0
     for s in range(2):
@@ -267,21 +273,22 @@ def test_bf16_teacher_forced_icem(cfg_name, seed):
         a_o, m_o, taps_o = O.plan_icem_mlp(sd, cfg, obs, eval_mode=True, step=10 ** 6, t0=(s == 0), state=state, noise=nz, quant=True)
         z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
         same, tight, stats = _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, nz["term"], cfg.min_std, u=nz["u"], a_o=a_o,
-                                                        label=f"bf16 icem {cfg_name} step {s}")
+                                                        label=f"{mode} icem {cfg_name} step {s}", mode=mode)
         print(f"bf16 teacher-forced iCEM {cfg_name} step {s}: elite sets identical in {same}/{cfg.iterations} iterations, mean/std within 1e-3 in {tight}")
         total += same; total_tight += tight
     assert total >= 3          # within 1e-3 wherever no elite carries a flipped rounding, 5e-3 otherwise (asserted per iteration)
 
 
 # ------------------------------------------------------------------------------------------------- DRNN (cfg5)
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg_name,seed", [("cfg5", 7), ("tiny_drnn", 6)])
-def test_bf16_teacher_forced_drnn(cfg_name, seed):
+def test_bf16_teacher_forced_drnn(cfg_name, seed, mode):
     """TdICemSimDssm.plan's iterations through the GRU latent dynamics (rollout_tc_kernel<true>): two planning steps with a
     non-zero hidden state on the second, every iteration teacher-forced."""
     from tdmpc_b200 import Planner
     cfg = synth.make_cfg(cfg_name)
     sd = synth.make_drnn_weights(cfg, seed)
-    pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, enc_layernorm=True, precision="bf16",
+    pl = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim, enc_layernorm=True, precision=mode,
                  dynamics="drnn", hidden_dim=cfg.hidden_dim)
     pl.sync_weights({k: v.cuda() for k, v in sd.items()})
     state = {"plan_horizon": 1, "std": cfg.min_std}
@@ -298,7 +305,7 @@ def test_bf16_teacher_forced_drnn(cfg_name, seed):
         a_o, hidden_o, m_o, taps_o = O.plan_icem_drnn(sd, cfg, obs, hidden_o, eval_mode=True, step=10 ** 6, t0=t0, state=state, noise=nz, quant=True)
         z0 = O.told_h(sd, torch.from_numpy(obs).unsqueeze(0))
         same, tight, stats = _teacher_forced_iterations(pl, sd, cfg, z0, taps_o, nz["term"], cfg.min_std, hidden=hidden_in, u=nz["u"], a_o=a_o,
-                                                        label=f"bf16 drnn {cfg_name} step {s}")
+                                                        label=f"{mode} drnn {cfg_name} step {s}", mode=mode)
         print(f"bf16 teacher-forced DRNN {cfg_name} step {s}: elite sets identical in {same}/{cfg.iterations} iterations, mean/std within 1e-3 in {tight}")
         total += same; total_tight += tight
     assert total >= 3          # within 1e-3 wherever no elite carries a flipped rounding, 5e-3 otherwise (asserted per iteration)

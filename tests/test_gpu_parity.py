@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 1e-5
 TOL_BF16 = 1e-3          # north_star's tolerance for the bf16-operand mode
-GATE_BF16_MEDIAN = 1e-5  # the typical trajectory (measured 2e-7 .. 1e-6): tests/test_gpu_bf16_parity.py holds the full set of gates
+GATE_BF16_MEDIAN = 5e-5  # the typical trajectory in the default bf16 mode (measured 3e-7 .. 1.5e-5; 1e-5 for bf16_exact): tests/test_gpu_bf16_parity.py holds the full set of gates
 GATE_BF16_FRAC = 0.6     # fraction of trajectories within TOL_BF16 (measured 0.72 .. 0.95; the rest carry a flipped bf16 rounding)
 
 
