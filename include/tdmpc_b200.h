@@ -280,12 +280,48 @@ TDMPC_API int64_t tdmpc_replay_workspace_bytes(int64_t total, int32_t batch);
 TDMPC_API int tdmpc_replay_sample(const tdmpc_replay_sample_args* args, void* stream);
 TDMPC_API int tdmpc_replay_gather(const tdmpc_replay_gather_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step forward: the loss terms of TDMPC.update (algorithm/tdmpc.py:191-228) with the
+ * TD target of TDMPC._td_target (tdmpc.py:180-189) for one replay batch, fp32.  `online` and `target` are two handles of the
+ * same model shape holding agent.model and agent.model_target (MLP dynamics, precision any: the fp32 parameter arena is used).
+ * Per sample b (the reference's [B, 1] tensors):
+ *   consistency[b] = sum_t rho^t mean_L (z_{t+1} - h_target(next_obs_t))^2      reward_loss[b] = sum_t rho^t (r_t - reward_t)^2
+ *   value[b]       = sum_t rho^t ((Q1 - td)^2 + (Q2 - td)^2)                    priority[b]    = sum_t rho^t (|Q1 - td| + |Q2 - td|)
+ *   total[b]       = c_cons min(consistency, 1e4) + c_rew min(reward_loss, 1e4) + c_val min(value, 1e4)
+ * with td = reward_t + discount * min(Q_target(h(next_obs_t), pi(h(next_obs_t), min_std))).  The mean / weighted reductions
+ * over the batch, the backward pass and the optimiser stay with the caller (not implemented here). */
+typedef struct {
+  int32_t batch, horizon;
+  double discount, rho;            /* cfg.discount, cfg.rho (python floats in the reference)                       */
+  float min_std;
+  float consistency_coef, reward_coef, value_coef;
+  const float* obs;                /* [batch, obs_dim]                 replay_buffer.sample()[0]                   */
+  const float* next_obses;         /* [horizon, batch, obs_dim]        ...[1][:horizon]                            */
+  const float* action;             /* [horizon, batch, action_dim]     ...[2][:horizon]                            */
+  const float* reward;             /* [horizon, batch]                 ...[3][:horizon].squeeze(2)                 */
+  const float* noise_pi;           /* [horizon, batch, action_dim] standard-normal draws of pi() inside _td_target, or NULL:
+                                    * Philox (seed, call)                                                           */
+  uint64_t seed, call;
+  float* consistency_loss;         /* out [batch]                                                                   */
+  float* reward_loss;              /* out [batch]                                                                   */
+  float* value_loss;               /* out [batch]                                                                   */
+  float* priority_loss;            /* out [batch]  (what update() hands to update_priorities, before its clamp)     */
+  float* total_loss;               /* out [batch]                                                                   */
+  float* zs;                       /* out [horizon + 1, batch, latent_dim] or NULL: the latents update_pi consumes   */
+  float* td_target;                /* out [horizon, batch] or NULL (debug taps)                                      */
+  float* q1;                       /* out [horizon, batch] or NULL                                                   */
+  float* q2;                       /* out [horizon, batch] or NULL                                                   */
+  float* reward_pred;              /* out [horizon, batch] or NULL                                                   */
+} tdmpc_update_args;
+
+TDMPC_API int tdmpc_update_forward(tdmpc_handle* online, tdmpc_handle* target, const tdmpc_update_args* args, void* stream);
+
 /* Number of kernels of THIS library launched by the handle so far (bench.py's gpu_launches). */
 TDMPC_API uint64_t tdmpc_launch_count(const tdmpc_handle* h);
 
 /* Layout self-check for FFI bindings: writes up to n of {sizeof(tdmpc_model_cfg), sizeof(tdmpc_weights),
  * sizeof(tdmpc_plan_args), offsetof(plan_args, obs), offsetof(.., seed), offsetof(.., action), offsetof(.., tap_z0),
- * sizeof(tdmpc_replay_sample_args), sizeof(tdmpc_replay_gather_args)} and returns how many values exist. */
+ * sizeof(tdmpc_replay_sample_args), sizeof(tdmpc_replay_gather_args), sizeof(tdmpc_update_args)} and returns how many values exist. */
 TDMPC_API int32_t tdmpc_abi_sizes(int32_t* out, int32_t n);
 
 /* Build information: "sm_100a;tcgen05=1;..." */

@@ -17,6 +17,7 @@ Reference lines followed (all under /root/reference/src):
   algorithm/tdmpc.py:30-50     TOLD.h / next / pi / Q
   algorithm/tdmpc.py:83-92     TDMPC.estimate_value
   algorithm/tdmpc.py:94-163    TDMPC.plan
+  algorithm/tdmpc.py:180-228   TDMPC._td_target / update (forward half: loss terms, TD targets, priorities)
   algorithm/helper.py:71-96    TruncatedNormal.sample
   algorithm/helper.py:119-133,156-176,197-201   enc / dmlab_enc_norm / mlp / q layer stacks
   algorithm/helper.py:639-652  linear_schedule
@@ -515,6 +516,41 @@ def plan_icem_drnn(sd, cfg, obs, hidden, *, eval_mode, step, t0, state, noise, q
     taps["pick"] = j
     taps["score"] = score.squeeze(1).clone()
     return a, hidden_next, metrics, taps
+
+
+# ----------------------------------------------------------------------------- TDMPC.update, forward half
+
+
+def update_forward(sd, sd_target, cfg, batch):
+    """Forward of TDMPC.update (tdmpc.py:191-228) with _td_target (tdmpc.py:180-189), fp32, for a replay batch as
+    tests/synth.make_update_batch builds it (state observations: h.RandomShiftsAug is the identity, helper.py:256-262).
+    Returns the per-sample loss tensors [B,1], total / weighted loss and the latents zs the policy update consumes."""
+    obs, next_obses, action, reward = batch["obs"], batch["next_obses"], batch["action"], batch["reward"]
+    z = told_h(sd, obs)
+    zs = [z]
+    consistency_loss, reward_loss, value_loss, priority_loss = 0, 0, 0, 0
+    taps = {"td_target": [], "q1": [], "q2": [], "reward_pred": []}
+    for t in range(cfg.horizon):
+        Q1, Q2 = told_Q(sd, z, action[t])
+        z, reward_pred = told_next(sd, z, action[t])
+        next_obs = next_obses[t]
+        next_z = told_h(sd_target, next_obs)
+        nz_on = told_h(sd, next_obs)                                  # _td_target: ONLINE encoder and policy, TARGET Q heads
+        td_target = reward[t] + cfg.discount * torch.min(*told_Q(sd_target, nz_on, told_pi(sd, nz_on, cfg.min_std, batch["noise_pi"][t])))
+        zs.append(z)
+        rho = cfg.rho ** t
+        consistency_loss = consistency_loss + rho * torch.mean(F.mse_loss(z, next_z, reduction="none"), dim=1, keepdim=True)
+        reward_loss = reward_loss + rho * F.mse_loss(reward_pred, reward[t], reduction="none")
+        value_loss = value_loss + rho * (F.mse_loss(Q1, td_target, reduction="none") + F.mse_loss(Q2, td_target, reduction="none"))
+        priority_loss = priority_loss + rho * (F.l1_loss(Q1, td_target, reduction="none") + F.l1_loss(Q2, td_target, reduction="none"))
+        for k, v in (("td_target", td_target), ("q1", Q1), ("q2", Q2), ("reward_pred", reward_pred)):
+            taps[k].append(v.squeeze(1).clone())
+    total_loss = cfg.consistency_coef * consistency_loss.clamp(max=1e4) + cfg.reward_coef * reward_loss.clamp(max=1e4) + \
+        cfg.value_coef * value_loss.clamp(max=1e4)
+    weighted_loss = (total_loss * batch["weights"]).mean()
+    return {"consistency": consistency_loss, "reward": reward_loss, "value": value_loss, "priority": priority_loss,
+            "total": total_loss, "weighted_loss": float(weighted_loss), "zs": torch.stack(zs),
+            "taps": {k: torch.stack(v) for k, v in taps.items()}}
 
 
 # ----------------------------------------------------------------------------- flop / step accounting (SURVEY 8d)

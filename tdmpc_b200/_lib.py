@@ -19,7 +19,7 @@ EXPORTS = [
     "tdmpc_create", "tdmpc_destroy", "tdmpc_last_error", "tdmpc_reserve", "tdmpc_set_weights",
     "tdmpc_encode", "tdmpc_estimate_value", "tdmpc_estimate_value_drnn", "tdmpc_pi_rollout", "tdmpc_select_update", "tdmpc_plan",
     "tdmpc_fill_noise", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes",
-    "tdmpc_replay_workspace_bytes", "tdmpc_replay_sample", "tdmpc_replay_gather",
+    "tdmpc_replay_workspace_bytes", "tdmpc_replay_sample", "tdmpc_replay_gather", "tdmpc_update_forward",
 ]
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -81,6 +81,17 @@ class ReplayGatherArgs(C.Structure):
     ]
 
 
+class UpdateArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("horizon", C.c_int32), ("discount", C.c_double), ("rho", C.c_double), ("min_std", C.c_float),
+        ("consistency_coef", C.c_float), ("reward_coef", C.c_float), ("value_coef", C.c_float),
+        ("obs", _fp), ("next_obses", _fp), ("action", _fp), ("reward", _fp), ("noise_pi", _fp),
+        ("seed", C.c_uint64), ("call", C.c_uint64),
+        ("consistency_loss", _fp), ("reward_loss", _fp), ("value_loss", _fp), ("priority_loss", _fp), ("total_loss", _fp),
+        ("zs", _fp), ("td_target", _fp), ("q1", _fp), ("q2", _fp), ("reward_pred", _fp),
+    ]
+
+
 def build(verbose=False):
     """Compile libtdmpc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     r = subprocess.run(["make", "-C", CSRC, "-j8", "all"], capture_output=True, text=True)
@@ -125,10 +136,11 @@ def load():
     lib.tdmpc_replay_workspace_bytes.argtypes = [C.c_int64, C.c_int32]; lib.tdmpc_replay_workspace_bytes.restype = C.c_int64
     lib.tdmpc_replay_sample.argtypes = [C.POINTER(ReplaySampleArgs), C.c_void_p]
     lib.tdmpc_replay_gather.argtypes = [C.POINTER(ReplayGatherArgs), C.c_void_p]
-    got = (C.c_int32 * 9)()
-    lib.tdmpc_abi_sizes(got, 9)
+    lib.tdmpc_update_forward.argtypes = [H, H, C.POINTER(UpdateArgs), C.c_void_p]
+    got = (C.c_int32 * 10)()
+    lib.tdmpc_abi_sizes(got, 10)
     want = [C.sizeof(ModelCfg), C.sizeof(Weights), C.sizeof(PlanArgs), PlanArgs.obs.offset, PlanArgs.seed.offset,
-            PlanArgs.action.offset, PlanArgs.tap_z0.offset, C.sizeof(ReplaySampleArgs), C.sizeof(ReplayGatherArgs)]
+            PlanArgs.action.offset, PlanArgs.tap_z0.offset, C.sizeof(ReplaySampleArgs), C.sizeof(ReplayGatherArgs), C.sizeof(UpdateArgs)]
     if list(got) != want:
         raise RuntimeError(f"libtdmpc_b200.so ABI mismatch: library {list(got)} vs binding {want} (stale build?)")
     for name in EXPORTS:

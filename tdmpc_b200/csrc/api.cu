@@ -154,7 +154,7 @@ extern "C" int32_t tdmpc_abi_sizes(int32_t* out, int32_t n) {
   const int32_t v[] = {(int32_t)sizeof(tdmpc_model_cfg), (int32_t)sizeof(tdmpc_weights), (int32_t)sizeof(tdmpc_plan_args),
                        (int32_t)offsetof(tdmpc_plan_args, obs), (int32_t)offsetof(tdmpc_plan_args, seed),
                        (int32_t)offsetof(tdmpc_plan_args, action), (int32_t)offsetof(tdmpc_plan_args, tap_z0),
-                       (int32_t)sizeof(tdmpc_replay_sample_args), (int32_t)sizeof(tdmpc_replay_gather_args)};
+                       (int32_t)sizeof(tdmpc_replay_sample_args), (int32_t)sizeof(tdmpc_replay_gather_args), (int32_t)sizeof(tdmpc_update_args)};
   const int32_t m = (int32_t)(sizeof(v) / sizeof(v[0]));
   for (int32_t i = 0; i < n && i < m; ++i) out[i] = v[i];
   return m;
@@ -369,6 +369,34 @@ extern "C" int tdmpc_select_update(tdmpc_handle* h, const float* values, const f
   p.elite_idx = elite_idx; p.score = score;
   launch_select(p, (cudaStream_t)stream);
   return check_launch(h, "select");
+}
+
+extern "C" int tdmpc_update_forward(tdmpc_handle* h, tdmpc_handle* ht, const tdmpc_update_args* a, void* stream) {
+  if (!h || !ht || !a) return TDMPC_ERR_INVALID;
+  if (!h->weights_set || !ht->weights_set) FAIL(h, TDMPC_ERR_STATE, "update_forward: weights of the online / target handle not set");
+  const tdmpc_model_cfg &c = h->cfg, &ct = ht->cfg;
+  if (c.obs_dim != ct.obs_dim || c.action_dim != ct.action_dim || c.latent_dim != ct.latent_dim || c.mlp_dim != ct.mlp_dim ||
+      c.enc_dim != ct.enc_dim || c.enc_layernorm != ct.enc_layernorm || c.dynamics != ct.dynamics || c.device != ct.device)
+    FAIL(h, TDMPC_ERR_INVALID, "update_forward: online and target handles differ in shape or device");
+  if (c.dynamics != TDMPC_DYN_MLP) FAIL(h, TDMPC_ERR_INVALID, "update_forward: MLP dynamics only");
+  if (a->batch <= 0 || a->horizon <= 0 || a->horizon > TDMPC_MAX_H) FAIL(h, TDMPC_ERR_INVALID, "update_forward: bad batch / horizon");
+  if (!a->obs || !a->next_obses || !a->action || !a->reward || !a->consistency_loss || !a->reward_loss || !a->value_loss ||
+      !a->priority_loss || !a->total_loss)
+    FAIL(h, TDMPC_ERR_INVALID, "update_forward: a required pointer is NULL");
+  if (c.mlp_dim != 512 || c.enc_dim > c.mlp_dim) FAIL(h, TDMPC_ERR_INVALID, "update_forward: mlp_dim must be 512 and enc_dim <= mlp_dim");
+  cudaSetDevice(c.device);
+  UpdateFwdParams p{};
+  p.B = a->batch; p.H = a->horizon; p.D = c.obs_dim; p.E = c.enc_dim; p.L = c.latent_dim; p.A = c.action_dim; p.M = c.mlp_dim;
+  p.obs = a->obs; p.next_obses = a->next_obses; p.action = a->action; p.reward = a->reward;
+  p.noise = NoiseSrc{a->noise_pi, a->seed, a->call, NS_PI};
+  p.min_std = a->min_std; p.discount = (float)a->discount;
+  double r = 1.0;                       // rho = cfg.rho ** t: a python float, rounded once when it multiplies the fp32 tensor
+  for (int t = 0; t < a->horizon; ++t) { p.rho_pow[t] = (float)r; r *= a->rho; }
+  p.c_cons = a->consistency_coef; p.c_rew = a->reward_coef; p.c_val = a->value_coef;
+  p.consistency = a->consistency_loss; p.reward_loss = a->reward_loss; p.value = a->value_loss; p.priority = a->priority_loss;
+  p.total = a->total_loss; p.zs = a->zs; p.td_target = a->td_target; p.q1 = a->q1; p.q2 = a->q2; p.reward_pred = a->reward_pred;
+  if (launch_update_fwd(h->m32, ht->m32, p, (cudaStream_t)stream) < 0) FAIL(h, TDMPC_ERR_INVALID, "update_forward: shape does not fit in shared memory");
+  return check_launch(h, "update_fwd");
 }
 
 extern "C" int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,

@@ -234,3 +234,23 @@ void launch_sample(const SampleParams& p, int nparts, cudaStream_t st);
 void launch_bump_counter(uint64_t* c, cudaStream_t st);     // *c += 1 (tdmpc_plan_args.call_dev)
 void launch_fill_noise(int stream_id, uint64_t seed, uint64_t call, uint64_t count, void* out, cudaStream_t st);
 void launch_transpose_pack(const float* w, int N, int K, int Kp, int Kdst_off, float* wt, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------
+// Training-step forward (update_fwd.cu): TDMPC.update's loss terms for one replay batch.
+struct UpdateFwdParams {
+  int B, H, D, E, L, A, M;
+  const float* obs;          // [B][D]
+  const float* next_obses;   // [H][B][D]
+  const float* action;       // [H][B][A]
+  const float* reward;       // [H][B]
+  NoiseSrc noise;            // policy draws inside _td_target: element (t * B + b) * A + a
+  float min_std, discount;
+  float rho_pow[TDMPC_MAX_H];
+  float c_cons, c_rew, c_val;
+  float *consistency, *reward_loss, *value, *priority, *total;      // [B]
+  float *zs;                 // [H + 1][B][L] or nullptr (the latents update_pi consumes, tdmpc.py:201,213)
+  float *td_target, *q1, *q2, *reward_pred;                          // [H][B] or nullptr (taps)
+};
+
+size_t update_fwd_smem(const ModelFp32& m, int D, int L, int A, int M, int E);
+int launch_update_fwd(const ModelFp32& m, const ModelFp32& mt, const UpdateFwdParams& p, cudaStream_t st);

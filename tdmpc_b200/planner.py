@@ -609,8 +609,58 @@ class TDMPC:
         return v, float(r.mean().item())
 
     def update(self, replay_buffer, step):
-        raise NotImplementedError("training stays in the reference's PyTorch code; use tdmpc_b200.accelerate(agent) "
-                                  "on a reference TDMPC to keep update() and gain the CUDA plan()")
+        raise NotImplementedError("the optimiser step stays in the reference's PyTorch code (use tdmpc_b200.accelerate(agent) on a "
+                                  "reference TDMPC to keep update() and gain the CUDA plan()); the FORWARD of update() -- loss terms, "
+                                  "TD targets, priorities -- is available as update_forward()")
+
+    @torch.no_grad()
+    def update_forward(self, obs, next_obses, action, reward, weights=None, noise_pi=None, taps=False):
+        """Forward half of TDMPC.update (tdmpc.py:191-228) for one replay batch, as CUDA (tdmpc_update_forward, fp32):
+        obs [B,D], next_obses [>=H,B,D], action [>=H,B,A], reward [>=H,B,1] or [>=H,B] -- what ReplayBuffer.sample() returns --
+        and `weights` [B,1] its importance weights.  Returns the reference's metric names (consistency_loss, reward_loss,
+        value_loss, total_loss, weighted_loss: batch means as floats), the per-sample `priorities` [B,1] that update() hands to
+        update_priorities (already clamped at 1e4), the per-sample loss tensors and the latents `zs` [H+1,B,L] that update_pi
+        consumes.  Backward and the optimiser step are not part of this call."""
+        cfg = self.cfg
+        pl = self._planner
+        pl.sync_weights(self.model)
+        if getattr(self, "_planner_target", None) is None:
+            self._planner_target = Planner(cfg.obs_shape[0], cfg.action_dim, cfg.latent_dim, cfg.mlp_dim, cfg.enc_dim,
+                                           enc_layernorm="_encoder.3.weight" in self.model_target.state_dict(),
+                                           precision="fp32", device=self.device)
+        pt = self._planner_target
+        pt.sync_weights(self.model_target)
+        H = int(cfg.horizon)
+        dev = self.device
+        obs = _f32(obs, dev); B = obs.shape[0]
+        nxt, act = _f32(next_obses[:H], dev), _f32(action[:H], dev)
+        rew = _f32(reward[:H], dev).reshape(H, B)
+        out = {k: torch.empty(B, device=dev) for k in ("consistency", "reward", "value", "priority", "total")}
+        zs = torch.empty(H + 1, B, cfg.latent_dim, device=dev)
+        a = _lib.UpdateArgs()
+        a.batch, a.horizon, a.discount, a.rho, a.min_std = B, H, float(cfg.discount), float(cfg.rho), float(cfg.min_std)
+        a.consistency_coef, a.reward_coef, a.value_coef = float(cfg.consistency_coef), float(cfg.reward_coef), float(cfg.value_coef)
+        a.obs, a.next_obses, a.action, a.reward = obs.data_ptr(), nxt.data_ptr(), act.data_ptr(), rew.data_ptr()
+        nz = None
+        if noise_pi is not None:
+            nz = _f32(noise_pi, dev)
+            assert tuple(nz.shape) == (H, B, cfg.action_dim)
+            a.noise_pi = nz.data_ptr()
+        pl.call += 1
+        a.seed, a.call = pl.seed, pl.call
+        a.consistency_loss, a.reward_loss, a.value_loss = out["consistency"].data_ptr(), out["reward"].data_ptr(), out["value"].data_ptr()
+        a.priority_loss, a.total_loss, a.zs = out["priority"].data_ptr(), out["total"].data_ptr(), zs.data_ptr()
+        tp = None
+        if taps:
+            tp = {k: torch.empty(H, B, device=dev) for k in ("td_target", "q1", "q2", "reward_pred")}
+            a.td_target, a.q1, a.q2, a.reward_pred = (tp[k].data_ptr() for k in ("td_target", "q1", "q2", "reward_pred"))
+        pl._check(pl.lib.tdmpc_update_forward(pl._h, pt._h, C.byref(a), pl._stream()), "tdmpc_update_forward")
+        self._keep_update = (obs, nxt, act, rew, nz)
+        w = torch.ones(B, device=dev) if weights is None else _f32(weights, dev).reshape(B)
+        return {"consistency_loss": float(out["consistency"].mean().item()), "reward_loss": float(out["reward"].mean().item()),
+                "value_loss": float(out["value"].mean().item()), "total_loss": float(out["total"].mean().item()),
+                "weighted_loss": float((out["total"] * w).mean().item()),
+                "priorities": out["priority"].clamp(max=1e4).unsqueeze(1), "per_sample": out, "zs": zs, "taps": tp}
 
 
 class TdICemSimMlp(TDMPC):

@@ -193,6 +193,53 @@ def run_sim_case(name, cfg_name, plan, seed=0, eval_mode=True, **over):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def run_update_case(name, cfg_name, batch=96, seed=0, **over):
+    """TDMPC.update (tdmpc.py:191-245), the unmodified reference method, on CPU for one fixed replay batch: the returned
+    metrics (loss means, weighted loss, grad norm) and the per-sample priorities it hands to update_priorities.  The online and
+    the target model get DIFFERENT synthetic parameters so that a mix-up of the two (the TD target uses the online encoder and
+    policy with the target Q heads) shows."""
+    cfg = synth.make_cfg(cfg_name, batch_size=batch, **over)
+    torch.manual_seed(0)
+    agent = TDMPC(cfg)
+    sd, sd_t = synth.make_told_weights(cfg, seed), synth.make_told_weights(cfg, seed + 50)
+    agent.model.load_state_dict(sd)
+    agent.model_target.load_state_dict(sd_t)
+    b = synth.make_update_batch(cfg, seed, batch)
+
+    class Buf:
+        def sample(self):
+            return b["obs"], b["next_obses"], b["action"], b["reward"], b["idxs"], b["weights"]
+
+        def update_priorities(self, idxs, pr):
+            self.idxs, self.pr = idxs.clone(), pr.clone()
+
+    buf = Buf()
+    q = [b["noise_pi"][t] for t in range(cfg.horizon)]
+    real = ref_h._standard_normal
+
+    def stdn(shape, dtype=None, device=None):
+        if q:
+            x = q.pop(0)
+            assert tuple(x.shape) == tuple(shape), (x.shape, shape)
+            return x.clone()
+        return real(shape, dtype=dtype, device=device)                # the draws of update_pi (after the optimiser step)
+
+    ref_h._standard_normal = stdn
+    try:
+        m = agent.update(buf, 10 ** 6)
+    finally:
+        ref_h._standard_normal = real
+    assert not q and torch.equal(buf.idxs, b["idxs"])
+    o = O.update_forward(sd, sd_t, cfg, b)
+    out = {"priorities": buf.pr.numpy().copy(), "meta": np.array([seed, batch], dtype=np.int64),
+           "metrics": np.array([m["consistency_loss"], m["reward_loss"], m["value_loss"], m["total_loss"], m["weighted_loss"], m["grad_norm"], m["pi_loss"]], dtype=np.float64)}
+    mo = [float(o["consistency"].mean()), float(o["reward"].mean()), float(o["value"].mean()), float(o["total"].mean()), o["weighted_loss"]]
+    dp = (o["priority"].clamp(max=1e4) - buf.pr).abs().max().item()
+    print(f"[{name}] reference metrics {out['metrics'][:5]} oracle {mo} |dpriority| {dp:.3e}")
+    assert np.allclose(out["metrics"][:5], mo, rtol=1e-6, atol=1e-7) and dp < 1e-6
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
 SIM_PLAN = [(9000, True), (9001, False), (17000, False), (17001, True), (17002, False)]     # horizon schedule: 3, 3, (4 ignored), 4, 4
 
 
@@ -415,6 +462,11 @@ if __name__ == "__main__":
         run_replay_case("replay_small", "small", seed=0)
         run_replay_case("replay_full", "full", seed=1)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "update":
+        run_update_case("update_tiny", "tiny", batch=70, seed=12)
+        run_update_case("update_cfg3", "cfg3", batch=96, seed=13)
+        run_update_case("update_cfg2s", "cfg2s", batch=40, seed=14)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sim":
         run_sim_case("tdmpcsim_tiny", "tiny", SIM_PLAN, seed=8, horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)
         run_sim_case("tdmpcsim_cfg3", "cfg3", SIM_PLAN[:4], seed=9, eval_mode=False)
@@ -433,4 +485,7 @@ if __name__ == "__main__":
     run_replay_case("replay_full", "full", seed=1)
     run_sim_case("tdmpcsim_tiny", "tiny", SIM_PLAN, seed=8, horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)
     run_sim_case("tdmpcsim_cfg3", "cfg3", SIM_PLAN[:4], seed=9, eval_mode=False)
+    run_update_case("update_tiny", "tiny", batch=70, seed=12)
+    run_update_case("update_cfg3", "cfg3", batch=96, seed=13)
+    run_update_case("update_cfg2s", "cfg2s", batch=40, seed=14)
     print("golden fixtures written to", HERE)

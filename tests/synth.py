@@ -24,6 +24,8 @@ def make_cfg(name="cfg1", **over):
         factor_decrease_num=1.25, shift_elites_over_time=True, fraction_elites_reused=0.25,
         keep_previous_elites=True, noise_beta=2.5, normalize=False, norm_type="ln", norm_cell=True,
         img_size=84, frame_stack=1, num_channels=32, train_steps=500000, episode_length=1000, optim_id="adamw", pi_lr=1e-3,
+        # training-step scalars (cfgs/default.yaml:32-44; rho 0.5 as upstream TD-MPC so that its powers are exercised)
+        rho=0.5, consistency_coef=2.0, reward_coef=0.5, value_coef=0.1, grad_clip_norm=10, update_freq=2, tau=0.01,
     )
     dims = {
         "cfg1": dict(obs_shape=(5,), action_dim=1),                       # cartpole-swingup
@@ -159,6 +161,18 @@ def make_noise_hp(cfg, seed, H, P):
     }
     n["u"] = float(rs.random_sample())
     return n
+
+
+def make_update_batch(cfg, seed, batch):
+    """What ReplayBuffer.sample() hands to TDMPC.update (helper.py:506-534, latent_plan=True): obs [B,D], next_obses [H+1,B,D],
+    action [H+1,B,A], reward [H+1,B,1], idxs [B], weights [B,1]; plus the standard-normal draws of pi() inside _td_target
+    [H,B,A] (tdmpc.py:188)."""
+    rs = np.random.RandomState(4000 + seed)
+    H, D, A = cfg.horizon, cfg.obs_shape[0], cfg.action_dim
+    return {"obs": _t(rs.standard_normal((batch, D))), "next_obses": _t(rs.standard_normal((H + 1, batch, D))),
+            "action": _t(rs.uniform(-1, 1, (H + 1, batch, A))), "reward": _t(rs.standard_normal((H + 1, batch, 1))),
+            "idxs": torch.from_numpy(rs.permutation(10 * batch)[:batch].astype(np.int64)),
+            "weights": _t(rs.uniform(0.2, 1.0, (batch, 1))), "noise_pi": _t(rs.standard_normal((H, batch, A)))}
 
 
 def make_icem_noise(cfg, seed, sizes, H, have_elites, single_beta=False):

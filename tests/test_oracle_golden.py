@@ -199,3 +199,25 @@ def test_oracle_matches_tdmpcsim_fixture(golden_dir, name, cfg_name, over):
                 assert set(taps["elite_idx"][i].tolist()) == set(g[f"s{s}_elite_idx"][i].tolist())
         np.testing.assert_allclose(state["_prev_mean"].numpy(), g[f"s{s}_prev_mean"], rtol=0, atol=1e-4)
         np.testing.assert_allclose(a.numpy(), g[f"s{s}_action"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("name,cfg_name", [("update_tiny", "tiny"), ("update_cfg3", "cfg3"), ("update_cfg2s", "cfg2s")])
+def test_oracle_update_forward_matches_reference_fixture(golden_dir, name, cfg_name):
+    """oracle.update_forward against what the unmodified TDMPC.update (tdmpc.py:191-245) returned for the same replay batch:
+    loss means, weighted loss, and the per-sample priorities it handed to ReplayBuffer.update_priorities."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, batch = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name, batch_size=batch)
+    sd, sd_t = synth.make_told_weights(cfg, seed), synth.make_told_weights(cfg, seed + 50)
+    o = O.update_forward(sd, sd_t, cfg, synth.make_update_batch(cfg, seed, batch))
+    got = [float(o["consistency"].mean()), float(o["reward"].mean()), float(o["value"].mean()), float(o["total"].mean()), o["weighted_loss"]]
+    np.testing.assert_allclose(got, g["metrics"][:5], rtol=2e-5)
+    np.testing.assert_allclose(o["priority"].clamp(max=1e4).numpy(), g["priorities"], rtol=2e-5, atol=1e-6)
+    assert tuple(o["zs"].shape) == (cfg.horizon + 1, batch, cfg.latent_dim)
+
+
+def test_package_accounting_matches_oracle():
+    from tdmpc_b200 import accounting as A
+    for args in ((5, 1, 50, 512, 256, 5, [537] * 6, 25), (223, 38, 100, 512, 256, 5, [537] * 8, 25), (18, 4, 50, 512, 256, 10, [1544, 1236, 990], 512)):
+        assert A.flops_per_plan(*args) == O.flops_per_plan(*args)
+    assert A.sample_steps_per_plan(5, [537] * 6, 25) == O.sample_steps_per_plan(5, [537] * 6, 25) == 16235
