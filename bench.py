@@ -263,6 +263,38 @@ def replay_extra(dev, hbm_peak):
     return out
 
 
+def update_forward_extra(dev, batch=512):
+    """SURVEY 8(f) row 2, forward half: TDMPC.update's loss terms for one replay batch (cfg3 dims, batch 512, H = 5) through
+    tdmpc_update_forward (fp32 CUDA-core kernel), next to the same op sequence run eagerly by torch on this GPU and on the host."""
+    from oracle import tdmpc_oracle as O
+    from tdmpc_b200 import TDMPC
+    cfg = synth.make_cfg("cfg3", batch_size=batch, device=str(dev), precision="fp32")
+    sd, sd_t = synth.make_told_weights(cfg, 0), synth.make_told_weights(cfg, 50)
+    agent = TDMPC(cfg)
+    agent.model.load_state_dict(sd); agent.model_target.load_state_dict(sd_t)
+    b = {k: v.to(dev) for k, v in synth.make_update_batch(cfg, 0, batch).items()}
+    args = (b["obs"], b["next_obses"], b["action"], b["reward"])
+    ms = time_kernel(lambda: agent.update_forward(*args, weights=b["weights"]), reps=5)
+    sdd, sdt = {k: v.to(dev) for k, v in sd.items()}, {k: v.to(dev) for k, v in sd_t.items()}
+
+    def eager():
+        with torch.device(dev):
+            O.update_forward(sdd, sdt, cfg, b)
+    ms_e = time_kernel(eager, reps=5)
+    bc = synth.make_update_batch(cfg, 0, batch)
+    t = []
+    for _ in range(4):
+        t0 = time.perf_counter(); O.update_forward(sd, sd_t, cfg, bc); t.append((time.perf_counter() - t0) * 1e3)
+    L, A, M = cfg.latent_dim, cfg.action_dim, cfg.mlp_dim
+    from tdmpc_b200.accounting import mlp_flops
+    f_dyn, f_rew, f_pi, f_q = mlp_flops(L, A, M)
+    f_enc = 2 * (cfg.obs_shape[0] * cfg.enc_dim + cfg.enc_dim * L)
+    flop = batch * (f_enc + cfg.horizon * (f_dyn + f_rew + 2 * f_q + 2 * f_enc + f_pi + 2 * f_q))
+    return {"workload": f"TDMPC.update forward (losses, TD targets, priorities): cfg3 dims, batch {batch}, H = {cfg.horizon}, fp32",
+            "ms_per_call": ms, "incl": "weight-change check + target re-pack + batch-mean reductions (host syncs)", "flop_per_call": flop,
+            "tflops_fp32": flop / (ms * 1e-3) / 1e12, "gpu_eager_ms": ms_e, "cpu_port_ms": float(np.median(t)), "cpu_threads": torch.get_num_threads()}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -631,6 +663,7 @@ def main():
         extra["cfg4_b256"] = icem_batched(dev, args.precision, 256, False, roofline=True)
         if world == 1:
             extra["replay_sample_1m"] = replay_extra(dev, measured_peaks()[2])
+            extra["update_forward_b512"] = update_forward_extra(dev)
         # the batched environment-stepping loop (tdmpc_b200.PlanLoop): numpy observations in, numpy
         # actions out, one pinned H2D + one CUDA-graph replay of the whole plan + one D2H per step (wall clock, host included)
         from tdmpc_b200 import PlanLoop

@@ -629,7 +629,9 @@ class TDMPC:
                                            enc_layernorm="_encoder.3.weight" in self.model_target.state_dict(),
                                            precision="fp32", device=self.device)
         pt = self._planner_target
-        pt.sync_weights(self.model_target)
+        # always re-packed: the reference moves the target with `p_target.data.lerp_(p.data, tau)` (helper.ema, helper.py:48-52),
+        # and writes through `.data` do not bump Tensor._version, which is what sync_weights watches
+        pt.sync_weights(self.model_target, force=True)
         H = int(cfg.horizon)
         dev = self.device
         obs = _f32(obs, dev); B = obs.shape[0]
