@@ -15,7 +15,8 @@ so each sample has (approximately) unit variance.
 
 Because every sample is a fixed linear map of white Gaussians, ``synthesis_matrix``
 below returns that map explicitly; the CUDA sampler multiplies white noise by the same
-matrix, which is how the device generator is validated (tests/test_colored_noise.py).
+matrix, which is how the device generator is validated (tests/test_oracle_golden.py::test_colored_noise_matrix_is_the_generator,
+tests/test_gpu_parity.py::test_icem_builtin_colored_sampler_statistics).
 """
 import numpy as np
 
