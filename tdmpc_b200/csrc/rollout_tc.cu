@@ -43,6 +43,7 @@ constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
 constexpr int MAX_JOBS = 22 * TDMPC_MAX_H + 20;
 constexpr uint32_t TM_ACC = 0, TM_A = 256;
+constexpr uint32_t TM_ACC2 = 384;           // third accumulator of the layer-1 jobs (F_ACC2): the columns of the h1 chunks 2 and 3
 constexpr uint32_t TM_X = 256, TM_Y = 384;  // DRNN: gh_n and gi_n of the newval gate, inside the (then idle) h1 region
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 232448;
@@ -63,6 +64,8 @@ struct KParams {
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
   uint32_t jw[MAX_JOBS];
   int one;                     // always 1 (an opaque branch condition: tc_prims.cuh, tmem_drain_aux)
+  int fast;                    // 1: the job list is the plain value-mode schedule of the MLP model (17 jobs per step, then the terminal
+                               //    policy and the Q heads): the MMA warp and the epilogue walk the steps with structured loops
   unsigned int* tile_counter;  // dynamic tile scheduler: tickets handed out so far in this launch (zero between launches)
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter space");
@@ -88,6 +91,10 @@ __device__ __forceinline__ float tanh_bf16(float x) {
   float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
+// A value the compiler must treat as unknown at every call (no constant propagation, no hoisting out of loops), but whose range
+// it knows: the fast paths pass the chain index through this, so that the job's type and flags stay compile-time constants
+// while the chain's parameter pointers are NOT loop invariants that would be hoisted into registers held across the epilogues.
+__device__ __forceinline__ int opaque3(int x) { asm volatile("" : "+r"(x)); return x & 7; }
 __device__ __forceinline__ float4 ldg4(const float* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
 
 __device__ __forceinline__ int job_tiles(const TcModel& m, uint32_t job) {
@@ -180,7 +187,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   // when it starts on tile n and publishes it through a 4-entry ring (tq_full: one arrival per entry use); all roles read the
   // ring in order.  They stay within a tile of each other (weight ring, accumulator and operand barriers), so an entry is
   // never overwritten before its last reader is done.
-  uint64_t* tq_full = d3_full + 1;
+  uint64_t* acc2_full = d3_full + 1;     // third accumulator (F_ACC2): complete / drained
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint64_t* tq_full = acc2_empty + 1;
   uint32_t* tile_q = reinterpret_cast<uint32_t*>(tq_full + 4);
   uint32_t* tmem_slot = tile_q + 4;
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
     mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(r_ready, 128); mbar_init(u_ready, 128);
     mbar_init(d3_full, 1);
+    mbar_init(acc2_full, 1); mbar_init(acc2_empty, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&tq_full[i], 1);
     fence_barrier_init();
   }
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       // predicate sits inside the asm statements (tc_prims.cuh, umma_*_p), which keeps the operands in uniform registers.
       const uint32_t lead = elect_one() ? 1u : 0u;
       uint32_t stage = 0, wphase = 0;
-      uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
+      uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0, a2cnt = 0;
       // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
       // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
       // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
@@ -289,8 +299,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       // issue; tile_release(slot) commits the slot that was just consumed.
       uint32_t ready = 0;                    // result of the early probe of w_full[stage]
       uint32_t cur_stage = 0;
+#ifdef TDMPC_TRACE_WAITS
+      long long tw[3] = {0, 0, 0};            // diagnosis build: cycles this job spent waiting for {accumulator, weight tile, operand data}
+#define TW(k, stmt) do { const long long _t0 = clock64(); stmt; tw[k] += clock64() - _t0; } while (0)
+#else
+#define TW(k, stmt) do { stmt; } while (0)
+#endif
       auto tile_acquire = [&]() -> uint32_t {
-        if (!ready) mbar_wait(&w_full[stage], wphase, 2);
+        if (!ready) TW(1, mbar_wait(&w_full[stage], wphase, 2));
         tcgen05_fence_after();
         cur_stage = stage;
         if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
@@ -301,19 +317,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         umma_commit_p(&w_empty[cur_stage], lead);
       };
       auto acc_acquire = [&](int b) {
-        mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
+        TW(0, mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3));
         ++ecnt[b];
       };
       auto h1_wait = [&](int c) {
-        mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
+        TW(2, mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4));
         h1_phase ^= 1u << c;
       };
       auto xs_wait = [&](int c) {
-        mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
+        TW(2, mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5));
         xs_phase ^= 1u << c;
       };
       uint32_t hs_phase = 0;
       const uint32_t hs_addr = smem_u32(hs);
+      // Staged schedule (F_CP): h1 chunk c (k-blocks 2c, 2c+1) was written to XS by a layer-1 epilogue that ran while the tensor
+      // pipe still read the TMEM h1 buffer; move it there now.  tcgen05.cp executes in issue order with this thread's MMAs: behind
+      // the reward chain's layer-2 MMAs (the last readers of the buffer), ahead of the MMAs that consume the copy.
+      auto h1_stage = [&](int c) {
+        xs_wait(c);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int kb = 2 * c + k2;
+          const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tmem_cp_p(tmem + TM_A + kb * 32 + ks * 8, umma_desc_make(alo + 2 * ks), lead);
+        }
+      };
       // one k-block (<= 4 k-steps of 16) with both operands in shared memory
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
         const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
@@ -328,20 +358,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         else kblock_ss(d, za_addr + kb * TILE_BYTES, b_addr, idesc, min(4, ks1_total - kb * 4), first);
       };
 
-      for (int it = 0; next_tile() >= 0; ++it)
-        for (int j = 0; j < kp.njobs; ++j) {
-          const uint32_t job = kp.jw[j];
+      for (int it = 0; next_tile() >= 0; ++it) {
+        // one job's MMAs; as in the epilogue, the fast path calls this with constant job words
+        auto mma_job = [&](const uint32_t job, const int j) __attribute__((always_inline)) {
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
           const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
-          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
+          if (flags & F_WAIT_ZA) { TW(2, mbar_wait(za_full, za_phase, 6)); za_phase ^= 1; }
           if (DRNN && (flags & F_WAIT_HS)) { mbar_wait(hs_full, hs_phase, 10); hs_phase ^= 1; tcgen05_fence_after(); }
           if (!DRNN && (flags & F_BUF0)) nbuf = 0;
+          const bool staged = !DRNN && (flags & F_CP);
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
-            acc_acquire(b);
+            const bool acc2 = !DRNN && (flags & F_ACC2) && chunk == 2;        // third accumulator; the ping-pong count goes on as if b were used
+            if (acc2) { TW(0, mbar_wait(acc2_empty, (a2cnt & 1) ^ 1, 3)); ++a2cnt; }
+            else acc_acquire(b);
             tcgen05_fence_after();
-            const uint32_t d = tmem + TM_ACC + b * 128;
+            const uint32_t d = acc2 ? tmem + TM_ACC2 : tmem + TM_ACC + b * 128;
             if (DRNN && (flags & F_A_HS)) {
               // prior / reward layer 1 of the DRNN model: A = the hidden state h' (K = 128)
               for (int kb = 0; kb < 2; ++kb) {
@@ -356,7 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 tile_release();
               }
             }
-            umma_commit_p(&acc_full[b], lead);
+            umma_commit_p(acc2 ? acc2_full : &acc_full[b], lead);
             // every MMA issued so far -- the parked layer 3 and all layer-1 jobs that read this step's [z,a] -- complete
             if (!DRNN && (flags & F_D3)) umma_commit_p(d3_full, lead);
           } else if (DRNN && type == J_G) {
@@ -404,8 +437,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
                 const int kb = kb0 + k4;
-                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
-                mbar_wait(&w_full[k4], wphase, 2);
+                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
+                TW(1, mbar_wait(&w_full[k4], wphase, 2));
                 tcgen05_fence_after();
                 const uint32_t blo = ring_lo[k4];
                 const uint32_t a = tmem + TM_A + kb * 32;
@@ -418,7 +451,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             } else {
               for (int k4 = 0; k4 < 4; ++k4) {
                 const int kb = kb0 + k4;
-                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
                 const uint32_t wt = tile_acquire();
                 const uint32_t blo = umma_desc_lo(wt);
                 const uint32_t a = tmem + TM_A + kb * 32;
@@ -450,8 +483,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int kb = 0; kb < 8; ++kb) {
                 const int st = kb & 3;
-                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
-                mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
+                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
+                TW(1, mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2));
                 tcgen05_fence_after();
                 {
                   const uint32_t blo = ring_lo[st];
@@ -462,10 +495,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 }
               }
               ready = 0;                       // slot 0 again, same parity: the early probe must be redone
+            } else if (S == 4 && stage == 2) {
+              // the same with the ring half a turn on (staged schedule: two single-tile layer-1 jobs precede this one):
+              // k-block kb sits in slot (kb + 2) & 3, the parity flips after two and again after six k-blocks
+#pragma unroll
+              for (int kb = 0; kb < 8; ++kb) {
+                const int st = (kb + 2) & 3;
+                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
+                TW(1, mbar_wait(&w_full[st], wphase ^ (uint32_t)(((kb + 2) >> 2) & 1), 2));
+                tcgen05_fence_after();
+                {
+                  const uint32_t blo = ring_lo[st];
+                  const uint32_t a = tmem + TM_A + kb * 32;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
+                  umma_commit_p(&w_empty[st], lead);
+                }
+              }
+              ready = 0;                       // slot 2 again, same parity
             } else {
 #pragma unroll
               for (int kb = 0; kb < 8; ++kb) {
-                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
                 const uint32_t wt = tile_acquire();
                 {
                   const uint32_t blo = umma_desc_lo(wt);
@@ -510,7 +561,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 const int st = kb >> 1;
                 if ((kb & 1) == 0) {
                   xs_wait(kb >> 1); tcgen05_fence_after();
-                  mbar_wait(&w_full[st], wphase, 2);
+                  TW(1, mbar_wait(&w_full[st], wphase, 2));
                   tcgen05_fence_after();
                 }
                 {
@@ -552,7 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 for (int kb = 0; kb < 8; ++kb) {
                   const int st = kb & 3;
                   if (c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-                  mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
+                  TW(1, mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2));
                   tcgen05_fence_after();
                   {
                     const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES), blo = ring_lo[st];
@@ -578,8 +629,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
           }
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2 + 1] = clock64();
+#ifdef TDMPC_TRACE_WAITS
+          if (tr) { unsigned long long* w = kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * 256 + 2 * MAX_JOBS * 2 + j * 3; w[0] = tw[0]; w[1] = tw[1]; w[2] = tw[2]; }
+          tw[0] = tw[1] = tw[2] = 0;
+#endif
           __syncwarp();
+        };
+        int j0 = 0;
+#ifdef TDMPC_TC_FAST
+        if (!DRNN && kp.fast) {
+#pragma unroll 1
+          for (int t = 0; t < p.H; ++t) {
+            const int jb = 17 * t;
+            mma_job(tc_job(J_L1, CH_DYN, 0, t, F_WAIT_ZA), jb);
+#pragma unroll 1
+            for (int c = 1; c < 4; ++c) mma_job(tc_job(J_L1, CH_DYN, c, t, F_ACC2), jb + c);
+            mma_job(tc_job(J_L2, CH_DYN, 0, t, 0), jb + 4);
+#pragma unroll 1
+            for (int c = 1; c < 4; ++c) mma_job(tc_job(J_L2, CH_DYN, c, t, 0), jb + 4 + c);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) mma_job(tc_job(J_L1, CH_REW, c, t, F_ACC2), jb + 8 + c);
+            mma_job(tc_job(J_L3, CH_DYN, 0, t, 0), jb + 12);
+            mma_job(tc_job(J_L2, CH_REW, 0, t, 0), jb + 13);
+#pragma unroll 1
+            for (int c = 1; c < 4; ++c) mma_job(tc_job(J_L2, CH_REW, c, t, 0), jb + 13 + c);
+          }
+          j0 = 17 * p.H;
         }
+#endif
+        for (int j = j0; j < kp.njobs; ++j) mma_job(kp.jw[j], j);
+      }
     }
   } else {
     // ============================== epilogue: two warpgroups, thread = trajectory ==============================
@@ -595,6 +674,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
     uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
+    uint32_t a2f = 0, a2e = 0;                      // third accumulator: phases of acc2_full (owner group) / acc2_empty (chunk 3's group)
     uint32_t d3_phase = 0;                          // overlapped schedule: phase of d3_full (group 0 only)
     uint32_t x_phase = 0, ga = 0;                  // DRNN: phase of x_full / r_ready / u_ready, group that owns the reset gate of this step
     float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
@@ -604,15 +684,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     float* m_ssq = xch + (1 * 2 + grp) * 128;
     float* m_dot = xch + (2 * 2 + grp) * 128;
 
+    unsigned long long* trx = nullptr;              // trace: {accumulator ready, accumulator released} of the current job (or null)
     auto acc_wait = [&]() {
       mbar_wait(&acc_full[grp], fcnt & 1, 7);
       ++fcnt;
+      if (trx) trx[0] = clock64();
     };
     // early release: the accumulator goes back to the MMA warp as soon as it sits in registers (tmem_drain_aux)
     const int go_math = (kp.debug & 4) ? 0 : kp.one;     // experiment (bit 2): skip the activation math of the MLP layers (power probe, wrong results)
     const bool late_release = (kp.debug & 2) != 0;      // experiment: release after the activation math, as before
     auto acc_release = [&]() {
       if (!late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
+      if (trx) trx[1] = clock64();
     };
     auto acc_release_late = [&]() {
       if (late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
@@ -671,20 +754,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         mbar_arrive(za_full);
       }
 
-      for (int j = 0; j < kp.njobs; ++j) {
-        const uint32_t job = sjobs[j];
+      // One job of this tile as seen by my epilogue group.  Called by the generic walk over the job list and -- with job words
+      // whose type, chain and flags are compile-time constants, so that the decode and every branch below fold away -- by the
+      // structured fast path of the plain value-mode schedule (the generic walk costs ~200 instructions per job per group).
+      auto epi_job = [&](const uint32_t job, const int j) __attribute__((always_inline)) {
         const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, t = (job >> 8) & 31, flags = job >> 13;
         const TcChain& ch = m.chain[chain];
         const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && threadIdx.x % 128 == 0;
         unsigned long long* trp = kp.trace + ((1 + grp) * MAX_JOBS + j) * 2;
+        trx = tr ? kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * 256 + (grp * MAX_JOBS + j) * 2 : nullptr;
 
         if (DRNN && type >= J_G) {
           // ---- NormGRUCell (models/rnns.py:19-29): thread = trajectory, LayerNorm over the 128 gate values in-thread ----
-          if (type == J_GH) continue;                                  // MMAs only
+          if (type == J_GH) return;                                  // MMAs only
           if (type == J_G) {
             const int b = nbuf; nbuf ^= 1;
             if (chunk == 0) ga = (uint32_t)b;
-            if (b != grp) continue;
+            if (b != grp) return;
             if (tr) trp[0] = clock64();
             const uint32_t acc = tlane + TM_ACC + b * 128;
             acc_wait();
@@ -719,7 +805,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tcgen05_fence_before();
             mbar_arrive(chunk == 0 ? r_ready : u_ready);
             if (tr) trp[1] = clock64();
-            continue;
+            return;
           }
           // J_GI: n = tanh(LN_n(gi_n + r * gh_n)); h' = u * n + (1 - u) * h  (rnns.py:27-28).  Both groups work on it, 64
           // columns each (it sits on the step's critical path); x = gi_n + r * gh_n stays in registers between the
@@ -786,20 +872,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           epi_bar_sync();                                   // both halves have read the gates (and the exchange slots)
           if (ga == (uint32_t)grp) { mbar_arrive(&acc_empty[0]); mbar_arrive(&acc_empty[1]); }
           if (tr) trp[1] = clock64();
-          continue;
+          return;
         }
         if (type <= J_L3) {
-          if (!DRNN && type == J_L3 && (flags & F_PARK)) continue;             // MMAs only (overlapped schedule)
-          if (!DRNN && type == J_L2 && (flags & F_KLO)) continue;              // first half of a split layer-2 chunk: MMAs only
+          if (!DRNN && type == J_L3 && (flags & F_PARK)) return;             // MMAs only (overlapped schedule)
+          if (!DRNN && type == J_L2 && (flags & F_KLO)) return;              // first half of a split layer-2 chunk: MMAs only
           const bool epi_only = !DRNN && type == J_L3 && (flags & F_EPI);      // epilogue of the parked layer 3: group 0
-          if (epi_only && grp != 0) continue;
+          if (epi_only && grp != 0) return;
           if (!DRNN && (flags & F_BUF0)) nbuf = 0;
           int b = grp;
           if (!epi_only) { b = nbuf; nbuf ^= 1; }
           const bool mine = b == grp;
           if (tr && (mine || (type == J_L2 && chain == CH_REW && chunk == 3))) trp[0] = clock64();
           if (type == J_L1) {
-            if (!mine) continue;
+            // third accumulator: both groups count its uses (its owner alternates with the ping-pong), one of them waits
+            uint32_t a2ph = 0;
+            if (!DRNN && (flags & F_ACC2)) { if (chunk == 2) a2ph = a2f++ & 1u; else if (chunk == 3) a2ph = a2e++ & 1u; }
+            if (!mine) return;
             if (!DRNN && (flags & F_TO_XS)) {
               // reward chain of the overlapped schedule: h1 chunk = ELU(acc + b1) -> bf16 -> XS (the layer-3 MMAs that read
               // XS were issued before this job's MMAs, so the accumulator barrier covers them)
@@ -824,7 +913,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               mbar_arrive(&xs_full[chunk]);
               acc_release_late();
               if (tr) trp[1] = clock64();
-              continue;
+              return;
             }
             if (DRNN && (flags & F_BN)) {
               // prior MLP layer 1: Linear, eval-mode BatchNorm1d (folded: y = acc * scale + shift'), ELU -> TMEM h1
@@ -853,16 +942,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               tcgen05_fence_before();
               mbar_arrive(&h1_full[chunk]);
               acc_release_late();
-              continue;
+              return;
             }
             // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
             const float* bias = ch.b1 + chunk * 128;
             const uint32_t dst = tlane + TM_A + chunk * 64;
+            const bool acc2 = !DRNN && (flags & F_ACC2) && chunk == 2;       // third accumulator (tc_model.cuh)
+            const bool acc2w = !DRNN && (flags & F_ACC2) && chunk == 3;      // my h1 columns are the tail of that accumulator
             float4 x0[8];
             load8(bias, 0, x0);
-            acc_wait();
+            if (acc2) { mbar_wait(acc2_full, a2ph, 7); if (trx) trx[0] = clock64(); }
+            else acc_wait();
             tcgen05_fence_after();
-            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+            auto release = [&]() {
+              if (acc2) { tcgen05_fence_before(); mbar_arrive(acc2_empty); if (trx) trx[1] = clock64(); }
+              else acc_release();
+              if (acc2w) { mbar_wait(acc2_empty, a2ph, 7); tcgen05_fence_after(); }
+            };
+            tmem_drain_aux(acc2 ? tlane + TM_ACC2 : tlane + TM_ACC + b * 128, x0, go_math, release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
               uint32_t o[16];
 #pragma unroll
@@ -977,7 +1074,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             if (tr && (mine || (!to_xs && chunk == 3))) trp[1] = clock64();
           } else {
-            if (!mine) continue;
+            if (!mine) return;
             // the next step's actions of this row are fetched before waiting for the accumulator
             float an[8];
 #pragma unroll
@@ -1173,7 +1270,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           mbar_arrive(&acc_empty[grp]);
           if (tr) trp[1] = clock64();
         }
+      };
+      int j0 = 0;
+#ifdef TDMPC_TC_FAST      // experiment (DESIGN.md 4.1, round 2 second session): measured slower -- the specialised copies do not share instruction-cache lines
+      if (!DRNN && kp.fast) {
+        // plain value-mode schedule (build_jobs): per step L1 dyn x4, L2 dyn x4, L1 rew x4, L3 dyn, L2 rew x4
+#pragma unroll 1
+        for (int t = 0; t < p.H; ++t) {
+          const int jb = 17 * t;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L1, opaque3(CH_DYN), c, t, F_ACC2), jb + c);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L2, opaque3(CH_DYN), c, t, 0), jb + 4 + c);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L1, opaque3(CH_REW), c, t, F_ACC2), jb + 8 + c);
+          if (t == p.H - 1) epi_job(tc_job(J_L3, opaque3(CH_DYN), 0, t, F_LAST_STEP), jb + 12);
+          else epi_job(tc_job(J_L3, opaque3(CH_DYN), 0, t, 0), jb + 12);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L2, opaque3(CH_REW), c, t, 0), jb + 13 + c);
+        }
+        j0 = 17 * p.H;
       }
+#endif
+      for (int j = j0; j < kp.njobs; ++j) epi_job(sjobs[j], j);
       if (kp.trace && blockIdx.x == 0 && threadIdx.x == 128 && it < 128) {
         unsigned long long ns;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
@@ -1235,6 +1354,9 @@ int launch_pack(const float* W, int N, int K, uint8_t* dst, int n_chunks, int nk
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// value-mode schedule of the MLP model: 0 plain, 1 / 2 staged (two job orders); TDMPC_TC_STAGED overrides the default
+int staged_schedule() { const char* e = getenv("TDMPC_TC_STAGED"); return e ? atoi(e) : 0; }
+
 std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) {
   std::vector<uint32_t> j;
   auto chain12 = [&](int type, int chain, int t, int first_flags) {
@@ -1290,7 +1412,33 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
     j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
     return j;
   }
-  if (mode == MODE_VALUE && !getenv("TDMPC_TC_OVERLAP")) {
+  if (mode == MODE_VALUE && staged_schedule() && !getenv("TDMPC_TC_OVERLAP")) {
+    // Staged schedule.  In the plain schedule the tensor pipe idles through every layer-1 epilogue (the one TMEM h1 buffer makes
+    // each chain's layer 2 wait for its own layer 1: ~12 k of a 41 k-cycle step).  Here the layer 1 of the NEXT consumer of z'
+    // (N: dynamics of step t+1, or the terminal policy) is interleaved with the reward chain's 512 x 512 layer (R, TS mode from
+    // the h1 buffer): its epilogue writes the activation to XS -- idle between the dynamics' layer 3 and the next layer-2
+    // epilogue -- and the consumer's first layer-2 job copies it into the h1 buffer (tcgen05.cp, F_CP) once R has been issued.
+    // R0 R1 first: they only need the reward's h1, while N0 has to wait for z' (layer 3 + its epilogue); R3 last, so the
+    // reward combine (a barrier over both epilogue groups) does not hold up a layer-1 epilogue the copy is waiting for.
+    chain12(J_L1, CH_DYN, 0, F_WAIT_ZA);
+    for (int t = 0; t < H; ++t) {
+      const bool last = t == H - 1;
+      chain12(J_L2, CH_DYN, t, t > 0 ? F_CP : 0);
+      chain12(J_L1, CH_REW, t, 0);
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, last ? F_LAST_STEP : 0));
+      const int nch = last ? CH_PI : CH_DYN, nt = last ? 0 : t + 1;
+      auto R = [&](int c) { j.push_back(tc_job(J_L2, CH_REW, c, t, 0)); };
+      auto N = [&](int c) { j.push_back(tc_job(J_L1, nch, c, nt, F_TO_XS | (c == 0 ? F_WAIT_ZA : 0))); };
+      if (staged_schedule() == 2) { R(0); R(1); N(0); N(1); R(2); N(2); N(3); R(3); }
+      else { R(0); R(1); N(0); N(1); N(2); N(3); R(2); R(3); }      // keeps every 512 x 512 job on slot 0 of a 4-slot ring for any k-block count
+    }
+    chain12(J_L2, CH_PI, 0, F_CP);
+    j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
+    j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
+    j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
+    j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+  } else if (mode == MODE_VALUE && !getenv("TDMPC_TC_OVERLAP")) {
     // the plain schedule (default): dynamics and reward alternate on the one TMEM h1 buffer
     for (int t = 0; t < H; ++t) {
       chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
@@ -1513,7 +1661,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   // (K = 138 -> 128 + 16) that is the difference between a 2-slot and a 3-slot weight ring
   m.za_compact = (!drnn && nkb1 >= 2 && m.K1p - 64 * (nkb1 - 1) == 16 && !getenv("TDMPC_TC_NO_COMPACT")) ? 1 : 0;
   m.za_bytes = m.za_compact ? (nkb1 - 1) * TILE_BYTES + K16_BLOCK_BYTES : nkb1 * TILE_BYTES;
-  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 26) * 8 + 32 + 1024;
+  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 28) * 8 + 32 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
@@ -1527,6 +1675,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   m.exact_act = c.precision == TDMPC_PREC_BF16_EXACT ? 1 : 0;
+  m.fast_value = (!drnn && staged_schedule() == 0 && !getenv("TDMPC_TC_OVERLAP") && !getenv("TDMPC_TC_SPLIT") && !getenv("TDMPC_TC_NOFAST")) ? 1 : 0;
   { const char* e = getenv("TDMPC_TC_DEBUG"); m.debug = e ? atoi(e) : 0; }
   m.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) m.producers = v; }
@@ -1540,7 +1689,7 @@ void tc_release_host(TcModel* m) {
 
 static unsigned long long* g_tc_trace = nullptr;
 void tc_set_trace(unsigned long long* dev_buf) { g_tc_trace = dev_buf; }
-int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256 + 4 * 256; }      // + end-of-tile stamps of block 0's first 128 tiles + per-block stats
+int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256 + 4 * 256 + 2 * MAX_JOBS * 2 + 3 * MAX_JOBS; }   // ... + MMA-warp wait cycles (-DTDMPC_TRACE_WAITS)      // ... + {accumulator ready, released} per group and job      // + end-of-tile stamps of block 0's first 128 tiles + per-block stats
 
 int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st) {
   if (p.H < 1 || p.H > TDMPC_MAX_H) return -1;
@@ -1556,6 +1705,11 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.tile_counter = m.tile_counter;
   kp.debug = m.debug;
   kp.producers = m.producers;
+#ifdef TDMPC_TC_FAST
+  kp.fast = (m.fast_value && p.mode == MODE_VALUE && kp.njobs == 17 * p.H + 13) ? 1 : 0;
+#else
+  kp.fast = 0;
+#endif
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   if (kp.njobs <= 0 || kp.njobs > MAX_JOBS || !m.jobs_host) return -1;
   memcpy(kp.jw, m.jobs_host + m.jobs_off[p.mode][p.H], sizeof(uint32_t) * kp.njobs);

@@ -292,6 +292,13 @@ __device__ __forceinline__ void umma_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead) : "memory");
 }
+// shared memory -> tensor memory, 128 lanes x 256 bits: one K = 16 slice of a K-major bf16 operand tile (the descriptor an SS-mode
+// A operand would use) lands as 8 columns of the TS-mode A operand (lane = row, column = two consecutive k).  Executes in issue
+// order with the MMAs of the same thread (tools/tc_cp_probe.cu checks the layout).  SASS: UTCCP.
+__device__ __forceinline__ void tmem_cp_p(uint32_t taddr, uint64_t sdesc, uint32_t lead) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q tcgen05.cp.cta_group::1.128x256b [%0], %1;\n\t}" ::"r"(taddr), "l"(sdesc), "r"(lead) : "memory");
+}
 __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t lead) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(lead) : "memory");
