@@ -316,12 +316,59 @@ typedef struct {
 
 TDMPC_API int tdmpc_update_forward(tdmpc_handle* online, tdmpc_handle* target, const tdmpc_update_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole training step: TDMPC.update (algorithm/tdmpc.py:191-245) with _td_target (:180-189),
+ * update_pi (:165-178), torch.nn.utils.clip_grad_norm_, torch.optim.Adam.step (both optimisers, default betas / eps, no weight
+ * decay) and helper.ema (helper.py:48-52) for one replay batch -- forward, backward through the H-step latent unroll, optimiser
+ * and target update -- fp32 on the device.  State observations, MLP dynamics, plain encoder (no LayerNorm variant).
+ *
+ * The PARAMETERS ARE UPDATED IN PLACE through the pointers of `online` (model) and `target` (model_target): the const in
+ * tdmpc_weights is cast away.  After the call every handle that packed these parameters must be given them again
+ * (tdmpc_set_weights).  Flat arenas (`adam_*`, `grads`) hold one float per parameter in state_dict order:
+ *   _encoder.0.{weight,bias} _encoder.2.{weight,bias} | _dynamics.{0,2,4}.{weight,bias} | _reward.{0,2,4}.{weight,bias} |
+ *   _pi.{0,2,4}.{weight,bias} | _Q1.0.{weight,bias} _Q1.1.{weight,bias} _Q1.3.{weight,bias} _Q1.4.{weight,bias} _Q1.6.{weight,bias} | _Q2...
+ * (tdmpc_train_param_count returns the total and the [begin, end) range of the _pi block).  The model optimiser never touches
+ * the _pi block of its arenas (those gradients are None in the reference), the policy optimiser has arenas of the _pi size. */
+typedef struct {
+  tdmpc_weights online, target;    /* device pointers of agent.model / agent.model_target; updated in place                     */
+  int32_t batch, horizon;
+  double discount, rho;            /* cfg.discount, cfg.rho                                                                    */
+  float min_std;
+  float consistency_coef, reward_coef, value_coef;
+  double lr, beta1, beta2, adam_eps;   /* torch.optim.Adam(lr=cfg.lr): betas (0.9, 0.999), eps 1e-8                            */
+  double grad_clip_norm;           /* cfg.grad_clip_norm                                                                       */
+  double tau;                      /* cfg.tau                                                                                  */
+  int32_t update_target;           /* step % cfg.update_freq == 0 (tdmpc.py:236)                                               */
+  int64_t adam_step, pi_adam_step; /* optimiser step counts BEFORE this call (state['step']); this call is step + 1            */
+  float* adam_m; float* adam_v;    /* [param_count] exp_avg / exp_avg_sq of agent.optim                                        */
+  float* pi_adam_m; float* pi_adam_v;  /* [pi_count] of agent.pi_optim                                                         */
+  float* grads;                    /* [param_count] out: the clipped gradients of the model step; _pi block: the clipped policy gradients */
+  const float* obs;                /* [batch, obs_dim]                                                                          */
+  const float* next_obses;         /* [horizon, batch, obs_dim]                                                                 */
+  const float* action;             /* [horizon, batch, action_dim]                                                              */
+  const float* reward;             /* [horizon, batch]                                                                          */
+  const float* weights;            /* [batch] importance weights of the prioritised sample                                      */
+  const float* noise_pi;           /* [horizon, batch, action_dim] draws of pi() inside _td_target, or NULL: Philox stream 0    */
+  const float* noise_pi_update;    /* [horizon + 1, batch, action_dim] draws of pi() inside update_pi, or NULL: Philox stream 1 */
+  uint64_t seed, call;
+  float* metrics;                  /* out [8] device: consistency_loss, reward_loss, value_loss, total_loss, weighted_loss (the
+                                    * means the reference returns), grad_norm (before clipping), pi_loss, pi grad norm         */
+  float* priorities;               /* out [batch]: priority_loss.clamp(max=1e4), what update() hands to update_priorities       */
+  void* workspace; int64_t workspace_bytes;   /* device scratch of tdmpc_train_workspace_bytes(cfg, batch, horizon)            */
+} tdmpc_train_args;
+
+TDMPC_API int64_t tdmpc_train_param_count(const tdmpc_model_cfg* cfg, int64_t* pi_begin, int64_t* pi_end);
+TDMPC_API int64_t tdmpc_train_workspace_bytes(const tdmpc_model_cfg* cfg, int32_t batch, int32_t horizon);
+/* `h`: any handle of the model's shape on the device (error reporting, launch counting); its packed weights are not used. */
+TDMPC_API int tdmpc_update(tdmpc_handle* h, const tdmpc_train_args* args, void* stream);
+
 /* Number of kernels of THIS library launched by the handle so far (bench.py's gpu_launches). */
 TDMPC_API uint64_t tdmpc_launch_count(const tdmpc_handle* h);
 
 /* Layout self-check for FFI bindings: writes up to n of {sizeof(tdmpc_model_cfg), sizeof(tdmpc_weights),
  * sizeof(tdmpc_plan_args), offsetof(plan_args, obs), offsetof(.., seed), offsetof(.., action), offsetof(.., tap_z0),
- * sizeof(tdmpc_replay_sample_args), sizeof(tdmpc_replay_gather_args), sizeof(tdmpc_update_args)} and returns how many values exist. */
+ * sizeof(tdmpc_replay_sample_args), sizeof(tdmpc_replay_gather_args), sizeof(tdmpc_update_args), sizeof(tdmpc_train_args)} and returns
+ * how many values exist. */
 TDMPC_API int32_t tdmpc_abi_sizes(int32_t* out, int32_t n);
 
 /* Build information: "sm_100a;tcgen05=1;..." */

@@ -18,6 +18,7 @@ Reference lines followed (all under /root/reference/src):
   algorithm/tdmpc.py:83-92     TDMPC.estimate_value
   algorithm/tdmpc.py:94-163    TDMPC.plan
   algorithm/tdmpc.py:180-228   TDMPC._td_target / update (forward half: loss terms, TD targets, priorities)
+  algorithm/tdmpc.py:165-245   TDMPC.update_pi / update as a whole (update_step: autograd over the forward above, clip, Adam, ema)
   algorithm/helper.py:71-96    TruncatedNormal.sample
   algorithm/helper.py:119-133,156-176,197-201   enc / dmlab_enc_norm / mlp / q layer stacks
   algorithm/helper.py:639-652  linear_schedule
@@ -113,7 +114,7 @@ def told_next(sd, z, a, quant=False):
     return mlp3(sd, "_dynamics", x, quant), mlp3(sd, "_reward", x, quant)
 
 
-def told_pi(sd, z, std=0.0, eps=None, quant=False):
+def told_pi(sd, z, std=0.0, eps=None, quant=False, ste=False):
     """TOLD.pi (tdmpc.py:39-45) + TruncatedNormal.sample(clip=0.3) (helper.py:86-96).
     `eps` is the standard-normal draw the reference takes from _standard_normal."""
     # the policy head is a tensor-core GEMM in the kernel for every action_dim (N padded to 16), so its operands are
@@ -123,6 +124,8 @@ def told_pi(sd, z, std=0.0, eps=None, quant=False):
         e = eps * (torch.ones_like(mu) * std)
         e = torch.clamp(e, -0.3, 0.3)
         x = mu + e
+        if ste:      # TruncatedNormal._clamp (helper.py:81-84): same value, gradient passed straight through (update_pi)
+            return x - x.detach() + torch.clamp(x, -1.0 + 1e-6, 1.0 - 1e-6).detach()
         return torch.clamp(x, -1.0 + 1e-6, 1.0 - 1e-6)
     return mu
 
@@ -534,9 +537,10 @@ def update_forward(sd, sd_target, cfg, batch):
         Q1, Q2 = told_Q(sd, z, action[t])
         z, reward_pred = told_next(sd, z, action[t])
         next_obs = next_obses[t]
-        next_z = told_h(sd_target, next_obs)
-        nz_on = told_h(sd, next_obs)                                  # _td_target: ONLINE encoder and policy, TARGET Q heads
-        td_target = reward[t] + cfg.discount * torch.min(*told_Q(sd_target, nz_on, told_pi(sd, nz_on, cfg.min_std, batch["noise_pi"][t])))
+        with torch.no_grad():                                         # tdmpc.py:207-210 (matters when update_step differentiates this)
+            next_z = told_h(sd_target, next_obs)
+            nz_on = told_h(sd, next_obs)                              # _td_target: ONLINE encoder and policy, TARGET Q heads
+            td_target = reward[t] + cfg.discount * torch.min(*told_Q(sd_target, nz_on, told_pi(sd, nz_on, cfg.min_std, batch["noise_pi"][t])))
         zs.append(z)
         rho = cfg.rho ** t
         consistency_loss = consistency_loss + rho * torch.mean(F.mse_loss(z, next_z, reduction="none"), dim=1, keepdim=True)
@@ -549,8 +553,89 @@ def update_forward(sd, sd_target, cfg, batch):
         cfg.value_coef * value_loss.clamp(max=1e4)
     weighted_loss = (total_loss * batch["weights"]).mean()
     return {"consistency": consistency_loss, "reward": reward_loss, "value": value_loss, "priority": priority_loss,
-            "total": total_loss, "weighted_loss": float(weighted_loss), "zs": torch.stack(zs),
+            "total": total_loss, "weighted_loss": float(weighted_loss.detach()), "zs": torch.stack(zs),
             "taps": {k: torch.stack(v) for k, v in taps.items()}}
+
+
+# ----------------------------------------------------------------------------- TDMPC.update, the whole step
+
+PI_KEYS = tuple(f"_pi.{i}.{s}" for i in (0, 2, 4) for s in ("weight", "bias"))
+
+
+def _clip_grad_norm(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ (norm_type 2, error_if_nonfinite False): returns the total norm, scales in place."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g, 2.0) for g in grads]), 2.0)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(coef)
+    return total
+
+
+def _adam_step(params, grads, state, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam, single-tensor path (torch/optim/adam.py::_single_tensor_adam; no amsgrad / weight decay / maximize).
+    `state[k]` = (exp_avg, exp_avg_sq), created as zeros on first use; `step` is the count AFTER this call."""
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    step_size = lr / bc1
+    bc2_sqrt = bc2 ** 0.5
+    for k, p in params.items():
+        g = grads[k]
+        if k not in state:
+            state[k] = (torch.zeros_like(p), torch.zeros_like(p))
+        m, v = state[k]
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / bc2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+
+
+def update_step(sd, sd_target, cfg, batch, opt=None, update_target=True):
+    """TDMPC.update (tdmpc.py:191-245) as a whole: forward (update_forward above), backward of weighted_loss / horizon,
+    clip_grad_norm_ + Adam over the model (the policy block has no gradient there), update_pi (tdmpc.py:165-178) on the
+    detached latents with the Q heads that were just stepped, its own clip + Adam, and helper.ema (helper.py:48-52).
+    `batch` additionally holds "noise_pi_update" [H+1,B,A], the draws of pi() inside update_pi.  `opt` carries the optimiser
+    state between calls: {"state": {}, "pi_state": {}, "step": 0, "pi_step": 0}.  Nothing is modified in place: returns
+    (metrics, new_sd, new_sd_target, grads, opt) with `grads` the CLIPPED gradients (the policy block: update_pi's)."""
+    opt = {"state": {}, "pi_state": {}, "step": 0, "pi_step": 0} if opt is None else \
+        {"state": {k: (a.clone(), b.clone()) for k, (a, b) in opt["state"].items()},
+         "pi_state": {k: (a.clone(), b.clone()) for k, (a, b) in opt["pi_state"].items()}, "step": opt["step"], "pi_step": opt["pi_step"]}
+    P = {k: v.clone().requires_grad_(k not in PI_KEYS) for k, v in sd.items()}
+    T = {k: v.clone() for k, v in sd_target.items()}
+    with torch.enable_grad():
+        o = update_forward(P, T, cfg, batch)
+        weighted = (o["total"] * batch["weights"]).mean()
+        (weighted * (1 / cfg.horizon)).backward()              # register_hook(grad * (1 / horizon)), tdmpc.py:224
+    model_keys = [k for k in sd if k not in PI_KEYS]
+    grads = {k: P[k].grad for k in model_keys}
+    grad_norm = _clip_grad_norm([grads[k] for k in model_keys], cfg.grad_clip_norm)
+    new = {k: v.detach().clone() for k, v in P.items()}
+    opt["step"] += 1
+    _adam_step({k: new[k] for k in model_keys}, grads, opt["state"], opt["step"], cfg.lr)
+    # update_pi: Q heads frozen (track_q_grad(False)), latents detached
+    Q = {k: v.clone() for k, v in new.items()}
+    for k in PI_KEYS:
+        Q[k] = new[k].clone().requires_grad_(True)
+    zs = o["zs"].detach()
+    with torch.enable_grad():
+        pi_loss = 0
+        for t in range(zs.shape[0]):
+            a = told_pi(Q, zs[t], cfg.min_std, batch["noise_pi_update"][t], ste=True)
+            q = torch.min(*told_Q(Q, zs[t], a))
+            pi_loss = pi_loss + (-q.mean() * (cfg.rho ** t))
+        pi_loss.backward()
+    pi_grads = {k: Q[k].grad for k in PI_KEYS}
+    pi_norm = _clip_grad_norm([pi_grads[k] for k in PI_KEYS], cfg.grad_clip_norm)
+    opt["pi_step"] += 1
+    _adam_step({k: new[k] for k in PI_KEYS}, pi_grads, opt["pi_state"], opt["pi_step"], cfg.lr)
+    if update_target:
+        for k in T:
+            T[k].lerp_(new[k], cfg.tau)
+    grads.update(pi_grads)
+    f = lambda x: float(x.detach())
+    metrics = {"consistency_loss": f(o["consistency"].mean()), "reward_loss": f(o["reward"].mean()),
+               "value_loss": f(o["value"].mean()), "pi_loss": f(pi_loss), "total_loss": f(o["total"].mean()),
+               "weighted_loss": f(weighted), "grad_norm": f(grad_norm), "pi_grad_norm": f(pi_norm),
+               "priorities": o["priority"].detach().clamp(max=1e4)}
+    return metrics, new, T, {k: g.detach() for k, g in grads.items()}, opt
 
 
 # ----------------------------------------------------------------------------- flop / step accounting (SURVEY 8d)

@@ -20,6 +20,7 @@ EXPORTS = [
     "tdmpc_encode", "tdmpc_estimate_value", "tdmpc_estimate_value_drnn", "tdmpc_pi_rollout", "tdmpc_select_update", "tdmpc_plan",
     "tdmpc_fill_noise", "tdmpc_launch_count", "tdmpc_build_info", "tdmpc_abi_sizes",
     "tdmpc_replay_workspace_bytes", "tdmpc_replay_sample", "tdmpc_replay_gather", "tdmpc_update_forward",
+    "tdmpc_train_param_count", "tdmpc_train_workspace_bytes", "tdmpc_update",
 ]
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -92,6 +93,23 @@ class UpdateArgs(C.Structure):
     ]
 
 
+class TrainArgs(C.Structure):
+    """tdmpc_train_args (include/tdmpc_b200.h): the whole training step."""
+    _fields_ = [
+        ("online", Weights), ("target", Weights),
+        ("batch", C.c_int32), ("horizon", C.c_int32), ("discount", C.c_double), ("rho", C.c_double), ("min_std", C.c_float),
+        ("consistency_coef", C.c_float), ("reward_coef", C.c_float), ("value_coef", C.c_float),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
+        ("grad_clip_norm", C.c_double), ("tau", C.c_double), ("update_target", C.c_int32),
+        ("adam_step", C.c_int64), ("pi_adam_step", C.c_int64),
+        ("adam_m", _fp), ("adam_v", _fp), ("pi_adam_m", _fp), ("pi_adam_v", _fp), ("grads", _fp),
+        ("obs", _fp), ("next_obses", _fp), ("action", _fp), ("reward", _fp), ("weights", _fp),
+        ("noise_pi", _fp), ("noise_pi_update", _fp),
+        ("seed", C.c_uint64), ("call", C.c_uint64),
+        ("metrics", _fp), ("priorities", _fp), ("workspace", _fp), ("workspace_bytes", C.c_int64),
+    ]
+
+
 def build(verbose=False):
     """Compile libtdmpc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     r = subprocess.run(["make", "-C", CSRC, "-j8", "all"], capture_output=True, text=True)
@@ -137,6 +155,11 @@ def load():
     lib.tdmpc_replay_sample.argtypes = [C.POINTER(ReplaySampleArgs), C.c_void_p]
     lib.tdmpc_replay_gather.argtypes = [C.POINTER(ReplayGatherArgs), C.c_void_p]
     lib.tdmpc_update_forward.argtypes = [H, H, C.POINTER(UpdateArgs), C.c_void_p]
+    lib.tdmpc_train_param_count.argtypes = [C.POINTER(ModelCfg), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.tdmpc_train_param_count.restype = C.c_int64
+    lib.tdmpc_train_workspace_bytes.argtypes = [C.POINTER(ModelCfg), C.c_int32, C.c_int32]
+    lib.tdmpc_train_workspace_bytes.restype = C.c_int64
+    lib.tdmpc_update.argtypes = [H, C.POINTER(TrainArgs), C.c_void_p]
     got = (C.c_int32 * 10)()
     lib.tdmpc_abi_sizes(got, 10)
     want = [C.sizeof(ModelCfg), C.sizeof(Weights), C.sizeof(PlanArgs), PlanArgs.obs.offset, PlanArgs.seed.offset,

@@ -154,7 +154,8 @@ extern "C" int32_t tdmpc_abi_sizes(int32_t* out, int32_t n) {
   const int32_t v[] = {(int32_t)sizeof(tdmpc_model_cfg), (int32_t)sizeof(tdmpc_weights), (int32_t)sizeof(tdmpc_plan_args),
                        (int32_t)offsetof(tdmpc_plan_args, obs), (int32_t)offsetof(tdmpc_plan_args, seed),
                        (int32_t)offsetof(tdmpc_plan_args, action), (int32_t)offsetof(tdmpc_plan_args, tap_z0),
-                       (int32_t)sizeof(tdmpc_replay_sample_args), (int32_t)sizeof(tdmpc_replay_gather_args), (int32_t)sizeof(tdmpc_update_args)};
+                       (int32_t)sizeof(tdmpc_replay_sample_args), (int32_t)sizeof(tdmpc_replay_gather_args), (int32_t)sizeof(tdmpc_update_args),
+                       (int32_t)sizeof(tdmpc_train_args)};
   const int32_t m = (int32_t)(sizeof(v) / sizeof(v[0]));
   for (int32_t i = 0; i < n && i < m; ++i) out[i] = v[i];
   return m;
@@ -397,6 +398,42 @@ extern "C" int tdmpc_update_forward(tdmpc_handle* h, tdmpc_handle* ht, const tdm
   p.total = a->total_loss; p.zs = a->zs; p.td_target = a->td_target; p.q1 = a->q1; p.q2 = a->q2; p.reward_pred = a->reward_pred;
   if (launch_update_fwd(h->m32, ht->m32, p, (cudaStream_t)stream) < 0) FAIL(h, TDMPC_ERR_INVALID, "update_forward: shape does not fit in shared memory");
   return check_launch(h, "update_fwd");
+}
+
+extern "C" int64_t tdmpc_train_param_count(const tdmpc_model_cfg* cfg, int64_t* pi_begin, int64_t* pi_end) {
+  if (!cfg) return -1;
+  long long lo = 0, hi = 0;
+  const long long n = train_param_layout(*cfg, &lo, &hi);
+  if (pi_begin) *pi_begin = lo;
+  if (pi_end) *pi_end = hi;
+  return n;
+}
+extern "C" int64_t tdmpc_train_workspace_bytes(const tdmpc_model_cfg* cfg, int32_t batch, int32_t horizon) {
+  if (!cfg || batch <= 0 || horizon <= 0) return -1;
+  return train_workspace_bytes(*cfg, batch, horizon);
+}
+extern "C" int tdmpc_update(tdmpc_handle* h, const tdmpc_train_args* a, void* stream) {
+  if (!h || !a) return TDMPC_ERR_INVALID;
+  const tdmpc_model_cfg& c = h->cfg;
+  if (c.dynamics != TDMPC_DYN_MLP || c.enc_layernorm) FAIL(h, TDMPC_ERR_INVALID, "update: MLP dynamics and the plain state encoder only");
+  if (a->batch <= 0 || a->horizon <= 0 || a->horizon >= TDMPC_MAX_H) FAIL(h, TDMPC_ERR_INVALID, "update: bad batch / horizon");
+  if (!a->obs || !a->next_obses || !a->action || !a->reward || !a->weights || !a->metrics || !a->priorities || !a->grads || !a->adam_m ||
+      !a->adam_v || !a->pi_adam_m || !a->pi_adam_v || !a->workspace)
+    FAIL(h, TDMPC_ERR_INVALID, "update: a required pointer is NULL");
+  const tdmpc_weights* ws[2] = {&a->online, &a->target};
+  for (const tdmpc_weights* w : ws) {
+    bool ok = w->enc_w[0] && w->enc_w[1] && w->enc_b[0] && w->enc_b[1];
+    for (int i = 0; i < 3; ++i)
+      ok = ok && w->dyn_w[i] && w->dyn_b[i] && w->rew_w[i] && w->rew_b[i] && w->pi_w[i] && w->pi_b[i] && w->q_w[0][i] && w->q_b[0][i] && w->q_w[1][i] && w->q_b[1][i];
+    for (int i = 0; i < 2; ++i) ok = ok && w->q_ln_g[0][i] && w->q_ln_b[0][i] && w->q_ln_g[1][i] && w->q_ln_b[1][i];
+    if (!ok) FAIL(h, TDMPC_ERR_INVALID, "update: a parameter pointer is NULL");
+  }
+  if (a->workspace_bytes < train_workspace_bytes(c, a->batch, a->horizon)) FAIL(h, TDMPC_ERR_INVALID, "update: workspace too small");
+  cudaSetDevice(c.device);
+  const int n = launch_train_step(c, *a, (cudaStream_t)stream);
+  if (n < 0) FAIL(h, TDMPC_ERR_CUDA, "update: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  h->launches += (uint64_t)n;
+  return TDMPC_OK;
 }
 
 extern "C" int tdmpc_fill_noise(tdmpc_handle* h, int32_t stream_id, uint64_t seed, uint64_t call, uint64_t count,

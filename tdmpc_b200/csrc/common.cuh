@@ -254,3 +254,7 @@ struct UpdateFwdParams {
 
 size_t update_fwd_smem(const ModelFp32& m, int D, int L, int A, int M, int E);
 int launch_update_fwd(const ModelFp32& m, const ModelFp32& mt, const UpdateFwdParams& p, cudaStream_t st);
+// whole training step (train.cu)
+long long train_param_layout(const tdmpc_model_cfg& c, long long* pi_begin, long long* pi_end);
+long long train_workspace_bytes(const tdmpc_model_cfg& c, int B, int H);
+int launch_train_step(const tdmpc_model_cfg& cfg, const tdmpc_train_args& a, cudaStream_t st);     // launches (> 0) or -1

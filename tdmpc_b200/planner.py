@@ -48,6 +48,7 @@ class Planner:
         self.Hd = int(hidden_dim) if self.drnn else 0
         cfg = _lib.ModelCfg(obs_dim, action_dim, latent_dim, mlp_dim, enc_dim, self.Hd, int(bool(enc_layernorm)),
                             {"mlp": _lib.DYN_MLP, "drnn": _lib.DYN_DRNN}[dynamics], _PREC[precision], self.device.index)
+        self._cfg = cfg
         self._h = C.c_void_p()
         rc = self.lib.tdmpc_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
@@ -608,10 +609,105 @@ class TDMPC:
         v, r = pl.estimate_value(z, acts, discount=self.cfg.discount, min_std=self.cfg.min_std, seed=pl.seed, call=pl.call)
         return v, float(r.mean().item())
 
+    # ------------------------------------------------------------------------------------------------ training step
+    TRAIN_KEYS = tuple(f"{m}.{i}.{s}" for m, idx in (("_encoder", (0, 2)), ("_dynamics", (0, 2, 4)), ("_reward", (0, 2, 4)), ("_pi", (0, 2, 4)))
+                       for i in idx for s in ("weight", "bias")) + \
+        tuple(f"{q}.{i}.{s}" for q in ("_Q1", "_Q2") for i in (0, 1, 3, 4, 6) for s in ("weight", "bias"))
+
+    @staticmethod
+    def _train_weights(model, device):
+        """tdmpc_weights over the module's OWN parameter storage (the training step updates it in place)."""
+        sd = dict(model.state_dict(keep_vars=True))
+        w = _lib.Weights()
+        for k in TDMPC.TRAIN_KEYS:
+            t = sd[k]
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != device:
+                raise ValueError(f"update(): parameter {k} must be a contiguous fp32 tensor on {device}")
+
+        def P(k):
+            return sd[k].data_ptr()
+
+        w.enc_w[0], w.enc_b[0], w.enc_w[1], w.enc_b[1] = P("_encoder.0.weight"), P("_encoder.0.bias"), P("_encoder.2.weight"), P("_encoder.2.bias")
+        for dst_w, dst_b, mod in ((w.dyn_w, w.dyn_b, "_dynamics"), (w.rew_w, w.rew_b, "_reward"), (w.pi_w, w.pi_b, "_pi")):
+            for j, i in enumerate((0, 2, 4)):
+                dst_w[j], dst_b[j] = P(f"{mod}.{i}.weight"), P(f"{mod}.{i}.bias")
+        for h, q in enumerate(("_Q1", "_Q2")):
+            for j, i in enumerate((0, 3, 6)):
+                w.q_w[h][j], w.q_b[h][j] = P(f"{q}.{i}.weight"), P(f"{q}.{i}.bias")
+            for j, i in enumerate((1, 4)):
+                w.q_ln_g[h][j], w.q_ln_b[h][j] = P(f"{q}.{i}.weight"), P(f"{q}.{i}.bias")
+        return w
+
+    def _train_state(self, B, H):
+        """Flat optimiser arenas (state_dict order; tdmpc_train_args) and the workspace, created on first use."""
+        pl = self._planner
+        st = getattr(self, "_train", None)
+        if st is None:
+            lo, hi = C.c_int64(), C.c_int64()
+            n = pl.lib.tdmpc_train_param_count(C.byref(pl._cfg), C.byref(lo), C.byref(hi))
+            if n != sum(p.numel() for p in self.model.parameters()):
+                raise RuntimeError("update(): the model is not the plain MLP TOLD the training step supports")
+            z = lambda k: torch.zeros(k, device=self.device)
+            st = self._train = {"n": n, "pi": (lo.value, hi.value), "m": z(n), "v": z(n), "pi_m": z(hi.value - lo.value), "pi_v": z(hi.value - lo.value),
+                                "grads": z(n), "step": 0, "pi_step": 0, "metrics": z(8), "ws": None, "ws_key": None}
+        if st["ws_key"] != (B, H):
+            nbytes = pl.lib.tdmpc_train_workspace_bytes(C.byref(pl._cfg), B, H)
+            st["ws"] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            st["ws_key"] = (B, H)
+        return st
+
+    @torch.no_grad()
+    def update_batch(self, obs, next_obses, action, reward, weights, step, noise_pi=None, noise_pi_update=None):
+        """One whole training step (tdmpc.py:191-245) on a replay batch, on the device (tdmpc_update): forward, backward, gradient
+        clipping, Adam over the model, update_pi with its own Adam, and the target EMA when `step % update_freq == 0`.
+        self.model / self.model_target are updated in place.  Returns the reference's metric dict plus `priorities` [B,1]
+        (device) and `pi_grad_norm`."""
+        cfg, pl, dev = self.cfg, self._planner, self.device
+        H = int(cfg.horizon)
+        obs = _f32(obs, dev); B = obs.shape[0]
+        nxt, act = _f32(next_obses[:H], dev), _f32(action[:H], dev)
+        rew = _f32(reward[:H], dev).reshape(H, B)
+        wts = _f32(weights, dev).reshape(B)
+        st = self._train_state(B, H)
+        pri = torch.empty(B, device=dev)
+        a = _lib.TrainArgs()
+        a.online, a.target = self._train_weights(self.model, dev), self._train_weights(self.model_target, dev)
+        a.batch, a.horizon, a.discount, a.rho, a.min_std = B, H, float(cfg.discount), float(cfg.rho), float(cfg.min_std)
+        a.consistency_coef, a.reward_coef, a.value_coef = float(cfg.consistency_coef), float(cfg.reward_coef), float(cfg.value_coef)
+        a.lr, a.beta1, a.beta2, a.adam_eps = float(cfg.lr), 0.9, 0.999, 1e-8
+        a.grad_clip_norm, a.tau = float(cfg.grad_clip_norm), float(cfg.tau)
+        a.update_target = 1 if step % cfg.update_freq == 0 else 0
+        a.adam_step, a.pi_adam_step = st["step"], st["pi_step"]
+        a.adam_m, a.adam_v, a.pi_adam_m, a.pi_adam_v, a.grads = (st[k].data_ptr() for k in ("m", "v", "pi_m", "pi_v", "grads"))
+        a.obs, a.next_obses, a.action, a.reward, a.weights = obs.data_ptr(), nxt.data_ptr(), act.data_ptr(), rew.data_ptr(), wts.data_ptr()
+        keep = [obs, nxt, act, rew, wts]
+        if noise_pi is not None:
+            n1 = _f32(noise_pi, dev); assert tuple(n1.shape) == (H, B, cfg.action_dim)
+            a.noise_pi = n1.data_ptr(); keep.append(n1)
+        if noise_pi_update is not None:
+            n2 = _f32(noise_pi_update, dev); assert tuple(n2.shape) == (H + 1, B, cfg.action_dim)
+            a.noise_pi_update = n2.data_ptr(); keep.append(n2)
+        pl.call += 1
+        a.seed, a.call = pl.seed, pl.call
+        a.metrics, a.priorities = st["metrics"].data_ptr(), pri.data_ptr()
+        a.workspace, a.workspace_bytes = st["ws"].data_ptr(), st["ws"].numel()
+        pl._check(pl.lib.tdmpc_update(pl._h, C.byref(a), pl._stream()), "tdmpc_update")
+        st["step"] += 1; st["pi_step"] += 1
+        pl._wver = None                                   # the parameters moved: re-pack before the next plan()
+        m = st["metrics"].tolist()                        # the one device -> host read of the step
+        self._keep_train = keep
+        return {"consistency_loss": m[0], "reward_loss": m[1], "value_loss": m[2], "pi_loss": m[6], "total_loss": m[3],
+                "weighted_loss": m[4], "grad_norm": m[5], "pi_grad_norm": m[7], "priorities": pri.unsqueeze(1)}
+
     def update(self, replay_buffer, step):
-        raise NotImplementedError("the optimiser step stays in the reference's PyTorch code (use tdmpc_b200.accelerate(agent) on a "
-                                  "reference TDMPC to keep update() and gain the CUDA plan()); the FORWARD of update() -- loss terms, "
-                                  "TD targets, priorities -- is available as update_forward()")
+        """TDMPC.update (tdmpc.py:191-245): same call, same returned metric names; every tensor operation of it runs in
+        tdmpc_update (csrc/train.cu) on the module's own parameters."""
+        obs, next_obses, action, reward, idxs, weights = replay_buffer.sample()
+        self.std = linear_schedule(self.cfg.std_schedule, step)
+        m = self.update_batch(obs, next_obses, action, reward, weights, step)
+        replay_buffer.update_priorities(idxs, m.pop("priorities"))
+        m.pop("pi_grad_norm")
+        return m
 
     @torch.no_grad()
     def update_forward(self, obs, next_obses, action, reward, weights=None, noise_pi=None, taps=False):

@@ -240,6 +240,70 @@ def run_update_case(name, cfg_name, batch=96, seed=0, **over):
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
 
 
+def run_train_case(name, cfg_name, batch=64, seed=0, steps=2, store_params=True, **over):
+    """The WHOLE TDMPC.update (tdmpc.py:191-245: backward, clip_grad_norm_, both Adam optimisers, update_pi, ema), unmodified, on
+    CPU for `steps` consecutive replay batches (step numbers chosen so that the target network moves on the first and not on
+    the second call, update_freq = 2).  Stored: the returned metrics per call and -- for the small model -- every parameter of
+    model and model_target after the last call; for the big ones a fingerprint (sum, sum of squares, 16 strided samples per
+    tensor).  oracle.update_step must reproduce all of it."""
+    cfg = synth.make_cfg(cfg_name, batch_size=batch, **over)
+    torch.manual_seed(0)
+    agent = TDMPC(cfg)
+    sd, sd_t = synth.make_told_weights(cfg, seed), synth.make_told_weights(cfg, seed + 50)
+    agent.model.load_state_dict(sd)
+    agent.model_target.load_state_dict(sd_t)
+    real = ref_h._standard_normal
+    mets = []
+    o_sd, o_t, o_opt = sd, sd_t, None
+    worst = 0.0
+    for s in range(steps):
+        b = synth.make_train_batch(cfg, seed + 7 * s, batch)
+
+        class Buf:
+            def sample(self):
+                return b["obs"], b["next_obses"], b["action"], b["reward"], b["idxs"], b["weights"]
+
+            def update_priorities(self, idxs, pr):
+                self.pr = pr.clone()
+
+        buf = Buf()
+        q = [b["noise_pi"][t] for t in range(cfg.horizon)] + [b["noise_pi_update"][t] for t in range(cfg.horizon + 1)]
+
+        def stdn(shape, dtype=None, device=None, _q=q):
+            x = _q.pop(0)
+            assert tuple(x.shape) == tuple(shape), (x.shape, shape)
+            return x.clone()
+
+        ref_h._standard_normal = stdn
+        try:
+            m = agent.update(buf, 10 ** 6 + s)                 # even step: ema; odd step: no ema
+        finally:
+            ref_h._standard_normal = real
+        assert not q
+        mets.append([m["consistency_loss"], m["reward_loss"], m["value_loss"], m["total_loss"], m["weighted_loss"], m["grad_norm"], m["pi_loss"]])
+        om, o_sd, o_t, o_g, o_opt = O.update_step(o_sd, o_t, cfg, b, o_opt, update_target=(10 ** 6 + s) % cfg.update_freq == 0)
+        got = [om[k] for k in ("consistency_loss", "reward_loss", "value_loss", "total_loss", "weighted_loss", "grad_norm", "pi_loss")]
+        dm = max(abs(a - c) / max(abs(a), 1e-12) for a, c in zip(mets[-1], got))
+        dpar = max((agent.model.state_dict()[k] - o_sd[k]).abs().max().item() for k in o_sd)
+        dtar = max((agent.model_target.state_dict()[k] - o_t[k]).abs().max().item() for k in o_t)
+        dgr = max((p.grad - o_g[k]).abs().max().item() for k, p in agent.model.named_parameters())
+        dpri = (buf.pr - om["priorities"]).abs().max().item()
+        print(f"[{name}] call {s}: metrics rel diff {dm:.2e}  |d params| {dpar:.2e}  |d target| {dtar:.2e}  |d grads| {dgr:.2e}  |d priorities| {dpri:.2e}")
+        worst = max(worst, dm, dpar, dtar, dgr)
+    assert worst < 1e-6, worst
+    out = {"metrics": np.array(mets, dtype=np.float64), "meta": np.array([seed, batch, steps], dtype=np.int64)}
+
+    def finger(t):
+        f = t.detach().double().flatten()
+        idx = torch.linspace(0, f.numel() - 1, 16).long()
+        return np.concatenate([[f.sum().item(), (f * f).sum().item()], f[idx].numpy()])
+
+    for tag, mod in (("model", agent.model), ("target", agent.model_target)):
+        for k, v in mod.state_dict().items():
+            out[f"{tag}/{k}"] = v.numpy().copy() if store_params else finger(v)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+
+
 SIM_PLAN = [(9000, True), (9001, False), (17000, False), (17001, True), (17002, False)]     # horizon schedule: 3, 3, (4 ignored), 4, 4
 
 
@@ -467,6 +531,10 @@ if __name__ == "__main__":
         run_update_case("update_cfg3", "cfg3", batch=96, seed=13)
         run_update_case("update_cfg2s", "cfg2s", batch=40, seed=14)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        run_train_case("train_small", "tiny", batch=48, seed=21, mlp_dim=64, enc_dim=32)
+        run_train_case("train_cfg3", "cfg3", batch=64, seed=22, store_params=False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sim":
         run_sim_case("tdmpcsim_tiny", "tiny", SIM_PLAN, seed=8, horizon=5, horizon_schedule="linear(2, 5, 25000, 0)", normalize=True)
         run_sim_case("tdmpcsim_cfg3", "cfg3", SIM_PLAN[:4], seed=9, eval_mode=False)
@@ -488,4 +556,6 @@ if __name__ == "__main__":
     run_update_case("update_tiny", "tiny", batch=70, seed=12)
     run_update_case("update_cfg3", "cfg3", batch=96, seed=13)
     run_update_case("update_cfg2s", "cfg2s", batch=40, seed=14)
+    run_train_case("train_small", "tiny", batch=48, seed=21, mlp_dim=64, enc_dim=32)
+    run_train_case("train_cfg3", "cfg3", batch=64, seed=22, store_params=False)
     print("golden fixtures written to", HERE)

@@ -175,6 +175,14 @@ def make_update_batch(cfg, seed, batch):
             "weights": _t(rs.uniform(0.2, 1.0, (batch, 1))), "noise_pi": _t(rs.standard_normal((H, batch, A)))}
 
 
+def make_train_batch(cfg, seed, batch):
+    """make_update_batch plus the standard-normal draws of pi() inside update_pi (tdmpc.py:172): [H+1,B,A]."""
+    b = make_update_batch(cfg, seed, batch)
+    rs = np.random.RandomState(4500 + seed)
+    b["noise_pi_update"] = _t(rs.standard_normal((cfg.horizon + 1, batch, cfg.action_dim)))
+    return b
+
+
 def make_icem_noise(cfg, seed, sizes, H, have_elites, single_beta=False):
     """Draws of one TdICemSimMlp.plan call in consumption order (tdmpc_icem_similarity_mlp.py:139-157,
     188-239): per iteration white randn + two colored blocks (series of length cfg.horizon, truncated to

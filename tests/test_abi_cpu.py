@@ -27,9 +27,10 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.ModelCfg) == 40
     assert C.sizeof(_lib.Weights) == 8 * (2 + 2 + 2 + 3 * 6 + 6 + 6 + 4 + 4 + 2 + 6 + 4 + 4)
     # the library reports its own sizeof/offsetof values; load() compares them with the ctypes mirror
-    got = (C.c_int32 * 10)()
-    assert _lib.load().tdmpc_abi_sizes(got, 10) == 10
-    assert list(got)[7:] == [C.sizeof(_lib.ReplaySampleArgs), C.sizeof(_lib.ReplayGatherArgs), C.sizeof(_lib.UpdateArgs)]
+    got = (C.c_int32 * 11)()
+    assert _lib.load().tdmpc_abi_sizes(got, 11) == 11
+    assert list(got)[7:] == [C.sizeof(_lib.ReplaySampleArgs), C.sizeof(_lib.ReplayGatherArgs), C.sizeof(_lib.UpdateArgs),
+                             C.sizeof(_lib.TrainArgs)]
     assert list(got)[:3] == [C.sizeof(_lib.ModelCfg), C.sizeof(_lib.Weights), C.sizeof(_lib.PlanArgs)]
     assert got[6] == _lib.PlanArgs.tap_z0.offset
     assert _lib.PlanArgs.n_samples.size == 4 * _lib.TDMPC_MAX_ITERS

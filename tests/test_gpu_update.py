@@ -70,5 +70,3 @@ def test_update_forward_uses_both_models_and_follows_weight_updates():
     a2 = agent.update_forward(b["obs"], b["next_obses"], b["action"], b["reward"])
     c = agent.update_forward(b["obs"], b["next_obses"], b["action"], b["reward"])
     assert torch.equal(a["per_sample"]["value"], a2["per_sample"]["value"]) and not torch.equal(a["per_sample"]["value"], c["per_sample"]["value"])
-    with pytest.raises(NotImplementedError):
-        agent.update(None, 0)

@@ -221,3 +221,27 @@ def test_package_accounting_matches_oracle():
     for args in ((5, 1, 50, 512, 256, 5, [537] * 6, 25), (223, 38, 100, 512, 256, 5, [537] * 8, 25), (18, 4, 50, 512, 256, 10, [1544, 1236, 990], 512)):
         assert A.flops_per_plan(*args) == O.flops_per_plan(*args)
     assert A.sample_steps_per_plan(5, [537] * 6, 25) == O.sample_steps_per_plan(5, [537] * 6, 25) == 16235
+
+
+@pytest.mark.parametrize("name,cfg_name,over", [("train_small", "tiny", dict(mlp_dim=64, enc_dim=32)), ("train_cfg3", "cfg3", {})])
+def test_oracle_update_step_matches_reference_golden(golden_dir, name, cfg_name, over):
+    """oracle.update_step (the whole TDMPC.update: backward, clip, both Adams, update_pi, ema) against what the unmodified
+    reference method returned and left in its parameters over two consecutive calls (tests/golden/make_golden.py train)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, batch, steps = [int(x) for x in g["meta"]]
+    cfg = synth.make_cfg(cfg_name, batch_size=batch, **over)
+    sd, sd_t, opt = synth.make_told_weights(cfg, seed), synth.make_told_weights(cfg, seed + 50), None
+    for s in range(steps):
+        b = synth.make_train_batch(cfg, seed + 7 * s, batch)
+        m, sd, sd_t, _, opt = O.update_step(sd, sd_t, cfg, b, opt, update_target=(10 ** 6 + s) % cfg.update_freq == 0)
+        got = [m[k] for k in ("consistency_loss", "reward_loss", "value_loss", "total_loss", "weighted_loss", "grad_norm", "pi_loss")]
+        np.testing.assert_allclose(got, g["metrics"][s], rtol=1e-6, atol=1e-9)
+    for tag, cur in (("model", sd), ("target", sd_t)):
+        for k, v in cur.items():
+            ref = g[f"{tag}/{k}"]
+            if name == "train_small":
+                np.testing.assert_allclose(v.numpy(), ref, rtol=0, atol=1e-7, err_msg=f"{tag}/{k}")
+            else:
+                f = v.double().flatten()
+                idx = torch.linspace(0, f.numel() - 1, 16).long()
+                np.testing.assert_allclose(np.concatenate([[f.sum().item(), (f * f).sum().item()], f[idx].numpy()]), ref, rtol=1e-9, atol=1e-9)
