@@ -64,6 +64,7 @@ struct KParams {
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
   uint32_t jw[MAX_JOBS];
   int one;                     // always 1 (an opaque branch condition: tc_prims.cuh, tmem_drain_aux)
+  int dual;                    // 1: warps 1 and 3 take turns issuing the jobs' MMAs (MLP model, <= 2 producer warps)
   int fast;                    // 1: the job list is the plain value-mode schedule of the MLP model (17 jobs per step, then the terminal
                                //    policy and the Q heads): the MMA warp and the epilogue walk the steps with structured loops
   unsigned int* tile_counter;  // dynamic tile scheduler: tickets handed out so far in this launch (zero between launches)
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   // never overwritten before its last reader is done.
   uint64_t* acc2_full = d3_full + 1;     // third accumulator (F_ACC2): complete / drained
   uint64_t* acc2_empty = acc2_full + 1;
-  uint64_t* tq_full = acc2_empty + 1;
+  uint64_t* turn = acc2_empty + 1;       // two MMA issuers (kp.dual): turn[i] = issuer i may issue its next job
+  uint64_t* tq_full = turn + 2;
   uint32_t* tile_q = reinterpret_cast<uint32_t*>(tq_full + 4);
   uint32_t* tmem_slot = tile_q + 4;
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     mbar_init(d3_full, 1);
     mbar_init(acc2_full, 1); mbar_init(acc2_empty, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&tq_full[i], 1);
+    mbar_init(&turn[0], 1); mbar_init(&turn[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
     // registers to the two epilogue warpgroups.
     setmaxnreg_dec<Regs<DRNN>::CTRL>();
-    if (warp != 1) {
+    const bool dual = !DRNN && kp.dual;                 // second issuer: warp 3 (then never a producer: kp.producers <= 2)
+    if (warp != 1 && !(dual && warp == 3)) {
       // ============================== producers: weight tiles, L2 -> smem ring ==============================
       // One thread can only issue a bulk copy every ~400 cycles (measured: tools/smem_contention.cu), which caps a
       // single-producer weight stream at ~40 B/clk -- less than the MMAs consume.  So up to three warps (0, 2, 3)
@@ -276,8 +280,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           }
         }
       }
-    } else if (warp == 1) {
-      // ============================== MMA issuer ==============================
+    } else {
+      // ============================== MMA issuer(s) ==============================
+      // Issuing a tcgen05.mma blocks the thread until the tensor pipe accepts it (tools/mma_queue.cu: n MMAs take n x 64 cycles on the
+      // issue side, the pipe holds one or two), so everything the issuing thread does between two jobs -- decoding the job,
+      // waiting for the accumulator to come back, barrier probes, ~150 cycles until the first MMA of a burst starts -- is time the
+      // tensor pipe idles.  With kp.dual TWO warps take turns: issuer i runs the jobs whose running number is i mod 2, does all
+      // of that preparation while the other one is still issuing, and then waits for its turn (an mbarrier the other issuer
+      // arrives on after its last MMA) -- tools/mma_dual.cu.  Both walk the whole job list and keep identical ring / phase
+      // state: mma_skip() advances it for the other issuer's jobs.  tcgen05.commit tracks the issuing thread's own MMAs only;
+      // the cross-job orderings that used to follow from "one thread, issue order" now rest on the pipe executing MMAs in the
+      // order it accepted them (a job's MMAs are accepted after the previous job's: that is what the turn barrier guarantees).
+      const uint32_t issuer = warp == 1 ? 0u : 1u;
+      uint32_t turn_phase = 0, gjob = 0;           // phase of turn[issuer]; running job number of this CTA
       // The whole warp walks the job list converged (waits are warp-wide); one elected lane issues.
       // Elected once while converged: the same lane issues every MMA and commit.  The warp stays converged and the election
       // predicate sits inside the asm statements (tc_prims.cuh, umma_*_p), which keeps the operands in uniform registers.
@@ -364,9 +379,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
           const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
+          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
+          if (dual) {
+            // preparation that hides behind the other issuer's job: wait (without consuming the phase) for the first things this
+            // job needs -- the [z,a] operand, its accumulator(s), its first weight tile -- then for my turn
+            if (flags & F_WAIT_ZA) TW(2, mbar_wait_sleep(za_full, za_phase));
+            const bool q512 = type == J_QL1 || type == J_QL2;
+            const bool takes_acc = type == J_L1 ? !((flags & F_ACC2) && chunk == 2) : type == J_L2 ? !(flags & F_KHI) : type == J_L3 ? !(flags & (F_PARK | F_EPI)) : false;
+            if (takes_acc) TW(0, mbar_wait_sleep(&acc_empty[nbuf], (ecnt[nbuf] & 1) ^ 1));
+            if (q512) { TW(0, mbar_wait_sleep(&acc_empty[0], (ecnt[0] & 1) ^ 1)); TW(0, mbar_wait_sleep(&acc_empty[1], (ecnt[1] & 1) ^ 1)); }
+            if (gjob > 0) { mbar_wait_sleep(&turn[issuer], turn_phase); turn_phase ^= 1; }
+          }
           if (flags & F_WAIT_ZA) { TW(2, mbar_wait(za_full, za_phase, 6)); za_phase ^= 1; }
           if (DRNN && (flags & F_WAIT_HS)) { mbar_wait(hs_full, hs_phase, 10); hs_phase ^= 1; tcgen05_fence_after(); }
-          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
           const bool staged = !DRNN && (flags & F_CP);
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
@@ -633,7 +658,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           if (tr) { unsigned long long* w = kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * 256 + 2 * MAX_JOBS * 2 + j * 3; w[0] = tw[0]; w[1] = tw[1]; w[2] = tw[2]; }
           tw[0] = tw[1] = tw[2] = 0;
 #endif
+          if (dual && lead) mbar_arrive(&turn[issuer ^ 1u]);      // every MMA of this job has been accepted by the pipe: next issuer
           __syncwarp();
+        };
+        // the other issuer's job: advance the weight ring position, the accumulator ping-pong and every barrier phase exactly as
+        // mma_job does, without waiting or issuing
+        auto mma_skip = [&](const uint32_t job) {
+          const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
+          auto ring_advance = [&](int n) {
+            const uint32_t pos = stage + (uint32_t)n;
+            wphase ^= (pos / (uint32_t)S) & 1u;
+            stage = pos % (uint32_t)S;
+            ready = 0;
+          };
+          if (flags & F_WAIT_ZA) za_phase ^= 1;
+          if (flags & F_BUF0) nbuf = 0;
+          const bool staged = (flags & F_CP) != 0;
+          if (type == J_L1) {
+            const int b = nbuf; nbuf ^= 1;
+            if ((flags & F_ACC2) && chunk == 2) ++a2cnt; else ++ecnt[b];
+            ring_advance(m.nkb1);
+          } else if (type == J_L2 && (flags & (F_KLO | F_KHI))) {
+            const bool hi = (flags & F_KHI) != 0;
+            const int b = nbuf; nbuf ^= 1;
+            if (!hi) ++ecnt[b];
+            if (chunk == 0) { if (staged) xs_phase ^= hi ? 0xCu : 0x3u; else h1_phase ^= hi ? 0xCu : 0x3u; }
+            ring_advance(4);
+          } else if (type == J_L2) {
+            const int b = nbuf; nbuf ^= 1;
+            ++ecnt[b];
+            if (chunk == 0) { if ((flags & F_A_XS) || staged) xs_phase ^= 0xFu; else h1_phase ^= 0xFu; }
+            ring_advance(8);
+          } else if (type == J_L3 && (flags & F_EPI)) {
+          } else if (type == J_L3) {
+            if (!(flags & F_PARK)) { const int b = nbuf; nbuf ^= 1; ++ecnt[b]; }
+            xs_phase ^= 0xFu;
+            ring_advance(m.l3rows[chain] == 128 ? 8 : 4);
+          } else {
+            ++ecnt[0]; ++ecnt[1];
+            if (type == J_QL2) xs_phase ^= 0xFu;
+            ring_advance(type == J_QL1 ? 4 * m.nkb1 : 32);
+          }
         };
         int j0 = 0;
 #ifdef TDMPC_TC_FAST
@@ -657,7 +722,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           j0 = 17 * p.H;
         }
 #endif
-        for (int j = j0; j < kp.njobs; ++j) mma_job(kp.jw[j], j);
+        if (!dual) {
+          for (int j = j0; j < kp.njobs; ++j) mma_job(kp.jw[j], j);
+        } else {
+          for (int j = j0; j < kp.njobs; ++j, ++gjob) {
+            if ((gjob & 1u) == issuer) mma_job(kp.jw[j], j);
+            else mma_skip(kp.jw[j]);
+          }
+        }
       }
     }
   } else {
@@ -1661,7 +1733,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   // (K = 138 -> 128 + 16) that is the difference between a 2-slot and a 3-slot weight ring
   m.za_compact = (!drnn && nkb1 >= 2 && m.K1p - 64 * (nkb1 - 1) == 16 && !getenv("TDMPC_TC_NO_COMPACT")) ? 1 : 0;
   m.za_bytes = m.za_compact ? (nkb1 - 1) * TILE_BYTES + K16_BLOCK_BYTES : nkb1 * TILE_BYTES;
-  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 28) * 8 + 32 + 1024;
+  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 30) * 8 + 32 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
@@ -1679,6 +1751,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   { const char* e = getenv("TDMPC_TC_DEBUG"); m.debug = e ? atoi(e) : 0; }
   m.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) m.producers = v; }
+  m.dual_issue = getenv("TDMPC_TC_DUAL") ? 1 : 0;        // measured slower: off unless asked for
   *out = m;
   return launches;
 }
@@ -1705,6 +1778,7 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.tile_counter = m.tile_counter;
   kp.debug = m.debug;
   kp.producers = m.producers;
+  kp.dual = (!m.drnn && m.producers <= 2 && m.dual_issue) ? 1 : 0;
 #ifdef TDMPC_TC_FAST
   kp.fast = (m.fast_value && p.mode == MODE_VALUE && kp.njobs == 17 * p.H + 13) ? 1 : 0;
 #else

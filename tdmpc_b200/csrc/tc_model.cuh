@@ -88,6 +88,7 @@ struct TcModel {
   int producers;               // producer threads of the weight ring (divides `stages`)
   int exact_act;               // TDMPC_PREC_BF16_EXACT: two-MUFU tanh in the Q heads instead of tanh.approx
   int fast_value;              // the value-mode job list is the plain schedule: structured walk instead of the generic one
+  int dual_issue;              // two MMA-issuing warps take turns (MLP model with <= 2 producer warps); experiment, TDMPC_TC_DUAL=1 switches it on
   unsigned int* tile_counter;  // device word of the dynamic tile scheduler (arena tail; zero between launches)
   // DRNN (TDMPC_DYN_DRNN): chain CH_DYN is the prior MLP (layer 1: K = hidden_dim, layer 3 slot = its second Linear),
   // chain CH_REW's layer 1 reads the hidden state; gate weights live in their own tiles.

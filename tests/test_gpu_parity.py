@@ -234,7 +234,7 @@ def test_integer_exact_rollout(cfg_name, precision):
 
 
 @pytest.mark.parametrize("cfg_name", ["cfg3", "cfg2", "k80"])
-@pytest.mark.parametrize("switch", ["TDMPC_TC_OVERLAP", "TDMPC_TC_SPLIT", "TDMPC_TC_STAGED=1", "TDMPC_TC_STAGED=2", "TDMPC_TC_STAGED=0"])
+@pytest.mark.parametrize("switch", ["TDMPC_TC_OVERLAP", "TDMPC_TC_SPLIT", "TDMPC_TC_STAGED=1", "TDMPC_TC_STAGED=2", "TDMPC_TC_STAGED=0", "TDMPC_TC_DUAL=1"])
 def test_alternative_schedules_stay_bit_exact(switch, cfg_name, monkeypatch):
     """The two alternative job programs of rollout_tc_kernel that are kept behind environment switches (DESIGN.md 4.1:
     measured slower, so off by default) -- the overlapped dynamics / reward schedule and the split-k layer 2 -- walk
@@ -242,7 +242,7 @@ def test_alternative_schedules_stay_bit_exact(switch, cfg_name, monkeypatch):
     first-iteration values of a whole plan must agree with the default schedule's to fp32 summation order (the reward
     head's partial sums are grouped differently)."""
     gu = _gu()
-    if cfg_name != "cfg3" and not switch.startswith("TDMPC_TC_STAGED"):
+    if cfg_name != "cfg3" and not switch.startswith(("TDMPC_TC_STAGED", "TDMPC_TC_DUAL")):
         pytest.skip("the older alternatives are kept for cfg3 only")
     cfg = synth.make_cfg(cfg_name)
     sd = _integer_model(cfg, 11)
