@@ -295,6 +295,46 @@ def update_forward_extra(dev, batch=512):
             "tflops_fp32": flop / (ms * 1e-3) / 1e12, "gpu_eager_ms": ms_e, "cpu_port_ms": float(np.median(t)), "cpu_threads": torch.get_num_threads()}
 
 
+def train_step_extra(dev, batch=512):
+    """SURVEY 8(f) row 2, whole: one TDMPC.update (forward, backward through time, clip, both Adams, update_pi, ema) through
+    tdmpc_update (fp32 CUDA) next to the same step run eagerly by torch on this GPU (autograd + the oracle's op sequence) and on
+    the host cores."""
+    from oracle import tdmpc_oracle as O
+    from tdmpc_b200 import TDMPC
+    from tdmpc_b200.accounting import mlp_flops
+    cfg = synth.make_cfg("cfg3", batch_size=batch, device=str(dev), precision="fp32")
+    sd, sd_t = synth.make_told_weights(cfg, 0), synth.make_told_weights(cfg, 50)
+    agent = TDMPC(cfg)
+    agent.model.load_state_dict(sd); agent.model_target.load_state_dict(sd_t)
+    b = {k: v.to(dev) for k, v in synth.make_train_batch(cfg, 0, batch).items()}
+    n0 = agent._planner.launch_count
+    step = [0]
+
+    def ours():
+        agent.update_batch(b["obs"], b["next_obses"], b["action"], b["reward"], b["weights"], step[0]); step[0] += 1
+    ms = time_kernel(ours, reps=10)
+    launches = (agent._planner.launch_count - n0) / step[0]
+    st = {"sd": {k: v.to(dev) for k, v in sd.items()}, "t": {k: v.to(dev) for k, v in sd_t.items()}, "opt": None}
+
+    def eager():
+        with torch.device(dev):
+            _, st["sd"], st["t"], _, st["opt"] = O.update_step(st["sd"], st["t"], cfg, b, st["opt"], True)
+    ms_e = time_kernel(eager, reps=3)
+    bc = synth.make_train_batch(cfg, 0, batch)
+    t0 = time.perf_counter(); O.update_step(sd, sd_t, cfg, bc, None, True); ms_c = (time.perf_counter() - t0) * 1e3
+    L, A, M, H = cfg.latent_dim, cfg.action_dim, cfg.mlp_dim, cfg.horizon
+    f_dyn, f_rew, f_pi, f_q = mlp_flops(L, A, M)
+    f_enc = 2 * (cfg.obs_shape[0] * cfg.enc_dim + cfg.enc_dim * L)
+    fwd = f_enc + H * (f_dyn + f_rew + 2 * f_q)                       # online model, differentiated: backward ~ 2x
+    tgt = H * (2 * f_enc + f_pi + 2 * f_q)                            # TD targets (no gradient)
+    upi = (H + 1) * (f_pi + 2 * f_q)                                  # update_pi forward; backward: 2x policy, 1x Q (data gradients only)
+    flop = batch * (3 * fwd + tgt + upi + (H + 1) * (2 * f_pi + 2 * f_q))
+    return {"workload": f"TDMPC.update whole (forward, backward, clip, Adam x2, update_pi, ema): cfg3 dims, batch {batch}, H = {H}, fp32",
+            "ms_per_step": ms, "launches_per_step": launches, "flop_per_step": flop, "tflops_fp32": flop / (ms * 1e-3) / 1e12,
+            "gpu_eager_ms": ms_e, "cpu_port_ms": ms_c, "cpu_threads": torch.get_num_threads(),
+            "d2h_bytes_per_step": 32, "note": "parameters of the torch modules are updated in place; one 8-float metrics read per step"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -664,6 +704,7 @@ def main():
         if world == 1:
             extra["replay_sample_1m"] = replay_extra(dev, measured_peaks()[2])
             extra["update_forward_b512"] = update_forward_extra(dev)
+            extra["train_step_b512"] = train_step_extra(dev)
         # the batched environment-stepping loop (tdmpc_b200.PlanLoop): numpy observations in, numpy
         # actions out, one pinned H2D + one CUDA-graph replay of the whole plan + one D2H per step (wall clock, host included)
         from tdmpc_b200 import PlanLoop

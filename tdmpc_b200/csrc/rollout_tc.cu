@@ -43,7 +43,6 @@ constexpr int TILE_BYTES = 16384;
 constexpr int XS_BYTES = 8 * TILE_BYTES;      // 128 x 512 bf16
 constexpr int MAX_JOBS = 22 * TDMPC_MAX_H + 20;
 constexpr uint32_t TM_ACC = 0, TM_A = 256;
-constexpr uint32_t TM_ACC2 = 384;           // third accumulator of the layer-1 jobs (F_ACC2): the columns of the h1 chunks 2 and 3
 constexpr uint32_t TM_X = 256, TM_Y = 384;  // DRNN: gh_n and gi_n of the newval gate, inside the (then idle) h1 region
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 232448;
@@ -64,9 +63,8 @@ struct KParams {
   // whole control flow -- and with it every MMA operand -- in the uniform datapath.
   uint32_t jw[MAX_JOBS];
   int one;                     // always 1 (an opaque branch condition: tc_prims.cuh, tmem_drain_aux)
-  int dual;                    // 1: warps 1 and 3 take turns issuing the jobs' MMAs (MLP model, <= 2 producer warps)
-  int fast;                    // 1: the job list is the plain value-mode schedule of the MLP model (17 jobs per step, then the terminal
-                               //    policy and the Q heads): the MMA warp and the epilogue walk the steps with structured loops
+  int pair;                    // 1: value mode over CTA pairs (tile = blockIdx.x / 2, rank = blockIdx.x & 1): tc_model.cuh, build_jobs mode 2
+  int njobs1, j1off;           //    rank 1's job count and its offset inside jobs / jw (rank 0: njobs, offset 0)
   unsigned int* tile_counter;  // dynamic tile scheduler: tickets handed out so far in this launch (zero between launches)
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter space");
@@ -92,10 +90,6 @@ __device__ __forceinline__ float tanh_bf16(float x) {
   float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x)); }
-// A value the compiler must treat as unknown at every call (no constant propagation, no hoisting out of loops), but whose range
-// it knows: the fast paths pass the chain index through this, so that the job's type and flags stay compile-time constants
-// while the chain's parameter pointers are NOT loop invariants that would be hoisted into registers held across the epilogues.
-__device__ __forceinline__ int opaque3(int x) { asm volatile("" : "+r"(x)); return x & 7; }
 __device__ __forceinline__ float4 ldg4(const float* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
 
 __device__ __forceinline__ int job_tiles(const TcModel& m, uint32_t job) {
@@ -151,7 +145,9 @@ __device__ __forceinline__ void za_store8(uint8_t* za, int row, int k0, const fl
                "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
 }
 
-template <bool DRNN, bool EXACT>
+// PAIR: the CTA-pair variant (kp.pair launches) is its own instantiation -- merely branching around its mailbox code costs the
+// ordinary kernel registers and spills in the epilogues (measured: 3 - 5 %).
+template <bool DRNN, bool EXACT, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcModel& m = kp.m;
@@ -167,7 +163,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   float* xch = reinterpret_cast<float*>(wring + S * TILE_BYTES);     // [3][2 groups][128 rows] epilogue-group exchange
   float* qcs = xch + XCH_FLOATS;                                       // [4][512] Q-head layer constants (16-byte aligned)
   uint32_t* sjobs = reinterpret_cast<uint32_t*>(qcs + QC_FLOATS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sjobs + ((kp.njobs + 3) & ~3));
+  // CTA-pair mode: rank 0 (even block) dynamics / policy / Q1, rank 1 reward / Q2 / value.  Macros, not locals: without PAIR they
+  // must fold to exactly the expressions the single-CTA kernel always used (a local here costs the epilogues a register).
+#define TC_NJOBS ((PAIR && (blockIdx.x & 1u)) ? kp.njobs1 : kp.njobs)
+#define TC_JOFF ((PAIR && (blockIdx.x & 1u)) ? kp.j1off : 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sjobs + ((kp.njobs + (PAIR ? kp.njobs1 : 0) + 3) & ~3));
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + MAX_STAGES;
   uint64_t* acc_full = w_empty + MAX_STAGES;
@@ -188,10 +188,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   // when it starts on tile n and publishes it through a 4-entry ring (tq_full: one arrival per entry use); all roles read the
   // ring in order.  They stay within a tile of each other (weight ring, accumulator and operand barriers), so an entry is
   // never overwritten before its last reader is done.
-  uint64_t* acc2_full = d3_full + 1;     // third accumulator (F_ACC2): complete / drained
-  uint64_t* acc2_empty = acc2_full + 1;
-  uint64_t* turn = acc2_empty + 1;       // two MMA issuers (kp.dual): turn[i] = issuer i may issue its next job
-  uint64_t* tq_full = turn + 2;
+  uint64_t* tq_full = d3_full + 1;
   uint32_t* tile_q = reinterpret_cast<uint32_t*>(tq_full + 4);
   uint32_t* tmem_slot = tile_q + 4;
   // DRNN: during the steps XS is idle (the prior MLP runs layer 2 from TMEM, the reward head needs no h2 operand), so it
@@ -202,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < kp.njobs; i += NTHREADS) sjobs[i] = kp.jobs[i];
+  for (int i = threadIdx.x; i < TC_NJOBS; i += NTHREADS) sjobs[i] = kp.jobs[TC_JOFF + i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
@@ -211,9 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
     mbar_init(hs_full, 256); mbar_init(x_full, 1); mbar_init(r_ready, 128); mbar_init(u_ready, 128);
     mbar_init(d3_full, 1);
-    mbar_init(acc2_full, 1); mbar_init(acc2_empty, 128);
     for (int i = 0; i < 4; ++i) mbar_init(&tq_full[i], 1);
-    mbar_init(&turn[0], 1); mbar_init(&turn[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -238,8 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
     // registers to the two epilogue warpgroups.
     setmaxnreg_dec<Regs<DRNN>::CTRL>();
-    const bool dual = !DRNN && kp.dual;                 // second issuer: warp 3 (then never a producer: kp.producers <= 2)
-    if (warp != 1 && !(dual && warp == 3)) {
+    if (warp != 1) {
       // ============================== producers: weight tiles, L2 -> smem ring ==============================
       // One thread can only issue a bulk copy every ~400 cycles (measured: tools/smem_contention.cu), which caps a
       // single-producer weight stream at ~40 B/clk -- less than the MMAs consume.  So up to three warps (0, 2, 3)
@@ -249,9 +243,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       const int pk = warp == 0 ? 0 : warp - 1;
       if (lane == 0 && pk < P) {
         uint32_t stage = 0, phase = 0, mine = 0;    // mine: tile counter mod P
-        if (pk == 0) { tile_q[0] = blockIdx.x; mbar_arrive(&tq_full[0]); }
+        if (pk == 0) { tile_q[0] = PAIR ? (blockIdx.x >> 1) : blockIdx.x; mbar_arrive(&tq_full[0]); }
         for (uint32_t n = 0; next_tile() >= 0; ++n) {
-          if (pk == 0) {
+          if (PAIR && pk == 0) {                          // one tile per CTA pair
+            tile_q[(n + 1) & 3u] = 0xFFFFFFFFu;
+            mbar_arrive(&tq_full[(n + 1) & 3u]);
+          } else if (pk == 0) {
             // the ticket for tile n + 1, drawn now so that the weight stream never waits for it.  Exactly num_tiles tickets are
             // drawn per launch (one per tile started, CTA-first tiles included through the failing last draw of every CTA), so
             // the holder of the last one puts the counter back to zero for the next launch.
@@ -260,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tile_q[(n + 1) & 3u] = ticket + gridDim.x;
             mbar_arrive(&tq_full[(n + 1) & 3u]);
           }
-          for (int j = 0; j < kp.njobs; ++j) {
+          for (int j = 0; j < TC_NJOBS; ++j) {
             const uint32_t job = sjobs[j];
             const int nt = job_tiles(m, job);
             const uint8_t* src = m.tiles + (size_t)job_first_tile(m, job) * TILE_BYTES;
@@ -280,25 +277,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           }
         }
       }
-    } else {
-      // ============================== MMA issuer(s) ==============================
-      // Issuing a tcgen05.mma blocks the thread until the tensor pipe accepts it (tools/mma_queue.cu: n MMAs take n x 64 cycles on the
-      // issue side, the pipe holds one or two), so everything the issuing thread does between two jobs -- decoding the job,
-      // waiting for the accumulator to come back, barrier probes, ~150 cycles until the first MMA of a burst starts -- is time the
-      // tensor pipe idles.  With kp.dual TWO warps take turns: issuer i runs the jobs whose running number is i mod 2, does all
-      // of that preparation while the other one is still issuing, and then waits for its turn (an mbarrier the other issuer
-      // arrives on after its last MMA) -- tools/mma_dual.cu.  Both walk the whole job list and keep identical ring / phase
-      // state: mma_skip() advances it for the other issuer's jobs.  tcgen05.commit tracks the issuing thread's own MMAs only;
-      // the cross-job orderings that used to follow from "one thread, issue order" now rest on the pipe executing MMAs in the
-      // order it accepted them (a job's MMAs are accepted after the previous job's: that is what the turn barrier guarantees).
-      const uint32_t issuer = warp == 1 ? 0u : 1u;
-      uint32_t turn_phase = 0, gjob = 0;           // phase of turn[issuer]; running job number of this CTA
+    } else if (warp == 1) {
+      // ============================== MMA issuer ==============================
       // The whole warp walks the job list converged (waits are warp-wide); one elected lane issues.
       // Elected once while converged: the same lane issues every MMA and commit.  The warp stays converged and the election
       // predicate sits inside the asm statements (tc_prims.cuh, umma_*_p), which keeps the operands in uniform registers.
       const uint32_t lead = elect_one() ? 1u : 0u;
       uint32_t stage = 0, wphase = 0;
-      uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0, a2cnt = 0;
+      uint32_t ecnt[2] = {0, 0}, nbuf = 0, za_phase = 0;
       // bit c = parity to wait for.  h1 and XS have separate barriers: a shared one would let the
       // epilogue (reward layer 1 -> h1) complete a second phase before the MMA warp has waited for
       // the first (dynamics layer 2 -> XS), and a parity wait cannot tell the two apart.
@@ -314,14 +300,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       // issue; tile_release(slot) commits the slot that was just consumed.
       uint32_t ready = 0;                    // result of the early probe of w_full[stage]
       uint32_t cur_stage = 0;
-#ifdef TDMPC_TRACE_WAITS
-      long long tw[3] = {0, 0, 0};            // diagnosis build: cycles this job spent waiting for {accumulator, weight tile, operand data}
-#define TW(k, stmt) do { const long long _t0 = clock64(); stmt; tw[k] += clock64() - _t0; } while (0)
-#else
-#define TW(k, stmt) do { stmt; } while (0)
-#endif
       auto tile_acquire = [&]() -> uint32_t {
-        if (!ready) TW(1, mbar_wait(&w_full[stage], wphase, 2));
+        if (!ready) mbar_wait(&w_full[stage], wphase, 2);
         tcgen05_fence_after();
         cur_stage = stage;
         if (++stage == (uint32_t)S) { stage = 0; wphase ^= 1; }
@@ -332,33 +312,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         umma_commit_p(&w_empty[cur_stage], lead);
       };
       auto acc_acquire = [&](int b) {
-        TW(0, mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3));
+        mbar_wait(&acc_empty[b], (ecnt[b] & 1) ^ 1, 3);
         ++ecnt[b];
       };
       auto h1_wait = [&](int c) {
-        TW(2, mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4));
+        mbar_wait(&h1_full[c], (h1_phase >> c) & 1, 4);
         h1_phase ^= 1u << c;
       };
       auto xs_wait = [&](int c) {
-        TW(2, mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5));
+        mbar_wait(&xs_full[c], (xs_phase >> c) & 1, 5);
         xs_phase ^= 1u << c;
       };
       uint32_t hs_phase = 0;
       const uint32_t hs_addr = smem_u32(hs);
-      // Staged schedule (F_CP): h1 chunk c (k-blocks 2c, 2c+1) was written to XS by a layer-1 epilogue that ran while the tensor
-      // pipe still read the TMEM h1 buffer; move it there now.  tcgen05.cp executes in issue order with this thread's MMAs: behind
-      // the reward chain's layer-2 MMAs (the last readers of the buffer), ahead of the MMAs that consume the copy.
-      auto h1_stage = [&](int c) {
-        xs_wait(c);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int k2 = 0; k2 < 2; ++k2) {
-          const int kb = 2 * c + k2;
-          const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tmem_cp_p(tmem + TM_A + kb * 32 + ks * 8, umma_desc_make(alo + 2 * ks), lead);
-        }
-      };
       // one k-block (<= 4 k-steps of 16) with both operands in shared memory
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int nks, bool first) {
         const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
@@ -373,33 +339,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         else kblock_ss(d, za_addr + kb * TILE_BYTES, b_addr, idesc, min(4, ks1_total - kb * 4), first);
       };
 
-      for (int it = 0; next_tile() >= 0; ++it) {
-        // one job's MMAs; as in the epilogue, the fast path calls this with constant job words
-        auto mma_job = [&](const uint32_t job, const int j) __attribute__((always_inline)) {
+      for (int it = 0; next_tile() >= 0; ++it)
+        for (int j = 0; j < TC_NJOBS; ++j) {
+          const uint32_t job = kp.jw[TC_JOFF + j];
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
           const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
-          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
-          if (dual) {
-            // preparation that hides behind the other issuer's job: wait (without consuming the phase) for the first things this
-            // job needs -- the [z,a] operand, its accumulator(s), its first weight tile -- then for my turn
-            if (flags & F_WAIT_ZA) TW(2, mbar_wait_sleep(za_full, za_phase));
-            const bool q512 = type == J_QL1 || type == J_QL2;
-            const bool takes_acc = type == J_L1 ? !((flags & F_ACC2) && chunk == 2) : type == J_L2 ? !(flags & F_KHI) : type == J_L3 ? !(flags & (F_PARK | F_EPI)) : false;
-            if (takes_acc) TW(0, mbar_wait_sleep(&acc_empty[nbuf], (ecnt[nbuf] & 1) ^ 1));
-            if (q512) { TW(0, mbar_wait_sleep(&acc_empty[0], (ecnt[0] & 1) ^ 1)); TW(0, mbar_wait_sleep(&acc_empty[1], (ecnt[1] & 1) ^ 1)); }
-            if (gjob > 0) { mbar_wait_sleep(&turn[issuer], turn_phase); turn_phase ^= 1; }
-          }
-          if (flags & F_WAIT_ZA) { TW(2, mbar_wait(za_full, za_phase, 6)); za_phase ^= 1; }
+          if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
           if (DRNN && (flags & F_WAIT_HS)) { mbar_wait(hs_full, hs_phase, 10); hs_phase ^= 1; tcgen05_fence_after(); }
-          const bool staged = !DRNN && (flags & F_CP);
+          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
-            const bool acc2 = !DRNN && (flags & F_ACC2) && chunk == 2;        // third accumulator; the ping-pong count goes on as if b were used
-            if (acc2) { TW(0, mbar_wait(acc2_empty, (a2cnt & 1) ^ 1, 3)); ++a2cnt; }
-            else acc_acquire(b);
+            acc_acquire(b);
             tcgen05_fence_after();
-            const uint32_t d = acc2 ? tmem + TM_ACC2 : tmem + TM_ACC + b * 128;
+            const uint32_t d = tmem + TM_ACC + b * 128;
             if (DRNN && (flags & F_A_HS)) {
               // prior / reward layer 1 of the DRNN model: A = the hidden state h' (K = 128)
               for (int kb = 0; kb < 2; ++kb) {
@@ -414,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 tile_release();
               }
             }
-            umma_commit_p(acc2 ? acc2_full : &acc_full[b], lead);
+            umma_commit_p(&acc_full[b], lead);
             // every MMA issued so far -- the parked layer 3 and all layer-1 jobs that read this step's [z,a] -- complete
             if (!DRNN && (flags & F_D3)) umma_commit_p(d3_full, lead);
           } else if (DRNN && type == J_G) {
@@ -462,8 +415,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
                 const int kb = kb0 + k4;
-                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
-                TW(1, mbar_wait(&w_full[k4], wphase, 2));
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                mbar_wait(&w_full[k4], wphase, 2);
                 tcgen05_fence_after();
                 const uint32_t blo = ring_lo[k4];
                 const uint32_t a = tmem + TM_A + kb * 32;
@@ -476,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             } else {
               for (int k4 = 0; k4 < 4; ++k4) {
                 const int kb = kb0 + k4;
-                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
                 const uint32_t wt = tile_acquire();
                 const uint32_t blo = umma_desc_lo(wt);
                 const uint32_t a = tmem + TM_A + kb * 32;
@@ -508,8 +461,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
 #pragma unroll
               for (int kb = 0; kb < 8; ++kb) {
                 const int st = kb & 3;
-                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
-                TW(1, mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2));
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
+                mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
                 tcgen05_fence_after();
                 {
                   const uint32_t blo = ring_lo[st];
@@ -520,28 +473,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 }
               }
               ready = 0;                       // slot 0 again, same parity: the early probe must be redone
-            } else if (S == 4 && stage == 2) {
-              // the same with the ring half a turn on (staged schedule: two single-tile layer-1 jobs precede this one):
-              // k-block kb sits in slot (kb + 2) & 3, the parity flips after two and again after six k-blocks
-#pragma unroll
-              for (int kb = 0; kb < 8; ++kb) {
-                const int st = (kb + 2) & 3;
-                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
-                TW(1, mbar_wait(&w_full[st], wphase ^ (uint32_t)(((kb + 2) >> 2) & 1), 2));
-                tcgen05_fence_after();
-                {
-                  const uint32_t blo = ring_lo[st];
-                  const uint32_t a = tmem + TM_A + kb * 32;
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma_ts_p(d, a + ks * 8, umma_desc_make(blo + 2 * ks), idesc128, (kb | ks) ? 1u : 0u, lead);
-                  umma_commit_p(&w_empty[st], lead);
-                }
-              }
-              ready = 0;                       // slot 2 again, same parity
             } else {
 #pragma unroll
               for (int kb = 0; kb < 8; ++kb) {
-                if (chunk == 0 && (kb & 1) == 0) { if (staged) h1_stage(kb >> 1); else { h1_wait(kb >> 1); tcgen05_fence_after(); } }
+                if (chunk == 0 && (kb & 1) == 0) { h1_wait(kb >> 1); tcgen05_fence_after(); }
                 const uint32_t wt = tile_acquire();
                 {
                   const uint32_t blo = umma_desc_lo(wt);
@@ -586,7 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 const int st = kb >> 1;
                 if ((kb & 1) == 0) {
                   xs_wait(kb >> 1); tcgen05_fence_after();
-                  TW(1, mbar_wait(&w_full[st], wphase, 2));
+                  mbar_wait(&w_full[st], wphase, 2);
                   tcgen05_fence_after();
                 }
                 {
@@ -628,7 +563,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                 for (int kb = 0; kb < 8; ++kb) {
                   const int st = kb & 3;
                   if (c == 0 && (kb & 1) == 0) { xs_wait(kb >> 1); tcgen05_fence_after(); }
-                  TW(1, mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2));
+                  mbar_wait(&w_full[st], wphase ^ (uint32_t)(kb >> 2), 2);
                   tcgen05_fence_after();
                   {
                     const uint32_t alo = umma_desc_lo(xs_addr + kb * TILE_BYTES), blo = ring_lo[st];
@@ -654,83 +589,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
           }
           if (tr) kp.trace[(0 * MAX_JOBS + j) * 2 + 1] = clock64();
-#ifdef TDMPC_TRACE_WAITS
-          if (tr) { unsigned long long* w = kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * 256 + 2 * MAX_JOBS * 2 + j * 3; w[0] = tw[0]; w[1] = tw[1]; w[2] = tw[2]; }
-          tw[0] = tw[1] = tw[2] = 0;
-#endif
-          if (dual && lead) mbar_arrive(&turn[issuer ^ 1u]);      // every MMA of this job has been accepted by the pipe: next issuer
           __syncwarp();
-        };
-        // the other issuer's job: advance the weight ring position, the accumulator ping-pong and every barrier phase exactly as
-        // mma_job does, without waiting or issuing
-        auto mma_skip = [&](const uint32_t job) {
-          const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
-          auto ring_advance = [&](int n) {
-            const uint32_t pos = stage + (uint32_t)n;
-            wphase ^= (pos / (uint32_t)S) & 1u;
-            stage = pos % (uint32_t)S;
-            ready = 0;
-          };
-          if (flags & F_WAIT_ZA) za_phase ^= 1;
-          if (flags & F_BUF0) nbuf = 0;
-          const bool staged = (flags & F_CP) != 0;
-          if (type == J_L1) {
-            const int b = nbuf; nbuf ^= 1;
-            if ((flags & F_ACC2) && chunk == 2) ++a2cnt; else ++ecnt[b];
-            ring_advance(m.nkb1);
-          } else if (type == J_L2 && (flags & (F_KLO | F_KHI))) {
-            const bool hi = (flags & F_KHI) != 0;
-            const int b = nbuf; nbuf ^= 1;
-            if (!hi) ++ecnt[b];
-            if (chunk == 0) { if (staged) xs_phase ^= hi ? 0xCu : 0x3u; else h1_phase ^= hi ? 0xCu : 0x3u; }
-            ring_advance(4);
-          } else if (type == J_L2) {
-            const int b = nbuf; nbuf ^= 1;
-            ++ecnt[b];
-            if (chunk == 0) { if ((flags & F_A_XS) || staged) xs_phase ^= 0xFu; else h1_phase ^= 0xFu; }
-            ring_advance(8);
-          } else if (type == J_L3 && (flags & F_EPI)) {
-          } else if (type == J_L3) {
-            if (!(flags & F_PARK)) { const int b = nbuf; nbuf ^= 1; ++ecnt[b]; }
-            xs_phase ^= 0xFu;
-            ring_advance(m.l3rows[chain] == 128 ? 8 : 4);
-          } else {
-            ++ecnt[0]; ++ecnt[1];
-            if (type == J_QL2) xs_phase ^= 0xFu;
-            ring_advance(type == J_QL1 ? 4 * m.nkb1 : 32);
-          }
-        };
-        int j0 = 0;
-#ifdef TDMPC_TC_FAST
-        if (!DRNN && kp.fast) {
-#pragma unroll 1
-          for (int t = 0; t < p.H; ++t) {
-            const int jb = 17 * t;
-            mma_job(tc_job(J_L1, CH_DYN, 0, t, F_WAIT_ZA), jb);
-#pragma unroll 1
-            for (int c = 1; c < 4; ++c) mma_job(tc_job(J_L1, CH_DYN, c, t, F_ACC2), jb + c);
-            mma_job(tc_job(J_L2, CH_DYN, 0, t, 0), jb + 4);
-#pragma unroll 1
-            for (int c = 1; c < 4; ++c) mma_job(tc_job(J_L2, CH_DYN, c, t, 0), jb + 4 + c);
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) mma_job(tc_job(J_L1, CH_REW, c, t, F_ACC2), jb + 8 + c);
-            mma_job(tc_job(J_L3, CH_DYN, 0, t, 0), jb + 12);
-            mma_job(tc_job(J_L2, CH_REW, 0, t, 0), jb + 13);
-#pragma unroll 1
-            for (int c = 1; c < 4; ++c) mma_job(tc_job(J_L2, CH_REW, c, t, 0), jb + 13 + c);
-          }
-          j0 = 17 * p.H;
         }
-#endif
-        if (!dual) {
-          for (int j = j0; j < kp.njobs; ++j) mma_job(kp.jw[j], j);
-        } else {
-          for (int j = j0; j < kp.njobs; ++j, ++gjob) {
-            if ((gjob & 1u) == issuer) mma_job(kp.jw[j], j);
-            else mma_skip(kp.jw[j]);
-          }
-        }
-      }
     }
   } else {
     // ============================== epilogue: two warpgroups, thread = trajectory ==============================
@@ -746,7 +606,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     const int L = m.L, A = m.A;
     const long long total = (long long)p.B * p.T;
     uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
-    uint32_t a2f = 0, a2e = 0;                      // third accumulator: phases of acc2_full (owner group) / acc2_empty (chunk 3's group)
     uint32_t d3_phase = 0;                          // overlapped schedule: phase of d3_full (group 0 only)
     uint32_t x_phase = 0, ga = 0;                  // DRNN: phase of x_full / r_ready / u_ready, group that owns the reset gate of this step
     float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
@@ -756,18 +615,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     float* m_ssq = xch + (1 * 2 + grp) * 128;
     float* m_dot = xch + (2 * 2 + grp) * 128;
 
-    unsigned long long* trx = nullptr;              // trace: {accumulator ready, accumulator released} of the current job (or null)
     auto acc_wait = [&]() {
       mbar_wait(&acc_full[grp], fcnt & 1, 7);
       ++fcnt;
-      if (trx) trx[0] = clock64();
     };
     // early release: the accumulator goes back to the MMA warp as soon as it sits in registers (tmem_drain_aux)
     const int go_math = (kp.debug & 4) ? 0 : kp.one;     // experiment (bit 2): skip the activation math of the MLP layers (power probe, wrong results)
     const bool late_release = (kp.debug & 2) != 0;      // experiment: release after the activation math, as before
     auto acc_release = [&]() {
       if (!late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
-      if (trx) trx[1] = clock64();
     };
     auto acc_release_late = [&]() {
       if (late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
@@ -826,23 +682,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         mbar_arrive(za_full);
       }
 
-      // One job of this tile as seen by my epilogue group.  Called by the generic walk over the job list and -- with job words
-      // whose type, chain and flags are compile-time constants, so that the decode and every branch below fold away -- by the
-      // structured fast path of the plain value-mode schedule (the generic walk costs ~200 instructions per job per group).
-      auto epi_job = [&](const uint32_t job, const int j) __attribute__((always_inline)) {
+      // CTA-pair mailbox (global memory): rows [z_t | a_t] of this tile, Q1, and one flag word per slot
+      float* mb_rows = PAIR ? kp.m.pair_rows + (size_t)tile_idx * (TDMPC_MAX_H + 1) * 128 * m.K1p : nullptr;
+      float* mb_q1 = PAIR ? kp.m.pair_rows + (size_t)PAIR_MAX_TILES * (TDMPC_MAX_H + 1) * 128 * m.K1p + (size_t)tile_idx * 128 : nullptr;
+      unsigned int* mb_flags = PAIR ? kp.m.pair_flags + tile_idx * 32 : nullptr;
+      auto mb_publish = [&](int idx) {                 // my group's 128 threads have written their rows: make them visible, raise the flag
+        __threadfence();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        if ((threadIdx.x & 127) == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mb_flags + idx), "r"(1u) : "memory");
+      };
+      auto mb_wait = [&](int idx) {
+        const long long t0 = clock64();
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mb_flags + idx) : "memory");
+          if (!v && clock64() - t0 > 4000000000LL) asm volatile("trap;");
+        } while (!v);
+      };
+      auto mb_consume = [&](int idx, int idx2) {       // every thread of my group has read the slot: lower the flag(s) for the next launch
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        if ((threadIdx.x & 127) == 0) { mb_flags[idx] = 0u; if (idx2 >= 0) mb_flags[idx2] = 0u; }
+      };
+      for (int j = 0; j < TC_NJOBS; ++j) {
+        const uint32_t job = sjobs[j];
         const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, t = (job >> 8) & 31, flags = job >> 13;
         const TcChain& ch = m.chain[chain];
         const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && threadIdx.x % 128 == 0;
         unsigned long long* trp = kp.trace + ((1 + grp) * MAX_JOBS + j) * 2;
-        trx = tr ? kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * 256 + (grp * MAX_JOBS + j) * 2 : nullptr;
 
         if (DRNN && type >= J_G) {
           // ---- NormGRUCell (models/rnns.py:19-29): thread = trajectory, LayerNorm over the 128 gate values in-thread ----
-          if (type == J_GH) return;                                  // MMAs only
+          if (type == J_GH) continue;                                  // MMAs only
           if (type == J_G) {
             const int b = nbuf; nbuf ^= 1;
             if (chunk == 0) ga = (uint32_t)b;
-            if (b != grp) return;
+            if (b != grp) continue;
             if (tr) trp[0] = clock64();
             const uint32_t acc = tlane + TM_ACC + b * 128;
             acc_wait();
@@ -877,7 +751,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             tcgen05_fence_before();
             mbar_arrive(chunk == 0 ? r_ready : u_ready);
             if (tr) trp[1] = clock64();
-            return;
+            continue;
           }
           // J_GI: n = tanh(LN_n(gi_n + r * gh_n)); h' = u * n + (1 - u) * h  (rnns.py:27-28).  Both groups work on it, 64
           // columns each (it sits on the step's critical path); x = gi_n + r * gh_n stays in registers between the
@@ -944,23 +818,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           epi_bar_sync();                                   // both halves have read the gates (and the exchange slots)
           if (ga == (uint32_t)grp) { mbar_arrive(&acc_empty[0]); mbar_arrive(&acc_empty[1]); }
           if (tr) trp[1] = clock64();
-          return;
+          continue;
         }
         if (type <= J_L3) {
-          if (!DRNN && type == J_L3 && (flags & F_PARK)) return;             // MMAs only (overlapped schedule)
-          if (!DRNN && type == J_L2 && (flags & F_KLO)) return;              // first half of a split layer-2 chunk: MMAs only
+          if (!DRNN && type == J_L3 && (flags & F_PARK)) continue;             // MMAs only (overlapped schedule)
+          if (!DRNN && type == J_L2 && (flags & F_KLO)) continue;              // first half of a split layer-2 chunk: MMAs only
           const bool epi_only = !DRNN && type == J_L3 && (flags & F_EPI);      // epilogue of the parked layer 3: group 0
-          if (epi_only && grp != 0) return;
+          if (epi_only && grp != 0) continue;
           if (!DRNN && (flags & F_BUF0)) nbuf = 0;
           int b = grp;
           if (!epi_only) { b = nbuf; nbuf ^= 1; }
           const bool mine = b == grp;
           if (tr && (mine || (type == J_L2 && chain == CH_REW && chunk == 3))) trp[0] = clock64();
           if (type == J_L1) {
-            // third accumulator: both groups count its uses (its owner alternates with the ping-pong), one of them waits
-            uint32_t a2ph = 0;
-            if (!DRNN && (flags & F_ACC2)) { if (chunk == 2) a2ph = a2f++ & 1u; else if (chunk == 3) a2ph = a2e++ & 1u; }
-            if (!mine) return;
+            if (!mine) continue;
             if (!DRNN && (flags & F_TO_XS)) {
               // reward chain of the overlapped schedule: h1 chunk = ELU(acc + b1) -> bf16 -> XS (the layer-3 MMAs that read
               // XS were issued before this job's MMAs, so the accumulator barrier covers them)
@@ -985,7 +856,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               mbar_arrive(&xs_full[chunk]);
               acc_release_late();
               if (tr) trp[1] = clock64();
-              return;
+              continue;
             }
             if (DRNN && (flags & F_BN)) {
               // prior MLP layer 1: Linear, eval-mode BatchNorm1d (folded: y = acc * scale + shift'), ELU -> TMEM h1
@@ -1014,24 +885,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               tcgen05_fence_before();
               mbar_arrive(&h1_full[chunk]);
               acc_release_late();
-              return;
+              continue;
             }
             // h1 chunk = ELU(acc + b1) -> bf16x2 -> TMEM A-operand columns
             const float* bias = ch.b1 + chunk * 128;
             const uint32_t dst = tlane + TM_A + chunk * 64;
-            const bool acc2 = !DRNN && (flags & F_ACC2) && chunk == 2;       // third accumulator (tc_model.cuh)
-            const bool acc2w = !DRNN && (flags & F_ACC2) && chunk == 3;      // my h1 columns are the tail of that accumulator
             float4 x0[8];
             load8(bias, 0, x0);
-            if (acc2) { mbar_wait(acc2_full, a2ph, 7); if (trx) trx[0] = clock64(); }
-            else acc_wait();
+            acc_wait();
             tcgen05_fence_after();
-            auto release = [&]() {
-              if (acc2) { tcgen05_fence_before(); mbar_arrive(acc2_empty); if (trx) trx[1] = clock64(); }
-              else acc_release();
-              if (acc2w) { mbar_wait(acc2_empty, a2ph, 7); tcgen05_fence_after(); }
-            };
-            tmem_drain_aux(acc2 ? tlane + TM_ACC2 : tlane + TM_ACC + b * 128, x0, go_math, release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
+            tmem_drain_aux(tlane + TM_ACC + b * 128, x0, go_math, acc_release, [&](int s, float4 (&x)[8]) { load8(bias, s, x); },
                            [&](int s, uint32_t (&v)[32], float4 (&x)[8]) {
               uint32_t o[16];
 #pragma unroll
@@ -1146,7 +1009,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             if (tr && (mine || (!to_xs && chunk == 3))) trp[1] = clock64();
           } else {
-            if (!mine) return;
+            if (!mine) continue;
+            if (PAIR && epi_only) {
+              // CTA pair, rank 1: refill the [z,a] tile with the row rank 0 published for step t + 1 (last step: z_H and pi(z_H))
+              mbar_wait(d3_full, d3_phase, 15); d3_phase ^= 1;          // the reward's layer-1 MMAs have read the old tile
+              const bool lastf = (flags & F_LAST_STEP) != 0;
+              mb_wait(t + 1);
+              if (lastf) mb_wait(TDMPC_MAX_H + 1);
+              const float* mr = mb_rows + ((size_t)(t + 1) * 128 + row) * m.K1p;
+              for (int k0 = 0; k0 < (ckb >= 0 ? m.K1p : m.nkb1 * 64); k0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = (k0 + i < L + A) ? __ldcg(mr + k0 + i) : 0.0f;
+                za_store8(za, row, k0, v, ckb);
+              }
+              mb_consume(t + 1, lastf ? TDMPC_MAX_H + 1 : -1);
+              fence_proxy_async_smem();
+              mbar_arrive(za_full);
+              continue;
+            }
+            const bool pub = PAIR;                                     // CTA pair, rank 0: publish what goes into [z,a]
+            float* mrow = pub ? mb_rows + ((size_t)((chain == CH_DYN ? t + 1 : p.H)) * 128 + row) * m.K1p : nullptr;
             // the next step's actions of this row are fetched before waiting for the accumulator
             float an[8];
 #pragma unroll
@@ -1191,6 +1074,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                       const float4 bb = bz[c8 * 2 + (i >> 2)];
                       o[i] = __uint_as_float(v[c8 * 8 + i]) + ((i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w);
                     }
+                    if (pub) {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) if (kk + i < L) mrow[kk + i] = o[i];
+                    }
                     if (kk + 8 <= L) za_store8(za, row, kk, o, ckb);
                     else {
                       // the 8-column group that also holds action columns: z elements only
@@ -1202,8 +1089,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
               if (next_act) {
 #pragma unroll
-                for (int a = 0; a < 8; ++a) if (a < A) za_store1(za, row, L + a, an[a], ckb);
-                for (int a = 8; a < A; ++a) za_store1(za, row, L + a, valid ? __ldg(act_row + (size_t)(t + 1) * A + a) : 0.0f, ckb);
+                for (int a = 0; a < 8; ++a) if (a < A) { za_store1(za, row, L + a, an[a], ckb); if (pub) mrow[L + a] = an[a]; }
+                for (int a = 8; a < A; ++a) {
+                  const float av = valid ? __ldg(act_row + (size_t)(t + 1) * A + a) : 0.0f;
+                  za_store1(za, row, L + a, av, ckb);
+                  if (pub) mrow[L + a] = av;
+                }
               }
             } else {
               // a = clamp(tanh(acc + b3) + clip(eps * std)), written to the action columns of [z,a]
@@ -1230,6 +1121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                       if (!terminal) pi_row[(size_t)t * A + a] = x;
                     }
                     if (!(flags & F_LAST_STEP)) za_store1(za, row, L + a, x, ckb);
+                    if (pub && terminal) mrow[L + a] = x;
                   }
                 }
 #pragma unroll
@@ -1242,6 +1134,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               fence_proxy_async_smem();
               mbar_arrive(za_full);
             }
+            // CTA pair: raise the mailbox flag AFTER my own MMA warp has been released (the fence costs ~1 us; rank 1 has slack)
+            if (pub && (chain == CH_DYN || terminal)) mb_publish(chain == CH_DYN ? t + 1 : TDMPC_MAX_H + 1);
             if (tr) trp[1] = clock64();
           }
         } else {
@@ -1329,6 +1223,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             epi_bar_sync();
             if (grp == 0) {
               const float qv = (qdot + x_dot[row]) + __ldg(ch.b3);
+              if (PAIR) {
+                if (chain == CH_Q1) { mb_q1[row] = qv; mb_publish(TDMPC_MAX_H + 2); }           // rank 0 -> rank 1
+                else { mb_wait(TDMPC_MAX_H + 2); q1v = __ldcg(mb_q1 + row); mb_consume(TDMPC_MAX_H + 2, -1); }
+              }
               if (chain == CH_Q1) q1v = qv;
               else if (valid) {
                 // G += discount * min(Q1, Q2); nan_to_num_   (tdmpc.py:91-92)
@@ -1342,29 +1240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           mbar_arrive(&acc_empty[grp]);
           if (tr) trp[1] = clock64();
         }
-      };
-      int j0 = 0;
-#ifdef TDMPC_TC_FAST      // experiment (DESIGN.md 4.1, round 2 second session): measured slower -- the specialised copies do not share instruction-cache lines
-      if (!DRNN && kp.fast) {
-        // plain value-mode schedule (build_jobs): per step L1 dyn x4, L2 dyn x4, L1 rew x4, L3 dyn, L2 rew x4
-#pragma unroll 1
-        for (int t = 0; t < p.H; ++t) {
-          const int jb = 17 * t;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L1, opaque3(CH_DYN), c, t, F_ACC2), jb + c);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L2, opaque3(CH_DYN), c, t, 0), jb + 4 + c);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L1, opaque3(CH_REW), c, t, F_ACC2), jb + 8 + c);
-          if (t == p.H - 1) epi_job(tc_job(J_L3, opaque3(CH_DYN), 0, t, F_LAST_STEP), jb + 12);
-          else epi_job(tc_job(J_L3, opaque3(CH_DYN), 0, t, 0), jb + 12);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) epi_job(tc_job(J_L2, opaque3(CH_REW), c, t, 0), jb + 13 + c);
-        }
-        j0 = 17 * p.H;
       }
-#endif
-      for (int j = j0; j < kp.njobs; ++j) epi_job(sjobs[j], j);
       if (kp.trace && blockIdx.x == 0 && threadIdx.x == 128 && it < 128) {
         unsigned long long ns;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
@@ -1426,11 +1302,38 @@ int launch_pack(const float* W, int N, int K, uint8_t* dst, int n_chunks, int nk
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-// value-mode schedule of the MLP model: 0 plain, 1 / 2 staged (two job orders); TDMPC_TC_STAGED overrides the default
-int staged_schedule() { const char* e = getenv("TDMPC_TC_STAGED"); return e ? atoi(e) : 0; }
-
-std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) {
+std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0, int* pair_n0 = nullptr) {
   std::vector<uint32_t> j;
+  if (mode == 2) {
+    // Value mode over a CTA PAIR (launches of a few tiles: single-environment plans, where one tile's serial chain through H + 2
+    // networks is the whole latency).  The reward chain never feeds back into z, so rank 0 runs the dynamics chain, the terminal
+    // policy and Q1 and publishes every [z_t | a_t] row through a global-memory mailbox; rank 1 follows one step behind with the
+    // reward chain (it owns the discounted return) and Q2, and forms the value.  Rank 1's [z,a] tile is refilled from the mailbox
+    // by an epilogue-only job (J_L3 | F_EPI) once the MMA warp's d3_full commit says the reward's layer 1 has read the old one.
+    if (drnn) return j;
+    auto c12 = [&](int type, int chain, int t, int first_flags, int last_flags = 0) {
+      for (int c = 0; c < 4; ++c) j.push_back(tc_job(type, chain, c, t, (c == 0 ? first_flags : 0) | (c == 3 ? last_flags : 0)));
+    };
+    for (int t = 0; t < H; ++t) {
+      c12(J_L1, CH_DYN, t, F_WAIT_ZA);
+      c12(J_L2, CH_DYN, t, 0);
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, t == H - 1 ? F_LAST_STEP : 0));
+    }
+    c12(J_L1, CH_PI, 0, F_WAIT_ZA);
+    c12(J_L2, CH_PI, 0, 0);
+    j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
+    j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
+    j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
+    if (pair_n0) *pair_n0 = (int)j.size();
+    for (int t = 0; t < H; ++t) {
+      c12(J_L1, CH_REW, t, F_WAIT_ZA, F_D3);
+      c12(J_L2, CH_REW, t, 0);
+      j.push_back(tc_job(J_L3, CH_DYN, 0, t, F_EPI | (t == H - 1 ? F_LAST_STEP : 0)));     // refill [z_{t+1} | a_{t+1}] (last: [z_H | pi(z_H)])
+    }
+    j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, F_WAIT_ZA));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+    return j;
+  }
   auto chain12 = [&](int type, int chain, int t, int first_flags) {
     for (int c = 0; c < 4; ++c) j.push_back(tc_job(type, chain, c, t, c == 0 ? first_flags : 0));
   };
@@ -1484,33 +1387,7 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0) 
     j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
     return j;
   }
-  if (mode == MODE_VALUE && staged_schedule() && !getenv("TDMPC_TC_OVERLAP")) {
-    // Staged schedule.  In the plain schedule the tensor pipe idles through every layer-1 epilogue (the one TMEM h1 buffer makes
-    // each chain's layer 2 wait for its own layer 1: ~12 k of a 41 k-cycle step).  Here the layer 1 of the NEXT consumer of z'
-    // (N: dynamics of step t+1, or the terminal policy) is interleaved with the reward chain's 512 x 512 layer (R, TS mode from
-    // the h1 buffer): its epilogue writes the activation to XS -- idle between the dynamics' layer 3 and the next layer-2
-    // epilogue -- and the consumer's first layer-2 job copies it into the h1 buffer (tcgen05.cp, F_CP) once R has been issued.
-    // R0 R1 first: they only need the reward's h1, while N0 has to wait for z' (layer 3 + its epilogue); R3 last, so the
-    // reward combine (a barrier over both epilogue groups) does not hold up a layer-1 epilogue the copy is waiting for.
-    chain12(J_L1, CH_DYN, 0, F_WAIT_ZA);
-    for (int t = 0; t < H; ++t) {
-      const bool last = t == H - 1;
-      chain12(J_L2, CH_DYN, t, t > 0 ? F_CP : 0);
-      chain12(J_L1, CH_REW, t, 0);
-      j.push_back(tc_job(J_L3, CH_DYN, 0, t, last ? F_LAST_STEP : 0));
-      const int nch = last ? CH_PI : CH_DYN, nt = last ? 0 : t + 1;
-      auto R = [&](int c) { j.push_back(tc_job(J_L2, CH_REW, c, t, 0)); };
-      auto N = [&](int c) { j.push_back(tc_job(J_L1, nch, c, nt, F_TO_XS | (c == 0 ? F_WAIT_ZA : 0))); };
-      if (staged_schedule() == 2) { R(0); R(1); N(0); N(1); R(2); N(2); N(3); R(3); }
-      else { R(0); R(1); N(0); N(1); N(2); N(3); R(2); R(3); }      // keeps every 512 x 512 job on slot 0 of a 4-slot ring for any k-block count
-    }
-    chain12(J_L2, CH_PI, 0, F_CP);
-    j.push_back(tc_job(J_L3, CH_PI, 0, 0, F_TERMINAL));
-    j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
-    j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
-    j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
-    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
-  } else if (mode == MODE_VALUE && !getenv("TDMPC_TC_OVERLAP")) {
+  if (mode == MODE_VALUE && !getenv("TDMPC_TC_OVERLAP")) {
     // the plain schedule (default): dynamics and reward alternate on the one TMEM h1 buffer
     for (int t = 0; t < H; ++t) {
       chain12(J_L1, CH_DYN, t, F_WAIT_ZA);
@@ -1606,7 +1483,7 @@ static int tc_tiles_total(const tdmpc_model_cfg& c, int* nkb1_out, int l3rows[CH
 
 static size_t jobs_bytes_total() {
   size_t n = 0;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 3; ++mode)
     for (int H = 1; H <= TDMPC_MAX_H; ++H) n += (build_jobs(mode, H).size() + 3) & ~(size_t)3;
   return n * sizeof(uint32_t);
 }
@@ -1706,9 +1583,9 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   uint32_t* jdst = reinterpret_cast<uint32_t*>(base + (size_t)tiles * TILE_BYTES);
   std::vector<uint32_t> all;
   size_t off = 0;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 3; ++mode)
     for (int H = 1; H <= TDMPC_MAX_H; ++H) {
-      std::vector<uint32_t> j = build_jobs(mode, H, drnn, A);
+      std::vector<uint32_t> j = build_jobs(mode, H, drnn, A, &m.pair_n0[H]);
       m.jobs[mode][H] = jdst + off;
       m.njobs[mode][H] = (int)j.size();
       j.resize((j.size() + 3) & ~(size_t)3, 0);
@@ -1724,7 +1601,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
     memcpy(hj, all.data(), all.size() * sizeof(uint32_t));
     free(const_cast<uint32_t*>(out->jobs_host));          // re-pack of the same handle
     m.jobs_host = hj;
-    for (int mode = 0; mode < 2; ++mode)
+    for (int mode = 0; mode < 3; ++mode)
       for (int H = 1; H <= TDMPC_MAX_H; ++H) m.jobs_off[mode][H] = (int)(m.jobs[mode][H] - jdst);
   }
 
@@ -1733,7 +1610,7 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   // (K = 138 -> 128 + 16) that is the difference between a 2-slot and a 3-slot weight ring
   m.za_compact = (!drnn && nkb1 >= 2 && m.K1p - 64 * (nkb1 - 1) == 16 && !getenv("TDMPC_TC_NO_COMPACT")) ? 1 : 0;
   m.za_bytes = m.za_compact ? (nkb1 - 1) * TILE_BYTES + K16_BLOCK_BYTES : nkb1 * TILE_BYTES;
-  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 30) * 8 + 32 + 1024;
+  const int fixed = XS_BYTES + m.za_bytes + (XCH_FLOATS + QC_FLOATS) * 4 + MAX_JOBS * 4 + (2 * MAX_STAGES + 26) * 8 + 32 + 1024;
   int stages = (SMEM_LIMIT - fixed) / TILE_BYTES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages == 5) stages = 4;          // the producers split the ring evenly
@@ -1742,27 +1619,39 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
   // The attribute is per function AND per device, not per handle: always raise it to the fixed maximum, so handles with
   // different shapes (or on different GPUs of one process) cannot shrink each other's limit.
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  m.pair_mode = (!drnn && !getenv("TDMPC_TC_NOPAIR")) ? 1 : 0;
+  m.pair_rows = out->pair_rows; m.pair_flags = out->pair_flags;          // kept across re-packs of the same handle
+  if (m.pair_mode && !m.pair_rows) {
+    const size_t rows = (size_t)PAIR_MAX_TILES * (TDMPC_MAX_H + 1) * 128 * m.K1p + (size_t)PAIR_MAX_TILES * 128;
+    if (cudaMalloc(&m.pair_rows, rows * sizeof(float)) != cudaSuccess) return -1;
+    if (cudaMalloc(&m.pair_flags, PAIR_MAX_TILES * 32 * sizeof(unsigned int)) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(m.pair_flags, 0, PAIR_MAX_TILES * 32 * sizeof(unsigned int), st) != cudaSuccess) return -1;
+  }
   m.exact_act = c.precision == TDMPC_PREC_BF16_EXACT ? 1 : 0;
-  m.fast_value = (!drnn && staged_schedule() == 0 && !getenv("TDMPC_TC_OVERLAP") && !getenv("TDMPC_TC_SPLIT") && !getenv("TDMPC_TC_NOFAST")) ? 1 : 0;
   { const char* e = getenv("TDMPC_TC_DEBUG"); m.debug = e ? atoi(e) : 0; }
   m.producers = m.stages % 2 == 0 ? 2 : (m.stages % 3 == 0 ? 3 : 1);
   if (const char* e = getenv("TDMPC_TC_PRODUCERS")) { const int v = atoi(e); if (v >= 1 && v <= 3 && m.stages % v == 0) m.producers = v; }
-  m.dual_issue = getenv("TDMPC_TC_DUAL") ? 1 : 0;        // measured slower: off unless asked for
   *out = m;
   return launches;
 }
 
 void tc_release_host(TcModel* m) {
-  if (m) { free(const_cast<uint32_t*>(m->jobs_host)); m->jobs_host = nullptr; }
+  if (m) {
+    free(const_cast<uint32_t*>(m->jobs_host)); m->jobs_host = nullptr;
+    if (m->pair_rows) { cudaFree(m->pair_rows); m->pair_rows = nullptr; }
+    if (m->pair_flags) { cudaFree(m->pair_flags); m->pair_flags = nullptr; }
+  }
 }
 
 static unsigned long long* g_tc_trace = nullptr;
 void tc_set_trace(unsigned long long* dev_buf) { g_tc_trace = dev_buf; }
-int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256 + 4 * 256 + 2 * MAX_JOBS * 2 + 3 * MAX_JOBS; }   // ... + MMA-warp wait cycles (-DTDMPC_TRACE_WAITS)      // ... + {accumulator ready, released} per group and job      // + end-of-tile stamps of block 0's first 128 tiles + per-block stats
+int tc_trace_slots() { return 3 * MAX_JOBS * 2 + 256 + 4 * 256; }      // + end-of-tile stamps of block 0's first 128 tiles + per-block stats
 
 int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st) {
   if (p.H < 1 || p.H > TDMPC_MAX_H) return -1;
@@ -1778,21 +1667,29 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.tile_counter = m.tile_counter;
   kp.debug = m.debug;
   kp.producers = m.producers;
-  kp.dual = (!m.drnn && m.producers <= 2 && m.dual_issue) ? 1 : 0;
-#ifdef TDMPC_TC_FAST
-  kp.fast = (m.fast_value && p.mode == MODE_VALUE && kp.njobs == 17 * p.H + 13) ? 1 : 0;
-#else
-  kp.fast = 0;
-#endif
-  const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
-  if (kp.njobs <= 0 || kp.njobs > MAX_JOBS || !m.jobs_host) return -1;
-  memcpy(kp.jw, m.jobs_host + m.jobs_off[p.mode][p.H], sizeof(uint32_t) * kp.njobs);
+  // CTA pairs for launches of a few tiles (single-environment plans): halves the serial chain of a tile
+  // (with the 3-slot weight ring of dog-run dims the pair measured 7 % slower than one CTA: single CTA there)
+  kp.pair = (m.pair_mode && m.pair_rows && m.stages >= 4 && p.mode == MODE_VALUE && kp.num_tiles <= PAIR_MAX_TILES && 2 * kp.num_tiles <= num_sms &&
+             !g_tc_trace) ? 1 : 0;
+  kp.njobs1 = 0; kp.j1off = 0;
+  if (kp.pair) {
+    kp.jobs = m.jobs[2][p.H];
+    kp.njobs = m.pair_n0[p.H];
+    kp.njobs1 = m.njobs[2][p.H] - kp.njobs;
+    kp.j1off = kp.njobs;
+  }
+  const int grid = kp.pair ? 2 * kp.num_tiles : (kp.num_tiles < num_sms ? kp.num_tiles : num_sms);
+  if (kp.njobs <= 0 || kp.njobs + kp.njobs1 > MAX_JOBS || !m.jobs_host) return -1;
+  memcpy(kp.jw, m.jobs_host + m.jobs_off[kp.pair ? 2 : p.mode][p.H], sizeof(uint32_t) * (kp.njobs + kp.njobs1));
   if (m.drnn) {
-    if (m.exact_act) rollout_tc_kernel<true, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    if (m.exact_act) rollout_tc_kernel<true, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<true, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   } else {
-    if (m.exact_act) rollout_tc_kernel<false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    if (kp.pair) {
+      if (m.exact_act) rollout_tc_kernel<false, true, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+      else rollout_tc_kernel<false, false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    } else if (m.exact_act) rollout_tc_kernel<false, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   }
   return 1;
 }

@@ -21,6 +21,7 @@ enum TcJobType {
   J_GI = 7     // gi_n = [z,a] x W_ih[newval] -> Y (columns 384-511); epilogue: n = tanh(LN(gi_n + r gh_n)),
                //   h' = u n + (1-u) h -> fp32 state + bf16 operand HS
 };
+constexpr int PAIR_MAX_TILES = 16;        // CTA-pair mode: launches of at most this many 128-trajectory tiles
 enum TcJobFlags {
   F_WAIT_ZA = 1, F_LAST_STEP = 2, F_TERMINAL = 4,
   F_WAIT_HS = 8,     // MMA: first consumer of a freshly written hidden-state operand HS
@@ -41,21 +42,10 @@ enum TcJobFlags {
   // (F_KLO, no epilogue), which are written first, and later over the rest (F_KHI, epilogue as usual).  The tensor pipe
   // then has two half-jobs of work while the layer-1 epilogue is still producing h1 chunks 2-3.
   F_KLO = 32768,     // J_L2: k-blocks 0-3 only; acquires the accumulator, no commit, no epilogue
-  F_KHI = 65536,     // J_L2: k-blocks 4-7 onto the accumulator its F_KLO half started; commit + epilogue
-  // Staged schedule (value mode, MLP dynamics): the layer-1 epilogue of the NEXT consumer of z' (dynamics of step t+1, or the
-  // terminal policy) runs while the tensor pipe works on the reward chain's 512 x 512 layer (TS mode, h1 buffer busy), writes
-  // its activation to XS (F_TO_XS) -- and the MMA thread then moves it into the TMEM h1 buffer with tcgen05.cp, so that the
-  // consumer's layer 2 still runs TS-mode (an SS-mode layer 2 is bound by its shared-memory operand reads: 125 vs 85 cycles).
-  F_CP = 131072,     // J_L2 chunk 0: h1 arrives in XS (xs_full), copied chunk by chunk into the TMEM h1 buffer ahead of its MMAs
-  // Third accumulator for the layer-1 jobs (structured fast path).  A layer-1 job is 4 MMAs; with two accumulators its chunks
-  // run at the pace of the accumulator round trip (MMAs complete -> commit -> epilogue wakes -> drains -> arrives -> the issuing
-  // thread sees it), ~1 k cycles per job.  While a layer 1 is computed the h1 buffer it will fill is still empty, so chunk 2
-  // accumulates in columns [384, 512) -- where the h1 chunks 2 and 3 will go: its own epilogue pulls the accumulator into
-  // registers before it writes chunk 2, and the epilogue of chunk 3 waits for that drain (acc2_empty) before it writes.
-  F_ACC2 = 262144    // J_L1 chunk 2: accumulate in TM_ACC2 (barriers acc2_full / acc2_empty); chunk 3: wait for chunk 2's drain
+  F_KHI = 65536      // J_L2: k-blocks 4-7 onto the accumulator its F_KLO half started; commit + epilogue
 };
 
-// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,31)
+// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,28)
 __host__ __device__ inline uint32_t tc_job(int type, int chain, int chunk, int t, int flags) {
   return (uint32_t)type | ((uint32_t)chain << 3) | ((uint32_t)chunk << 6) | ((uint32_t)t << 8) | ((uint32_t)flags << 13);
 }
@@ -77,19 +67,22 @@ struct TcModel {
   int za_bytes;                // shared-memory size of the [z,a] operand
   int n3p[CH_COUNT];           // L3 MMA N (multiple of 16) for dyn / pi
   int l3rows[CH_COUNT];        // rows per L3 weight k-block tile: 64 or 128
-  const uint32_t* jobs[2][TDMPC_MAX_H + 1];   // [mode][H] device job lists
-  int njobs[2][TDMPC_MAX_H + 1];
+  const uint32_t* jobs[3][TDMPC_MAX_H + 1];   // [mode][H] device job lists; mode 2: value mode split over a CTA pair (rank 0 | rank 1)
+  int njobs[3][TDMPC_MAX_H + 1];
+  int pair_n0[TDMPC_MAX_H + 1];                // pair programs: jobs of rank 0 (rank 1's follow)
   int stages;                  // weight ring depth that fits in shared memory
   size_t smem_bytes;
   // host-side launch state, fixed when the weights are packed (environment switches are read THERE, not per launch)
   const uint32_t* jobs_host;   // host copy of every job program (owned by the handle: tc_release_host)
-  int jobs_off[2][TDMPC_MAX_H + 1];
+  int jobs_off[3][TDMPC_MAX_H + 1];
   int debug;                   // TDMPC_TC_DEBUG (experiments only)
   int producers;               // producer threads of the weight ring (divides `stages`)
   int exact_act;               // TDMPC_PREC_BF16_EXACT: two-MUFU tanh in the Q heads instead of tanh.approx
-  int fast_value;              // the value-mode job list is the plain schedule: structured walk instead of the generic one
-  int dual_issue;              // two MMA-issuing warps take turns (MLP model with <= 2 producer warps); experiment, TDMPC_TC_DUAL=1 switches it on
   unsigned int* tile_counter;  // device word of the dynamic tile scheduler (arena tail; zero between launches)
+  // CTA-pair mode for launches of a few tiles (single-environment plans): mailbox between the dynamics CTA and the reward CTA
+  float* pair_rows;            // [PAIR_MAX_TILES][TDMPC_MAX_H + 1][128][K1p] fp32 rows [z_t | a_t] published by rank 0; then [PAIR_MAX_TILES][128] Q1
+  unsigned int* pair_flags;    // [PAIR_MAX_TILES][32]: slot t published (1) / consumed (0); [TDMPC_MAX_H + 1]: terminal action, [TDMPC_MAX_H + 2]: Q1
+  int pair_mode;               // 0 off (TDMPC_TC_NOPAIR), 1 on
   // DRNN (TDMPC_DYN_DRNN): chain CH_DYN is the prior MLP (layer 1: K = hidden_dim, layer 3 slot = its second Linear),
   // chain CH_REW's layer 1 reads the hidden state; gate weights live in their own tiles.
   int drnn;

@@ -59,22 +59,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
-// Wait that lets the hardware suspend the thread (suspend-time hint, ns) instead of re-polling shared memory: for waits that are
-// expected to be long (the other MMA issuer's whole job).  Still bounded.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(200000u) : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
-  }
-}
-
 // ------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -307,13 +291,6 @@ __device__ __forceinline__ void umma_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint
       "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead) : "memory");
-}
-// shared memory -> tensor memory, 128 lanes x 256 bits: one K = 16 slice of a K-major bf16 operand tile (the descriptor an SS-mode
-// A operand would use) lands as 8 columns of the TS-mode A operand (lane = row, column = two consecutive k).  Executes in issue
-// order with the MMAs of the same thread (tools/tc_cp_probe.cu checks the layout).  SASS: UTCCP.
-__device__ __forceinline__ void tmem_cp_p(uint32_t taddr, uint64_t sdesc, uint32_t lead) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-               "@q tcgen05.cp.cta_group::1.128x256b [%0], %1;\n\t}" ::"r"(taddr), "l"(sdesc), "r"(lead) : "memory");
 }
 __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t lead) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"

@@ -234,7 +234,7 @@ def test_integer_exact_rollout(cfg_name, precision):
 
 
 @pytest.mark.parametrize("cfg_name", ["cfg3", "cfg2", "k80"])
-@pytest.mark.parametrize("switch", ["TDMPC_TC_OVERLAP", "TDMPC_TC_SPLIT", "TDMPC_TC_STAGED=1", "TDMPC_TC_STAGED=2", "TDMPC_TC_STAGED=0", "TDMPC_TC_DUAL=1"])
+@pytest.mark.parametrize("switch", ["TDMPC_TC_OVERLAP", "TDMPC_TC_SPLIT", "TDMPC_TC_NOPAIR"])
 def test_alternative_schedules_stay_bit_exact(switch, cfg_name, monkeypatch):
     """The two alternative job programs of rollout_tc_kernel that are kept behind environment switches (DESIGN.md 4.1:
     measured slower, so off by default) -- the overlapped dynamics / reward schedule and the split-k layer 2 -- walk
@@ -242,8 +242,8 @@ def test_alternative_schedules_stay_bit_exact(switch, cfg_name, monkeypatch):
     first-iteration values of a whole plan must agree with the default schedule's to fp32 summation order (the reward
     head's partial sums are grouped differently)."""
     gu = _gu()
-    if cfg_name != "cfg3" and not switch.startswith(("TDMPC_TC_STAGED", "TDMPC_TC_DUAL")):
-        pytest.skip("the older alternatives are kept for cfg3 only")
+    if cfg_name != "cfg3" and switch != "TDMPC_TC_NOPAIR":
+        pytest.skip("the alternative schedules are kept for cfg3 only")
     cfg = synth.make_cfg(cfg_name)
     sd = _integer_model(cfg, 11)
     H, L, A = cfg.horizon, cfg.latent_dim, cfg.action_dim
@@ -254,13 +254,12 @@ def test_alternative_schedules_stay_bit_exact(switch, cfg_name, monkeypatch):
     sd2 = synth.make_told_weights(cfg, 3)
     obs = torch.from_numpy(np.stack([synth.make_obs(cfg, 70 + b) for b in range(2)])).cuda()
     kw = gu.plan_kwargs(cfg)
-    name, _, val = switch.partition("=")
-    # the reference run uses the OTHER setting of the staged switch (it became the default once measured faster)
-    monkeypatch.setenv("TDMPC_TC_STAGED", "1" if switch == "TDMPC_TC_STAGED=0" else "0")
+    # the reference runs take the default path: CTA pairs for these few-tile launches (rollout_tc.cu, build_jobs mode 2), so
+    # TDMPC_TC_NOPAIR compares the pair program with the single-CTA program, the other two the single-CTA alternatives
     ref = gu.make_planner(cfg, sd2, "bf16").plan(obs, **kw, eval_mode=False, t0=True, seed=3, call=4, taps=True)
     torch.cuda.synchronize()
-    if name != "TDMPC_TC_STAGED": monkeypatch.setenv("TDMPC_TC_STAGED", "0")
-    monkeypatch.setenv(name, val or "1")               # read when the job programs are built (set_weights) and at launch
+    monkeypatch.setenv(switch, "1")                    # read when the job programs are built (set_weights) and at launch
+    if switch != "TDMPC_TC_NOPAIR": monkeypatch.setenv("TDMPC_TC_NOPAIR", "1")
     pl = gu.make_planner(cfg, sd, "bf16")
     v_g, _ = pl.estimate_value(z0, actions, discount=cfg.discount, min_std=0.0)
     torch.cuda.synchronize()

@@ -26,9 +26,8 @@ lib.tdmpc_debug_set_trace(C.c_void_p(buf.data_ptr()))
 pl.estimate_value(z0, acts, discount=cfg.discount, min_std=cfg.min_std, seed=1, call=1)
 torch.cuda.synchronize(); lib.tdmpc_debug_set_trace(None)
 raw = buf.cpu().numpy()
-MJ = (n - 1280) // 13
-mw = raw[-3 * MJ:].reshape(MJ, 3); raw = raw[:-3 * MJ]           # MMA warp: cycles waiting for accumulator / weight tile / operand data
-ext = raw[-4 * MJ:].reshape(2, MJ, 2); raw = raw[:-4 * MJ]       # per group and job: accumulator ready, accumulator released
+MJ = (n - 1280) // 6
+has_ext = False      # builds with the finer stamps (git history: eafe16c, -DTDMPC_TRACE_WAITS) append [2][MJ][2] + [MJ][3] words
 blk = raw[-1024:].reshape(256, 4); raw = raw[:-1024]
 ends = raw[-256:-128]; ns = raw[-128:][ends > 0]; ends = ends[ends > 0]
 tr = raw[:-256].reshape(3, -1, 2)
@@ -39,16 +38,12 @@ nj = lib.tdmpc_debug_jobs(pl._h, 0, H, words, 1024)
 names = ["L1", "L2", "L3", "QL1", "QL2", "G", "GH", "GI"]; chains = ["dyn", "rew", "pi", "q1", "q2"]
 jobs = [(w & 7, (w >> 3) & 7, (w >> 6) & 3, (w >> 8) & 31) for w in words[:nj]]
 t0 = tr[0, 0, 0]
-print(f"{'job':>4} {'what':14} | {'mma start':>9} {'mma end':>9} {'dur':>6} | {'epi0 start':>10} {'end':>8} {'dur':>6} | {'epi1 start':>10} {'end':>8} {'dur':>6} | epilogue: start->acc ready->released->end")
+print(f"{'job':>4} {'what':14} | {'mma start':>9} {'mma end':>9} {'dur':>6} | {'epi0 start':>10} {'end':>8} {'dur':>6} | {'epi1 start':>10} {'end':>8} {'dur':>6} ")
 for j, (ty, chn, c, t) in enumerate(jobs):
     row = [f"{j:4d} {names[ty] + ' ' + chains[chn] + ' c' + str(c) + ' t' + str(t):14}"]
     for r in range(3):
         s_, e_ = tr[r, j]
         row.append(f"{(s_ - t0) if s_ else 0:>10} {(e_ - t0) if e_ else 0:>8} {(e_ - s_) if s_ and e_ else 0:>6}")
-    for g in range(2):
-        s_, e_ = tr[1 + g, j]; rd, rl = ext[g, j]
-        if s_ and e_ and rd: row.append(f"g{g} wait {rd - s_:5d} drain {rl - rd if rl else 0:5d} math {e_ - (rl or rd):5d}")
-    if mw[j].any(): row.append(f"mma waits acc {mw[j, 0]:5d} tile {mw[j, 1]:5d} data {mw[j, 2]:5d}")
     print(" | ".join(row))
 print("tile total cycles:", tr[:, :len(jobs), 1].max() - t0)
 print("tile periods of block 0 (cycles):", " ".join(str(int(x)) for x in np.diff(ends)))
