@@ -147,12 +147,16 @@ __device__ __forceinline__ void za_store8(uint8_t* za, int row, int k0, const fl
 
 // PAIR: the CTA-pair variant (kp.pair launches) is its own instantiation -- merely branching around its mailbox code costs the
 // ordinary kernel registers and spills in the epilogues (measured: 3 - 5 %).
-template <bool DRNN, bool EXACT, bool PAIR>
+// ALT: the alternative value-mode schedules behind TDMPC_TC_OVERLAP / TDMPC_TC_SPLIT (parked layer 3, reward activation in XS, split-k
+// layer 2) -- their branches too are compiled into their own instantiation only (ALTS below), not into the kernel the bench times.
+// TRACE: the clock64 stamps of tools/trace_rollout.py (a per-job 64-bit stamp pointer lives across the epilogue math otherwise).
+template <bool DRNN, bool EXACT, bool PAIR, bool ALT, bool TRACE>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcModel& m = kp.m;
   const RolloutParams& p = kp.p;
   const int S = kp.stages;
+  unsigned long long* const ktrace = TRACE ? kp.trace : nullptr;
 
   // 1024-byte aligned carve-up (the swizzle atoms need it)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
   uint32_t* sjobs = reinterpret_cast<uint32_t*>(qcs + QC_FLOATS);
   // CTA-pair mode: rank 0 (even block) dynamics / policy / Q1, rank 1 reward / Q2 / value.  Macros, not locals: without PAIR they
   // must fold to exactly the expressions the single-CTA kernel always used (a local here costs the epilogues a register).
+  constexpr bool ALTS = !DRNN && (ALT || PAIR);          // job flags F_BUF0 / F_D3 / F_KLO / F_KHI / F_A_XS / F_TO_XS / F_PARK / F_EPI can occur
 #define TC_NJOBS ((PAIR && (blockIdx.x & 1u)) ? kp.njobs1 : kp.njobs)
 #define TC_JOFF ((PAIR && (blockIdx.x & 1u)) ? kp.j1off : 0)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sjobs + ((kp.njobs + (PAIR ? kp.njobs1 : 0) + 3) & ~3));
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     return t < (uint32_t)kp.num_tiles ? (int)t : -1;
   };
   int tiles_done = 0;
-  const long long t_start = kp.trace ? clock64() : 0;
+  const long long t_start = ktrace ? clock64() : 0;
 
   if (warp < 4) {
     // warps 0-3 form one warpgroup: producer, MMA issuer, two idle warps.  They hand most of their
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (mine == (uint32_t)pk) {
                 const int ti = i;
                 mbar_wait(&w_empty[stage], phase ^ 1, 1);
-                if (kp.debug & 1) mbar_arrive(&w_full[stage]);
+                if (TRACE && (kp.debug & 1)) mbar_arrive(&w_full[stage]);
                 else {
                   mbar_arrive_expect_tx(&w_full[stage], TILE_BYTES);
                   bulk_g2s(wring + stage * TILE_BYTES, src + (size_t)ti * TILE_BYTES, TILE_BYTES, &w_full[stage]);
@@ -343,11 +348,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         for (int j = 0; j < TC_NJOBS; ++j) {
           const uint32_t job = kp.jw[TC_JOFF + j];
           const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, flags = job >> 13;
-          const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && lane == 0;
-          if (tr) kp.trace[(0 * MAX_JOBS + j) * 2] = clock64();
+          const bool tr = ktrace && blockIdx.x == 0 && it == 2 && lane == 0;
+          if (tr) ktrace[(0 * MAX_JOBS + j) * 2] = clock64();
           if (flags & F_WAIT_ZA) { mbar_wait(za_full, za_phase, 6); za_phase ^= 1; }
           if (DRNN && (flags & F_WAIT_HS)) { mbar_wait(hs_full, hs_phase, 10); hs_phase ^= 1; tcgen05_fence_after(); }
-          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
+          if (ALTS && (flags & F_BUF0)) nbuf = 0;
           if (type == J_L1) {
             const int b = nbuf; nbuf ^= 1;
             acc_acquire(b);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             umma_commit_p(&acc_full[b], lead);
             // every MMA issued so far -- the parked layer 3 and all layer-1 jobs that read this step's [z,a] -- complete
-            if (!DRNN && (flags & F_D3)) umma_commit_p(d3_full, lead);
+            if (ALTS && (flags & F_D3)) umma_commit_p(d3_full, lead);
           } else if (DRNN && type == J_G) {
             // gate pre-activation: [z,a] W_ih[g]^T + h W_hh[g]^T accumulated into one buffer (no biases, rnns.py:13-14)
             const int b = nbuf; nbuf ^= 1;
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
             for (int i = 0; i < m.gi_pad; ++i) { tile_acquire(); tile_release(); }     // padding tiles keep the ring aligned
             umma_commit_p(x_full, lead);                                            // covers J_GH's MMAs too
-          } else if (!DRNN && type == J_L2 && (flags & (F_KLO | F_KHI))) {
+          } else if (ALTS && type == J_L2 && (flags & (F_KLO | F_KHI))) {
             // half of a layer-2 chunk (see F_KLO): 4 k-blocks = 4 tiles = one turn of the ring
             const bool hi = (flags & F_KHI) != 0;
             const int b = nbuf; nbuf ^= 1;                 // KLO c0, KLO c1, KHI c0, KHI c1: the ping-pong lands on the same buffers
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             acc_acquire(b);
             tcgen05_fence_after();
             const uint32_t d = tmem + TM_ACC + b * 128;
-            if (!DRNN && (flags & F_A_XS)) {
+            if (ALTS && (flags & F_A_XS)) {
               // reward chain of the overlapped schedule: A = its hidden activation in XS (both operands in shared memory)
 #pragma unroll
               for (int kb = 0; kb < 8; ++kb) {
@@ -488,10 +493,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
             }
             umma_commit_p(&acc_full[b], lead);
-          } else if (!DRNN && type == J_L3 && (flags & F_EPI)) {
+          } else if (ALTS && type == J_L3 && (flags & F_EPI)) {
             // epilogue-only job
           } else if (type == J_L3) {
-            const bool park = !DRNN && (flags & F_PARK);
+            const bool park = ALTS && (flags & F_PARK);
             int b = 0;
             if (!park) { b = nbuf; nbuf ^= 1; acc_acquire(b); }
             tcgen05_fence_after();
@@ -588,7 +593,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               umma_commit_p(&q_full[c], lead);
             }
           }
-          if (tr) kp.trace[(0 * MAX_JOBS + j) * 2 + 1] = clock64();
+          if (tr) ktrace[(0 * MAX_JOBS + j) * 2 + 1] = clock64();
           __syncwarp();
         }
     }
@@ -608,20 +613,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     uint32_t fcnt = 0, nbuf = 0, q_phase = 0;
     uint32_t d3_phase = 0;                          // overlapped schedule: phase of d3_full (group 0 only)
     uint32_t x_phase = 0, ga = 0;                  // DRNN: phase of x_full / r_ready / u_ready, group that owns the reset gate of this step
-    float* x_sum = xch + (0 * 2 + (grp ^ 1)) * 128;      // the OTHER group's slots (read side)
-    float* x_ssq = xch + (1 * 2 + (grp ^ 1)) * 128;
-    float* x_dot = xch + (2 * 2 + (grp ^ 1)) * 128;
-    float* m_sum = xch + (0 * 2 + grp) * 128;            // my slots (write side)
-    float* m_ssq = xch + (1 * 2 + grp) * 128;
-    float* m_dot = xch + (2 * 2 + grp) * 128;
+    // exchange slots of my row as 32-bit shared-space addresses (explicit ld.shared / st.shared: a generic float* costs a
+    // register pair each and takes the slower generic path): x_* the OTHER group's slot (read side), m_* mine (write side)
+    const uint32_t xch_a = smem_u32(xch) + (uint32_t)row * 4u;
+    const uint32_t x_sum = xch_a + (0 * 2 + (grp ^ 1)) * 512, x_ssq = xch_a + (1 * 2 + (grp ^ 1)) * 512, x_dot = xch_a + (2 * 2 + (grp ^ 1)) * 512;
+    const uint32_t m_sum = xch_a + (0 * 2 + grp) * 512, m_ssq = xch_a + (1 * 2 + grp) * 512, m_dot = xch_a + (2 * 2 + grp) * 512;
 
     auto acc_wait = [&]() {
       mbar_wait(&acc_full[grp], fcnt & 1, 7);
       ++fcnt;
     };
     // early release: the accumulator goes back to the MMA warp as soon as it sits in registers (tmem_drain_aux)
-    const int go_math = (kp.debug & 4) ? 0 : kp.one;     // experiment (bit 2): skip the activation math of the MLP layers (power probe, wrong results)
-    const bool late_release = (kp.debug & 2) != 0;      // experiment: release after the activation math, as before
+    const int go_math = (TRACE && (kp.debug & 4)) ? 0 : kp.one;     // experiment (bit 2): skip the activation math of the MLP layers (power probe, wrong results)
+    const bool late_release = TRACE && (kp.debug & 2) != 0;      // experiment: release after the activation math, as before
     auto acc_release = [&]() {
       if (!late_release) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
     };
@@ -637,10 +641,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
     for (int it = 0; (tile_idx = next_tile()) >= 0; ++it, ++tiles_done) {
       const long long g = (long long)tile_idx * TILE_ROWS + row;
       const bool valid = g < total;
-      const long long pb = valid ? g / p.T : 0;
-      const long long pj = valid ? g - pb * p.T : 0;
-      const float* act_row = p.actions ? p.actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
-      float* pi_row = p.pi_actions ? p.pi_actions + ((size_t)(pb * p.Tcap + pj) * p.H) * A : nullptr;
+      const int pb = valid ? (int)(g / p.T) : 0;               // B * T < 2^31 (checked at launch)
+      const int pj = valid ? (int)(g - (long long)pb * p.T) : 0;
+      const float* act_row = p.actions ? p.actions + (((size_t)pb * p.Tcap + pj) * p.H) * A : nullptr;
+      float* pi_row = p.pi_actions ? p.pi_actions + (((size_t)pb * p.Tcap + pj) * p.H) * A : nullptr;
       float G = 0.0f, rlast = 0.0f, dot = 0.0f, q1v = 0.0f;
       float pd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // DRNN policy rollout: partial outputs of the last policy Linear
 
@@ -707,8 +711,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         const uint32_t job = sjobs[j];
         const int type = job & 7, chain = (job >> 3) & 7, chunk = (job >> 6) & 3, t = (job >> 8) & 31, flags = job >> 13;
         const TcChain& ch = m.chain[chain];
-        const bool tr = kp.trace && blockIdx.x == 0 && it == 2 && threadIdx.x % 128 == 0;
-        unsigned long long* trp = kp.trace + ((1 + grp) * MAX_JOBS + j) * 2;
+        const bool tr = ktrace && blockIdx.x == 0 && it == 2 && threadIdx.x % 128 == 0;
+        unsigned long long* trp = ktrace + ((1 + grp) * MAX_JOBS + j) * 2;
 
         if (DRNN && type >= J_G) {
           // ---- NormGRUCell (models/rnns.py:19-29): thread = trajectory, LayerNorm over the 128 gate values in-thread ----
@@ -779,10 +783,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               xv[sg * 32 + i] = y; sum += y; ssq = fmaf(y, y, ssq);
             }
           }
-          m_sum[row] = sum; m_ssq[row] = ssq;
+          sts1(m_sum, sum); sts1(m_ssq, ssq);
           epi_bar_sync();
-          const float s0 = grp == 0 ? sum : x_sum[row], s1 = grp == 0 ? x_sum[row] : sum;        // same order in both groups
-          const float q0 = grp == 0 ? ssq : x_ssq[row], q1 = grp == 0 ? x_ssq[row] : ssq;
+          const float os = lds1(x_sum), oq = lds1(x_ssq);
+          const float s0 = grp == 0 ? sum : os, s1 = grp == 0 ? os : sum;        // same order in both groups
+          const float q0 = grp == 0 ? ssq : oq, q1 = grp == 0 ? oq : ssq;
           const float mu = (s0 + s1) * (1.0f / 128.0f);
           const float rstd = 1.0f / sqrtf(fmaxf((q0 + q1) * (1.0f / 128.0f) - mu * mu, 0.0f) + 1e-3f);
           mbar_wait(u_ready, gph, 14);
@@ -821,18 +826,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           continue;
         }
         if (type <= J_L3) {
-          if (!DRNN && type == J_L3 && (flags & F_PARK)) continue;             // MMAs only (overlapped schedule)
-          if (!DRNN && type == J_L2 && (flags & F_KLO)) continue;              // first half of a split layer-2 chunk: MMAs only
-          const bool epi_only = !DRNN && type == J_L3 && (flags & F_EPI);      // epilogue of the parked layer 3: group 0
+          if (ALTS && type == J_L3 && (flags & F_PARK)) continue;             // MMAs only (overlapped schedule)
+          if (ALTS && type == J_L2 && (flags & F_KLO)) continue;              // first half of a split layer-2 chunk: MMAs only
+          const bool epi_only = ALTS && type == J_L3 && (flags & F_EPI);      // epilogue of the parked layer 3: group 0
           if (epi_only && grp != 0) continue;
-          if (!DRNN && (flags & F_BUF0)) nbuf = 0;
+          if (ALTS && (flags & F_BUF0)) nbuf = 0;
           int b = grp;
           if (!epi_only) { b = nbuf; nbuf ^= 1; }
           const bool mine = b == grp;
           if (tr && (mine || (type == J_L2 && chain == CH_REW && chunk == 3))) trp[0] = clock64();
           if (type == J_L1) {
             if (!mine) continue;
-            if (!DRNN && (flags & F_TO_XS)) {
+            if (ALTS && (flags & F_TO_XS)) {
               // reward chain of the overlapped schedule: h1 chunk = ELU(acc + b1) -> bf16 -> XS (the layer-3 MMAs that read
               // XS were issued before this job's MMAs, so the accumulator barrier covers them)
               const float* bias = ch.b1 + chunk * 128;
@@ -998,10 +1003,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             } else if (!to_xs && chunk == 3) {
               // both groups hold a partial reward dot product of this row: combine in group 0.  (A one-way hand-over -- group 1
               // publishes its partial sum and moves on -- was measured: no gain, group 0's three chunks in a row stay critical.)
-              m_dot[row] = dot;
+              sts1(m_dot, dot);
               epi_bar_sync();
               if (grp == 0) {
-                const float r = (dot + x_dot[row]) + __ldg(ch.b3);
+                const float r = (dot + lds1(x_dot)) + __ldg(ch.b3);
                 G = __fadd_rn(G, __fmul_rn(p.disc[t], r));   // G += discount * reward (tdmpc.py:89): mul, then add, as torch does
                 rlast = r;
               }
@@ -1182,9 +1187,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             });
           }
           q_phase ^= 1;
-          m_sum[row] = sum; m_ssq[row] = ssq;
+          sts1(m_sum, sum); sts1(m_ssq, ssq);
           epi_bar_sync();
-          sum += x_sum[row]; ssq += x_ssq[row];
+          sum += lds1(x_sum); ssq += lds1(x_ssq);
           const float mu = sum * (1.0f / 512.0f);
           const float var = fmaxf(ssq * (1.0f / 512.0f) - mu * mu, 0.0f);      // biased variance, as nn.LayerNorm
           const float rstd = 1.0f / sqrtf(var + 1e-5f);
@@ -1219,10 +1224,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             if (first) { fence_proxy_async_smem(); mbar_arrive(&xs_full[c]); }
           }
           if (!first) {
-            m_dot[row] = qdot;
+            sts1(m_dot, qdot);
             epi_bar_sync();
             if (grp == 0) {
-              const float qv = (qdot + x_dot[row]) + __ldg(ch.b3);
+              const float qv = (qdot + lds1(x_dot)) + __ldg(ch.b3);
               if (PAIR) {
                 if (chain == CH_Q1) { mb_q1[row] = qv; mb_publish(TDMPC_MAX_H + 2); }           // rank 0 -> rank 1
                 else { mb_wait(TDMPC_MAX_H + 2); q1v = __ldcg(mb_q1 + row); mb_consume(TDMPC_MAX_H + 2, -1); }
@@ -1231,8 +1236,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               else if (valid) {
                 // G += discount * min(Q1, Q2); nan_to_num_   (tdmpc.py:91-92)
                 const float val = __fadd_rn(G, __fmul_rn(p.disc[p.H], min_nanprop(q1v, qv)));
-                p.values[pb * p.Tcap + pj] = nan_to_num0(val);
-                if (p.last_reward) p.last_reward[pb * p.Tcap + pj] = rlast;
+                p.values[(size_t)pb * p.Tcap + pj] = nan_to_num0(val);
+                if (p.last_reward) p.last_reward[(size_t)pb * p.Tcap + pj] = rlast;
               }
             }
           }
@@ -1241,21 +1246,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
           if (tr) trp[1] = clock64();
         }
       }
-      if (kp.trace && blockIdx.x == 0 && threadIdx.x == 128 && it < 128) {
+      if (ktrace && blockIdx.x == 0 && threadIdx.x == 128 && it < 128) {
         unsigned long long ns;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-        kp.trace[3 * MAX_JOBS * 2 + it] = clock64();
-        kp.trace[3 * MAX_JOBS * 2 + 128 + it] = ns;
+        ktrace[3 * MAX_JOBS * 2 + it] = clock64();
+        ktrace[3 * MAX_JOBS * 2 + 128 + it] = ns;
       }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (kp.trace && threadIdx.x == 128 && blockIdx.x < 256) {
+  if (ktrace && threadIdx.x == 128 && blockIdx.x < 256) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    unsigned long long* bs = kp.trace + 3 * MAX_JOBS * 2 + 256 + 4 * blockIdx.x;
+    unsigned long long* bs = ktrace + 3 * MAX_JOBS * 2 + 256 + 4 * blockIdx.x;
     bs[0] = (unsigned long long)t_start; bs[1] = (unsigned long long)clock64(); bs[2] = (unsigned long long)tiles_done; bs[3] = smid;
   }
   if (warp == 1) tmem_dealloc<512>(tmem);
@@ -1619,13 +1624,18 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
   // The attribute is per function AND per device, not per handle: always raise it to the fixed maximum, so handles with
   // different shapes (or on different GPUs of one process) cannot shrink each other's limit.
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  m.pair_mode = (!drnn && !getenv("TDMPC_TC_NOPAIR")) ? 1 : 0;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  m.alt_sched = (!drnn && (getenv("TDMPC_TC_OVERLAP") || getenv("TDMPC_TC_SPLIT"))) ? 1 : 0;
+  m.pair_mode = (!drnn && !m.alt_sched && !getenv("TDMPC_TC_NOPAIR")) ? 1 : 0;
   m.pair_rows = out->pair_rows; m.pair_flags = out->pair_flags;          // kept across re-packs of the same handle
   if (m.pair_mode && !m.pair_rows) {
     const size_t rows = (size_t)PAIR_MAX_TILES * (TDMPC_MAX_H + 1) * 128 * m.K1p + (size_t)PAIR_MAX_TILES * 128;
@@ -1661,6 +1671,7 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   kp.njobs = m.njobs[p.mode][p.H];
   kp.stages = m.stages;
   const long long total = (long long)p.B * p.T;
+  if (total >= (1ll << 31)) return -1;
   kp.num_tiles = (int)((total + TILE_ROWS - 1) / TILE_ROWS);
   kp.trace = g_tc_trace;
   kp.one = 1;
@@ -1681,15 +1692,23 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   const int grid = kp.pair ? 2 * kp.num_tiles : (kp.num_tiles < num_sms ? kp.num_tiles : num_sms);
   if (kp.njobs <= 0 || kp.njobs + kp.njobs1 > MAX_JOBS || !m.jobs_host) return -1;
   memcpy(kp.jw, m.jobs_host + m.jobs_off[kp.pair ? 2 : p.mode][p.H], sizeof(uint32_t) * (kp.njobs + kp.njobs1));
-  if (m.drnn) {
-    if (m.exact_act) rollout_tc_kernel<true, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<true, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  if (kp.trace) {
+    // the stamping build: default precision mode, plain schedule only (tools/trace_rollout.py)
+    if (kp.pair || m.alt_sched || m.exact_act) return -1;
+    if (m.drnn) rollout_tc_kernel<true, false, false, false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<false, false, false, false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+  } else if (m.drnn) {
+    if (m.exact_act) rollout_tc_kernel<true, true, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<true, false, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   } else {
     if (kp.pair) {
-      if (m.exact_act) rollout_tc_kernel<false, true, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-      else rollout_tc_kernel<false, false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    } else if (m.exact_act) rollout_tc_kernel<false, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+      if (m.exact_act) rollout_tc_kernel<false, true, true, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+      else rollout_tc_kernel<false, false, true, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    } else if (m.alt_sched) {
+      if (m.exact_act) rollout_tc_kernel<false, true, false, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+      else rollout_tc_kernel<false, false, false, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    } else if (m.exact_act) rollout_tc_kernel<false, true, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    else rollout_tc_kernel<false, false, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
   }
   return 1;
 }

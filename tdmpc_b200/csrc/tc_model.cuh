@@ -83,6 +83,7 @@ struct TcModel {
   float* pair_rows;            // [PAIR_MAX_TILES][TDMPC_MAX_H + 1][128][K1p] fp32 rows [z_t | a_t] published by rank 0; then [PAIR_MAX_TILES][128] Q1
   unsigned int* pair_flags;    // [PAIR_MAX_TILES][32]: slot t published (1) / consumed (0); [TDMPC_MAX_H + 1]: terminal action, [TDMPC_MAX_H + 2]: Q1
   int pair_mode;               // 0 off (TDMPC_TC_NOPAIR), 1 on
+  int alt_sched;               // an alternative value-mode schedule is selected (TDMPC_TC_OVERLAP / TDMPC_TC_SPLIT): ALT instantiation
   // DRNN (TDMPC_DYN_DRNN): chain CH_DYN is the prior MLP (layer 1: K = hidden_dim, layer 3 slot = its second Linear),
   // chain CH_REW's layer 1 reads the hidden state; gate weights live in their own tiles.
   int drnn;
