@@ -1095,10 +1095,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               if (next_act) {
 #pragma unroll
                 for (int a = 0; a < 8; ++a) if (a < A) { za_store1(za, row, L + a, an[a], ckb); if (pub) mrow[L + a] = an[a]; }
-                for (int a = 8; a < A; ++a) {
-                  const float av = valid ? __ldg(act_row + (size_t)(t + 1) * A + a) : 0.0f;
-                  za_store1(za, row, L + a, av, ckb);
-                  if (pub) mrow[L + a] = av;
+                // action dimensions 8 .. A-1 (dog-run: 38): eight loads in flight at a time -- one load per iteration put ~30
+                // dependent global-memory round trips into every step's layer-3 epilogue (-6 % on the launch at dog-run dims).
+                // (Fetching them before the accumulator wait like an[] was measured too: 32 more live registers spill, +6 %.)
+#pragma unroll 1
+                for (int a0 = 8; a0 < A; a0 += 8) {
+                  float av[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) av[i] = (valid && a0 + i < A) ? __ldg(act_row + (size_t)(t + 1) * A + a0 + i) : 0.0f;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (a0 + i < A) { za_store1(za, row, L + a0 + i, av[i], ckb); if (pub) mrow[L + a0 + i] = av[i]; }
                 }
               }
             } else {
