@@ -61,11 +61,13 @@ typedef enum {
 /* Static model description: algorithm/tdmpc.py:12-23 (TOLD.__init__) + cfg fields it reads. */
 typedef struct {
   int32_t obs_dim;        /* cfg.obs_shape[0]                                  */
-  int32_t action_dim;     /* cfg.action_dim                                    */
-  int32_t latent_dim;     /* cfg.latent_dim                                    */
-  int32_t mlp_dim;        /* cfg.mlp_dim  (bf16 path requires 512)             */
+  int32_t action_dim;     /* cfg.action_dim     (<= 64; bf16 paths: latent_dim + action_dim <= 192; GRU policy rollout on tensor cores: <= 8) */
+  int32_t latent_dim;     /* cfg.latent_dim     (bf16 paths: <= 128)           */
+  int32_t mlp_dim;        /* cfg.mlp_dim        (bf16 paths and tdmpc_update_forward: 512; fp32 paths and tdmpc_update: any) */
   int32_t enc_dim;        /* cfg.enc_dim                                       */
-  int32_t hidden_dim;     /* cfg.hidden_dim (DRNN only)                        */
+  int32_t hidden_dim;     /* cfg.hidden_dim     (DRNN only; bf16 path: 128).  Shapes outside these limits make tdmpc_create /
+                           * tdmpc_set_weights return TDMPC_ERR_INVALID with the violated limit in tdmpc_last_error -- there is no
+                           * silent fallback to another path. */
   int32_t enc_layernorm;  /* 1: helper.dmlab_enc_norm state branch (helper.py:161-165) */
   int32_t dynamics;       /* tdmpc_dynamics                                    */
   int32_t precision;      /* tdmpc_precision                                   */

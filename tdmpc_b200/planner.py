@@ -547,10 +547,12 @@ def agent_kind(agent):
     return "tdmpc"
 
 
-def accelerate(agent, precision="bf16", kind=None):
+def accelerate(agent, precision="bf16", kind=None, update=False):
     """Give an existing reference-style agent (attributes cfg, model, std, device) the CUDA `plan`.
     The agent's nn.Module keeps owning the parameters; they are re-packed whenever they change.
-    `kind` overrides the class detection of agent_kind()."""
+    `kind` overrides the class detection of agent_kind().  `update=True` (plain TDMPC agents only) also rebinds
+    `update(replay_buffer, step)` to the device training step (tdmpc_update): the agent's parameters are stepped in place with
+    this library's own Adam state -- agent.optim / agent.pi_optim are no longer used and their state is not carried over."""
     cfg = agent.cfg
     kind = agent_kind(agent) if kind is None else kind
     if kind not in _PLAN_KINDS:
@@ -566,6 +568,11 @@ def accelerate(agent, precision="bf16", kind=None):
                              enc_layernorm=enc_ln, precision=precision, device=agent.device,
                              dynamics="drnn" if drnn else "mlp", hidden_dim=cfg.hidden_dim if drnn else 0)
     agent.plan = types.MethodType(_PLAN_KINDS[kind], agent)
+    if update:
+        if kind != "tdmpc" or enc_ln:
+            raise NotImplementedError("accelerate(update=True): the device training step covers the plain TDMPC agent (MLP TOLD, no LayerNorm encoder)")
+        for name in ("_train_state", "update_batch", "update"):
+            setattr(agent, name, types.MethodType(getattr(TDMPC, name), agent))
     return agent
 
 
@@ -671,7 +678,7 @@ class TDMPC:
         st = self._train_state(B, H)
         pri = torch.empty(B, device=dev)
         a = _lib.TrainArgs()
-        a.online, a.target = self._train_weights(self.model, dev), self._train_weights(self.model_target, dev)
+        a.online, a.target = TDMPC._train_weights(self.model, dev), TDMPC._train_weights(self.model_target, dev)
         a.batch, a.horizon, a.discount, a.rho, a.min_std = B, H, float(cfg.discount), float(cfg.rho), float(cfg.min_std)
         a.consistency_coef, a.reward_coef, a.value_coef = float(cfg.consistency_coef), float(cfg.reward_coef), float(cfg.value_coef)
         a.lr, a.beta1, a.beta2, a.adam_eps = float(cfg.lr), 0.9, 0.999, 1e-8

@@ -132,3 +132,45 @@ def test_update_dropin_surface_and_replan():
     ag1._planner.call = ag2._planner.call = 3
     m1, m2 = ag1.update(buf, 1), ag2.update(buf, 1)
     assert m1 == m2
+
+
+def test_accelerate_update_on_reference_style_agent():
+    """accelerate(agent, update=True) on an attribute-compatible stand-in of the reference TDMPC agent (it has its own model /
+    model_target modules): update() runs on the device, steps the agent's own parameters in place, and equals the drop-in class
+    started from the same state."""
+    from copy import deepcopy
+    from tdmpc_b200 import accelerate
+    from tests.test_dropin_cpu import _agent as standin
+    ag = standin("tdmpc", batch_size=32)
+    cfg = ag.cfg
+    sd, sd_t = synth.make_told_weights(cfg, 7), synth.make_told_weights(cfg, 57)
+    ag.model.load_state_dict(sd)
+    ag.model = ag.model.cuda().eval()
+    ag.model_target = deepcopy(ag.model)
+    ag.model_target.load_state_dict(sd_t)
+    ag.device = torch.device("cuda", torch.cuda.current_device())
+    accelerate(ag, precision="fp32", update=True)
+    b = synth.make_train_batch(cfg, 11, 32)
+
+    class Buf:
+        def sample(self):
+            return b["obs"], b["next_obses"], b["action"], b["reward"], b["idxs"], b["weights"]
+
+        def update_priorities(self, idxs, pr):
+            self.pr = pr
+
+    buf = Buf()
+    ag._planner.seed, ag._planner.call = 5, 20
+    m = ag.update(buf, 4)
+    ref = _agent(synth.make_cfg("tiny", batch_size=32, device="cuda", precision="fp32"), sd, sd_t)
+    ref._planner.seed, ref._planner.call = 5, 20
+    m_ref = ref.update(buf, 4)
+    assert m == m_ref and set(m) == {"consistency_loss", "reward_loss", "value_loss", "pi_loss", "total_loss", "weighted_loss", "grad_norm"}
+    for (k, p), (_, q) in zip(ag.model.state_dict().items(), ref.model.state_dict().items()):
+        assert torch.equal(p, q), k
+    moved = max((ag.model.state_dict()[k].cpu() - sd[k]).abs().max().item() for k in sd)
+    assert 0.5 * cfg.lr <= moved <= 1.001 * cfg.lr
+    a, _ = ag.plan(synth.make_obs(cfg, 2), eval_mode=True, step=10 ** 6, t0=True)      # the planner re-packs the moved parameters
+    assert torch.isfinite(a).all()
+    with pytest.raises(NotImplementedError):
+        accelerate(standin("icem"), precision="fp32", update=True)
