@@ -23,7 +23,10 @@ constexpr int GB = 64, GK = 16;
 
 template <bool TA, bool TB, int BM>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                    float* __restrict__ C, int ldc, float beta, const float* __restrict__ bias, int elu) {
+                                                    float* __restrict__ C, int ldc, float beta, const float* __restrict__ bias, int elu, int kslice) {
+  // split-k (kslice > 0): block z multiplies the k range [z * kslice, (z + 1) * kslice) into its own partial C + z * M * ldc
+  const int kbeg = kslice > 0 ? blockIdx.z * kslice : 0;
+  if (kslice > 0) { K = min(K, kbeg + kslice); C += (size_t)blockIdx.z * M * ldc; }
   constexpr int RM = BM / 16;                                // rows per thread: 4 (64-row tile) or 8 (128-row tile)
   __shared__ __align__(16) float As[GK][BM + 4];
   __shared__ __align__(16) float Bs[GK][GB + 4];
@@ -54,8 +57,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
       rb[r] = (gn < N && gkb < K) ? (TB ? __ldg(B + (size_t)gn * ldb + gkb) : __ldg(B + (size_t)gkb * ldb + gn)) : 0.0f;
     }
   };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < K; k0 += GK) {
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
       const int idx = tid + r * 256;
@@ -102,8 +105,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
   }
 }
 
+constexpr size_t SPLITK_FLOATS = (size_t)4 << 20;      // 16 MB: up to 16 partials of a 512 x 512 weight gradient
+
 struct Ctx {
   cudaStream_t st;
+  float* splitk = nullptr;        // partials of the split-k weight-gradient GEMMs
+  size_t splitk_floats = 0;
   int launches = 0;
   bool ok = true;
   void check() { if (cudaGetLastError() != cudaSuccess) ok = false; ++launches; }
@@ -111,16 +118,42 @@ struct Ctx {
 
 template <int BM>
 void gemm_bm(Ctx& c, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float beta,
-             const float* bias, bool elu) {
-  dim3 grid((N + GB - 1) / GB, (M + BM - 1) / BM);
-  if (ta && tb) sgemm_kernel<true, true, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0);
-  else if (ta) sgemm_kernel<true, false, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0);
-  else if (tb) sgemm_kernel<false, true, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0);
-  else sgemm_kernel<false, false, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0);
+             const float* bias, bool elu, int kslice = 0, int nz = 1) {
+  dim3 grid((N + GB - 1) / GB, (M + BM - 1) / BM, nz);
+  if (ta && tb) sgemm_kernel<true, true, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0, kslice);
+  else if (ta) sgemm_kernel<true, false, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0, kslice);
+  else if (tb) sgemm_kernel<false, true, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0, kslice);
+  else sgemm_kernel<false, false, BM><<<grid, 256, 0, c.st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0, kslice);
   c.check();
+}
+// C[i] = beta * C[i] + sum_z P[z][i]  (fixed order: the split-k result does not depend on scheduling)
+__global__ void splitk_reduce_kernel(const float* __restrict__ P, int nz, size_t n, float* __restrict__ C, float beta) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int z = 0; z < nz; ++z) s += P[(size_t)z * n + i];
+  C[i] = beta != 0.0f ? beta * C[i] + s : s;
 }
 void gemm(Ctx& c, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float beta = 0.0f,
           const float* bias = nullptr, bool elu = false) {
+  // Weight gradients (dW = dY^T X: small M x N, the batch as a long k): a few tiles would leave most SMs idle for 200+ us, so the
+  // k range is cut into slices that fill the GPU, each slice writes a partial, and a reduction adds them in a fixed order.
+  const long long tiles64 = (long long)((M + 63) / 64) * ((N + GB - 1) / GB);
+  if (ta && !tb && !bias && !elu && c.splitk && K >= 512 && tiles64 < 120 && ldc == N && (size_t)M * N <= c.splitk_floats / 2) {
+    int nz = (int)((148 + tiles64 - 1) / tiles64);
+    const int maxz = (int)(c.splitk_floats / ((size_t)M * N));
+    if (nz > maxz) nz = maxz;
+    if (nz > 32) nz = 32;
+    int kslice = ((K + nz - 1) / nz + GK - 1) / GK * GK;
+    nz = (K + kslice - 1) / kslice;
+    if (nz >= 2) {
+      gemm_bm<64>(c, ta, tb, M, N, K, A, lda, B, ldb, c.splitk, N, 0.0f, nullptr, false, kslice, nz);
+      const size_t n = (size_t)M * N;
+      splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(c.splitk, nz, n, C, beta);
+      c.check();
+      return;
+    }
+  }
   // 128-row tiles (8 x 4 outputs per thread) once they still fill the 148 SMs, 64-row tiles otherwise
   const long long tiles128 = (long long)((M + 127) / 128) * ((N + GB - 1) / GB);
   if (tiles128 >= 296) gemm_bm<128>(c, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu);
@@ -148,7 +181,35 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
     out[n] = accumulate ? out[n] + t : t;
   }
 }
+// row slice blockIdx.y of the column sums -> P[blockIdx.y][n]
+__global__ void __launch_bounds__(256) colsum_split_kernel(const float* __restrict__ X, int rows, int rs, int N, int ld, float* __restrict__ P) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rs, r1 = min(rows, r0 + rs);
+  float s = 0.0f;
+  if (n < N)
+    for (int r = r0 + ty; r < r1; r += 8) s += X[(size_t)r * ld + n];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    P[(size_t)blockIdx.y * N + n] = t;
+  }
+}
 void colsum(Ctx& c, const float* X, int rows, int N, int ld, float* out, bool accumulate) {
+  // many rows, few columns: row slices into partials, then the fixed-order reduction (as the split-k GEMM)
+  const int nz = rows >= 1024 && c.splitk ? 16 : 1;
+  if (nz > 1 && (size_t)nz * N <= c.splitk_floats) {
+    const int rs = (rows + nz - 1) / nz;
+    colsum_split_kernel<<<dim3((N + 31) / 32, nz), 256, 0, c.st>>>(X, rows, rs, N, ld, c.splitk);
+    c.check();
+    splitk_reduce_kernel<<<(N + 255) / 256, 256, 0, c.st>>>(c.splitk, nz, (size_t)N, out, accumulate ? 1.0f : 0.0f);
+    c.check();
+    return;
+  }
   colsum_kernel<<<(N + 31) / 32, 256, 0, c.st>>>(X, rows, N, ld, out, accumulate ? 1 : 0);
   c.check();
 }
@@ -508,6 +569,7 @@ long long train_workspace_bytes(const tdmpc_model_cfg& c, int B, int H) {
   f += R1 * W + 2 * R1 * M + R1 * M;   // dx, dh1, dh2, dln
   f += 2 * (size_t)B * L + (size_t)B * W + (size_t)B * E;   // dz carry, dzn, dxd, de1
   f += 5 * (size_t)B + 3 * R1 + R1 * A + 64;                 // per_sample, pi-loss scratch (dq1, dq2, qmin), dpre, control words
+  f += SPLITK_FLOATS;                                         // partials of the split-k weight-gradient GEMMs / column sums
   return (long long)(f * sizeof(float) + 256);
 }
 
@@ -542,6 +604,8 @@ int launch_train_step(const tdmpc_model_cfg& cfg, const tdmpc_train_args& a, cud
   float* per_sample = take(5 * (size_t)B);
   float* pq1 = take(R1); float* pq2 = take(R1); float* qmin = take(R1); float* dpre = take((size_t)R1 * A);
   ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~(uintptr_t)15);
+  float* skp = take(SPLITK_FLOATS);
+  c.splitk = skp; c.splitk_floats = SPLITK_FLOATS;
   float* ctl = take(64);                               // [0..3] doubles: sum-of-squares accumulators; [8] clip coef; [16..] rho powers
   if ((char*)ws - (char*)a.workspace > a.workspace_bytes) return -1;
   double* acc = reinterpret_cast<double*>(ctl);
