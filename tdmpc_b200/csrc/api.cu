@@ -108,6 +108,7 @@ extern "C" int tdmpc_create(const tdmpc_model_cfg* cfg, tdmpc_handle** out) {
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
   cudaSetDevice(cfg->device);
+  if (select_configure() != 0) { g_create_err = "cudaFuncSetAttribute(select_kernel) failed"; delete h; return TDMPC_ERR_CUDA; }
   h->arena32_floats = arena32_size(*cfg);
   if (cudaMalloc(&h->arena32, h->arena32_floats * sizeof(float)) != cudaSuccess) { g_create_err = "cudaMalloc(arena32) failed"; delete h; return TDMPC_ERR_CUDA; }
   if (cfg->precision != TDMPC_PREC_FP32) {
@@ -368,7 +369,7 @@ extern "C" int tdmpc_select_update(tdmpc_handle* h, const float* values, const f
   p.mean = mean; p.std = std; p.temperature = temperature; p.momentum = (float)momentum;
   p.one_minus_momentum = (float)(1.0 - momentum); p.std_floor = std_floor; p.std_max = std_max;
   p.elite_idx = elite_idx; p.score = score;
-  launch_select(p, (cudaStream_t)stream);
+  launch_select(p, batch < 2 * h->num_sms, (cudaStream_t)stream);
   return check_launch(h, "select");
 }
 
@@ -572,7 +573,7 @@ extern "C" int tdmpc_plan(tdmpc_handle* h, const tdmpc_plan_args* a, void* strea
     sp.u_pick = a->u_pick;
     sp.action = a->action; sp.metrics = a->metrics; sp.prev_mean = a->prev_mean;
     sp.tap_elite_idx = a->tap_elite_idx; sp.tap_mean = a->tap_mean; sp.tap_std = a->tap_std;
-    launch_select(sp, st);
+    launch_select(sp, B < 2 * h->num_sms, st);
     if (int r = check_launch(h, "select")) return r;
     if (!last && nparts > 1) if (int r = sample_split(sp.next, sp.elite_actions)) return r;
   }

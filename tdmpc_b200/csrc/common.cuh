@@ -181,6 +181,7 @@ struct SelectParams {
   float* mean; float* std;   // [B, H, A]
   float temperature, momentum, one_minus_momentum, std_floor, std_max;
   int do_sample, do_output;  // stage switches: sample the next iteration's rows / write the plan outputs
+  int stage;                 // set by launch_select: the K elite rows are gathered into shared memory first
   int* elite_idx;            // [B, K] scratch/out
   float* score;              // [B, K] scratch/out
   float* elite_actions;      // [B, K, H, A] out (iCEM carry-over) or nullptr
@@ -228,7 +229,8 @@ struct InitParams {
 void launch_encode(const ModelFp32& m, const float* obs, int B, int D, int E, int L, float* z, cudaStream_t st);
 void launch_rollout_fp32(const ModelFp32& m, const RolloutParams& p, cudaStream_t st);
 int  launch_rollout_tc(const struct TcModel& m, const RolloutParams& p, int num_sms, cudaStream_t st);
-void launch_select(const SelectParams& p, cudaStream_t st);
+void launch_select(const SelectParams& p, int small_batch, cudaStream_t st);   // small_batch: fewer CTAs than 2 per SM
+int select_configure();                                                       // once per device (tdmpc_create)
 void launch_init(const InitParams& p, cudaStream_t st);
 void launch_sample(const SampleParams& p, int nparts, cudaStream_t st);
 void launch_bump_counter(uint64_t* c, cudaStream_t st);     // *c += 1 (tdmpc_plan_args.call_dev)

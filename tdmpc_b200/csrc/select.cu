@@ -12,6 +12,7 @@
 namespace {
 
 constexpr int NT = 256;
+constexpr int NT_MAX = 1024;     // select_kernel on a small batch: one thread per sorted element
 constexpr int MAX_SORT = 4096;
 constexpr int MAX_K = 256;
 constexpr int MAX_HA = TDMPC_MAX_H * 64;
@@ -27,10 +28,11 @@ __device__ float block_sum(float v, float* red) {
   __syncthreads();
   if (lane == 0) red[warp] = v;
   __syncthreads();
-  float t = (threadIdx.x < NT / 32) ? red[threadIdx.x] : 0.0f;
+  // (the tree over 32 slots adds zeros first when the block has 8 warps: the same sums, bit for bit, as the 8-slot tree)
+  float t = (threadIdx.x < blockDim.x / 32) ? red[threadIdx.x] : 0.0f;
   if (warp == 0) {
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0) red[0] = t;
   }
   __syncthreads();
@@ -42,7 +44,7 @@ __device__ void bitonic_sort_desc(float* key, int* idx, int n) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       if (j >= 32) {
-        for (int i = threadIdx.x; i < n; i += NT) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
           const int l = i ^ j;
           if (l > i) {
             const float ka = key[i], kb = key[l];
@@ -55,7 +57,7 @@ __device__ void bitonic_sort_desc(float* key, int* idx, int n) {
         __syncthreads();
       } else {
         // all remaining strides of this k are < 32: finish them in registers with shuffles
-        for (int base = (threadIdx.x >> 5) * 32; base < n; base += NT) {
+        for (int base = (threadIdx.x >> 5) * 32; base < n; base += blockDim.x) {
           const int i = base + (threadIdx.x & 31);
           float ka = key[i]; int ia = idx[i];
           for (int jj = j; jj > 0; jj >>= 1) {
@@ -99,7 +101,7 @@ __device__ void sample_rows(int b, const SampleSpec& sp, int Tcap, int H, int A,
                             float* actions, const float* pi_actions, int P0, const float* reuse, int reuse_rows,
                             int part = 0, int nparts = 1) {
   const int HA = H * A;
-  const int first = part * NT + threadIdx.x, stride = nparts * NT;
+  const int first = part * blockDim.x + threadIdx.x, stride = nparts * blockDim.x;
   float* out = actions + (size_t)b * Tcap * HA;
   const uint64_t row0 = sp.cem_base + (uint64_t)b * sp.cem_bstride;
   if (!sp.cem.inj && sp.color_len == 0 && (A & 3) == 0 && (row0 & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(NT) sample_kernel(SampleParams p) {
   sample_rows(b, p.spec, p.Tcap, p.H, p.A, mean_s, std_s, p.actions, p.pi_actions, p.P0, p.reuse, p.reuse_rows, blockIdx.y, gridDim.y);
 }
 
-__global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
+__global__ void __launch_bounds__(NT_MAX) select_kernel(SelectParams p) {
   extern __shared__ __align__(16) unsigned char sraw[];
   const int b = blockIdx.x;
   const int T = p.T, K = p.K, H = p.H, A = p.A, HA = H * A;
@@ -158,9 +160,14 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
   float* mean_s = w + MAX_K;                            // [HA]
   float* std_s = mean_s + HA;                           // [HA]
   float* red = std_s + HA;                              // [32]
+  // p.stage: the K elite rows [K][HA] gathered into shared memory by all threads at once.  The weighted reductions below are
+  // one thread per (t, a) element walking the K elites in order (the order is part of the parity contract), so with few
+  // elements (cartpole: H*A = 5) a handful of threads would otherwise wait out 2 K dependent global-memory round trips --
+  // most of this kernel's time when a single environment is planned.  Same values, same order: bit-identical results.
+  float* erow = red + 32;
   __shared__ int pick_j;
 
-  for (int i = threadIdx.x; i < n2; i += NT) {
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     key[i] = i < T ? p.values[(size_t)b * p.Tcap + i] : -INFINITY;
     idx[i] = i < T ? i : 0x7fffffff;
   }
@@ -184,12 +191,22 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
   // weighted mean / std over the elites, clamp, momentum                (tdmpc.py:145-149)
   const float* act_b = p.actions + (size_t)b * p.Tcap * HA;
   const float one_m = p.one_minus_momentum;
-  for (int e = threadIdx.x; e < HA; e += NT) {
+  const bool staged = p.stage != 0;
+  if (staged) {
+    for (int e = threadIdx.x; e < K * HA; e += blockDim.x) {
+      const int k = e / HA;
+      erow[e] = act_b[(size_t)idx[k] * HA + (e - k * HA)];
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < HA; e += blockDim.x) {
     float m = 0.0f;
-    for (int k = 0; k < K; ++k) m += w[k] * act_b[(size_t)idx[k] * HA + e];
+    if (staged) for (int k = 0; k < K; ++k) m += w[k] * erow[k * HA + e];
+    else for (int k = 0; k < K; ++k) m += w[k] * act_b[(size_t)idx[k] * HA + e];
     m = m / s2;
     float var = 0.0f;
-    for (int k = 0; k < K; ++k) { const float d = act_b[(size_t)idx[k] * HA + e] - m; var += w[k] * (d * d); }
+    if (staged) for (int k = 0; k < K; ++k) { const float d = erow[k * HA + e] - m; var += w[k] * (d * d); }
+    else for (int k = 0; k < K; ++k) { const float d = act_b[(size_t)idx[k] * HA + e] - m; var += w[k] * (d * d); }
     float sd = sqrtf(var / s2);
     sd = fminf(fmaxf(sd, p.std_floor), p.std_max);
     const float old = p.mean[(size_t)b * HA + e];
@@ -201,9 +218,9 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
     if (p.tap_std) p.tap_std[((size_t)p.iter * p.B + b) * HA + e] = sd;
   }
   if (p.elite_actions)
-    for (int e = threadIdx.x; e < K * HA; e += NT) {
+    for (int e = threadIdx.x; e < K * HA; e += blockDim.x) {
       const int k = e / HA;
-      p.elite_actions[(size_t)b * K * HA + e] = act_b[(size_t)idx[k] * HA + (e - k * HA)];
+      p.elite_actions[(size_t)b * K * HA + e] = staged ? erow[e] : act_b[(size_t)idx[k] * HA + (e - k * HA)];
     }
   __syncthreads();
 
@@ -224,19 +241,19 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
     pick_j = j < K ? j : K - 1;
   }
   float rsum = 0.0f;
-  if (p.last_reward)
+  if (p.last_reward && threadIdx.x < NT)        // the first NT threads, NT apart: the same partial sums whatever the block size
     for (int i = threadIdx.x; i < T; i += NT) rsum += p.last_reward[(size_t)b * p.Tcap + i];
   rsum = block_sum(rsum, red);
   float ssd = 0.0f;
-  for (int a = threadIdx.x; a < A; a += NT) ssd += std_s[a];
+  for (int a = threadIdx.x; a < A; a += blockDim.x) ssd += std_s[a];
   ssd = block_sum(ssd, red);
   const int j = pick_j;
-  for (int a = threadIdx.x; a < A; a += NT) {
-    float v = act_b[(size_t)idx[j] * HA + a];                       // elite_actions[0, j]
+  for (int a = threadIdx.x; a < A; a += blockDim.x) {
+    float v = staged ? erow[j * HA + a] : act_b[(size_t)idx[j] * HA + a];   // elite_actions[0, j]
     if (!p.eval_mode) v += std_s[a] * noise_at(p.out_noise, (uint64_t)b * A + a);   // a += std * randn(A), no clamp
     p.action[(size_t)b * A + a] = v;
   }
-  for (int e = threadIdx.x; e < HA; e += NT) p.prev_mean[(size_t)b * HA + e] = mean_s[e];   // self._prev_mean = mean
+  for (int e = threadIdx.x; e < HA; e += blockDim.x) p.prev_mean[(size_t)b * HA + e] = mean_s[e];   // self._prev_mean = mean
   if (threadIdx.x == 0) {
     p.metrics[(size_t)b * 2 + 0] = rsum / (float)T;       // reward.mean() of the last step, last iteration
     p.metrics[(size_t)b * 2 + 1] = ssd / (float)A;        // std[0].mean()
@@ -321,11 +338,24 @@ void launch_bn_affine(const float* g, const float* b, const float* rm, const flo
   bn_affine_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, b, rm, rv, eps, n, scale, shift);
 }
 
-void launch_select(const SelectParams& p, cudaStream_t st) {
+// Elite rows are staged in shared memory (SelectParams::stage) when they are small (<= 16 KB: no occupancy cost) or when the
+// batch is too small to hide the gather latency behind other CTAs; the opt-in limit is raised once per device.
+constexpr size_t SELECT_SMEM_OPTIN = 160 * 1024;
+int select_configure() {
+  return cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELECT_SMEM_OPTIN) == cudaSuccess ? 0 : -1;
+}
+void launch_select(const SelectParams& p0, int small_batch, cudaStream_t st) {
+  SelectParams p = p0;
   int n2 = 64;
   while (n2 < p.T) n2 <<= 1;
-  const size_t smem = (size_t)n2 * 8 + sizeof(float) * (MAX_K + 2 * p.H * p.A + 32);
-  select_kernel<<<p.B, NT, smem, st>>>(p);
+  size_t smem = (size_t)n2 * 8 + sizeof(float) * (MAX_K + 2 * p.H * p.A + 32);
+  const size_t rows = sizeof(float) * (size_t)p.K * p.H * p.A;
+  p.stage = (rows <= 16384 || (small_batch && smem + rows <= SELECT_SMEM_OPTIN)) ? 1 : 0;
+  if (p.stage) smem += rows;
+  // One CTA per problem.  On a GPU-filling batch 256 threads (several CTAs per SM); on a small batch the kernel is a latency chain
+  // on a handful of SMs -- 1024 threads make every pass of the bitonic sort one round instead of four (B = 1: 28 -> 14 us).
+  // Every reduction is arranged so that both block sizes give bit-identical results.
+  select_kernel<<<p.B, small_batch ? NT_MAX : NT, smem, st>>>(p);
 }
 
 __global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }
