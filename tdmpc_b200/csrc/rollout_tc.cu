@@ -150,7 +150,10 @@ __device__ __forceinline__ void za_store8(uint8_t* za, int row, int k0, const fl
 // ALT: the alternative value-mode schedules behind TDMPC_TC_OVERLAP / TDMPC_TC_SPLIT (parked layer 3, reward activation in XS, split-k
 // layer 2) -- their branches too are compiled into their own instantiation only (ALTS below), not into the kernel the bench times.
 // TRACE: the clock64 stamps of tools/trace_rollout.py (a per-job 64-bit stamp pointer lives across the epilogue math otherwise).
-template <bool DRNN, bool EXACT, bool PAIR, bool ALT, bool TRACE>
+// WIDE: more than 8 action dimensions (dog-run: 38).  Their code -- the action-pair path of the z' epilogue and the batched
+// unconditional loads of the row fills -- lives in its own instantiations: compiled into the kernel the bench times it cost 3.5 %
+// at quadrotor dims (same-box A/B, profiles/r2c_ab_wide.txt), the epilogue's register allocation being what it is.
+template <bool DRNN, bool EXACT, bool PAIR, bool ALT, bool TRACE, bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcModel& m = kp.m;
@@ -637,6 +640,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
       for (int i = 0; i < 8; ++i) x[i] = ldg4(ptr, idx * 8 + i);
     };
 
+    // the tile after the current one (-1: none), without consuming the queue entry
+    auto peek_tile = [&]() -> int {
+      const uint32_t e = tq_n & 3u;
+      mbar_wait(&tq_full[e], (tq_n >> 2) & 1u, 16);
+      const uint32_t t = *reinterpret_cast<volatile uint32_t*>(&tile_q[e]);
+      return t < (uint32_t)kp.num_tiles ? (int)t : -1;
+    };
+    // [z0, a0, 0...] rows of tile `tile` into the [z,a] operand (my row), 16 loads in flight per round.  Called at the start of a
+    // tile, or -- F_TILE_END -- for the NEXT tile from inside the last Q-head job of the current one, while its MMAs run and
+    // this group would only wait: the tensor pipe then does not idle through the fill at every tile boundary.
+    auto fill_za = [&](int tile) {
+      const uint32_t g2 = (uint32_t)tile * TILE_ROWS + row;                       // B * T < 2^31 (checked at launch)
+      const bool v2 = (long long)g2 < total;
+      const uint32_t pb2 = v2 ? g2 / (uint32_t)p.T : 0u, pj2 = v2 ? g2 - pb2 * (uint32_t)p.T : 0u;
+      const float* ar = (p.actions && p.mode == MODE_VALUE) ? p.actions + (((size_t)pb2 * p.Tcap + pj2) * p.H) * A : nullptr;
+      const float* zr = p.z0 + (size_t)pb2 * L;
+      for (int k0 = 0; k0 < (ckb >= 0 ? m.K1p : m.nkb1 * 64); k0 += 16) {
+        float v[16];
+        if (WIDE) {
+          // unconditional loads (padding columns and rows past the end read z0 of problem 0), zeroed afterwards: a load under a
+          // per-element condition is followed by a move of its result, which serialises the sixteen round trips
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = k0 + i;
+            const float* src = (k >= L && k < L + A && ar) ? ar + (k - L) : zr + (k < L ? k : 0);
+            v[i] = __ldg(src);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = k0 + i;
+            if (!(v2 && (k < L || (k < L + A && ar)))) v[i] = 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = k0 + i;
+            float x = 0.0f;
+            if (v2) {
+              if (k < L) x = __ldg(zr + k);
+              else if (k < L + A && ar) x = __ldg(ar + (k - L));
+            }
+            v[i] = x;
+          }
+        }
+        za_store8(za, row, k0, v, ckb);
+        za_store8(za, row, k0 + 8, v + 8, ckb);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(za_full);
+    };
+    bool prefilled = false;
     int tile_idx;
     for (int it = 0; (tile_idx = next_tile()) >= 0; ++it, ++tiles_done) {
       const long long g = (long long)tile_idx * TILE_ROWS + row;
@@ -652,38 +706,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
         // initial GRU state of the problem (tdmpc_icem_similarity_drnn.py:202): fp32 copy + bf16 operand, 64 columns per
         // group.  XS was last read by the previous tile's Q-head MMAs, which both groups have seen complete.
         const float* h0 = p.hidden0 ? p.hidden0 + (size_t)pb * 128 : nullptr;
-        for (int k0 = grp * 64; k0 < grp * 64 + 64; k0 += 8) {
-          float v[8];
+        const bool hz = !(h0 && valid);                       // zero state
+        const float* hp = hz ? p.z0 : h0;                       // (unconditional loads: see fill_za)
+        for (int k0 = grp * 64; k0 < grp * 64 + 64; k0 += 16) {
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = (h0 && valid) ? __ldg(h0 + k0 + i) : 0.0f;
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(hp + (hz ? 0 : k0 + i));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (hz) v[i] = 0.0f;
             sts1(hf_addr + ((k0 + i) * 128 + row) * 4, v[i]);
           }
           sw_store8(hs, row, k0, v);
+          sw_store8(hs, row, k0 + 8, v + 8);
         }
         fence_proxy_async_smem();
         mbar_arrive(hs_full);
       }
 
-      // initial [z0, a0, 0...] row (group 0)
-      if (grp == 0) {
-        const float* zr = p.z0 + (size_t)pb * L;
-        for (int k0 = 0; k0 < (ckb >= 0 ? m.K1p : m.nkb1 * 64); k0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = k0 + i;
-            float x = 0.0f;
-            if (valid) {
-              if (k < L) x = __ldg(zr + k);
-              else if (k < L + A && p.mode == MODE_VALUE) x = __ldg(act_row + (k - L));
-            }
-            v[i] = x;
-          }
-          za_store8(za, row, k0, v, ckb);
+      // initial [z0, a0, 0...] row (group 0) -- unless the previous tile's last Q-head job already wrote it (fill_za below)
+      if (grp == 0 && !prefilled) fill_za(tile_idx);
+      prefilled = false;
+      // The action rows of the NEXT tile into L2 (group 1, idle here): a tile's rows were written by the sampling kernel a whole
+      // launch ago (176 MB at 4096 environments: HBM), and every step's layer-3 epilogue reads its slice of them with one row per
+      // thread -- at dog-run dims (38 actions) four dependent rounds of uncoalesced HBM latency per step without this.
+      if (grp == 1 && p.mode == MODE_VALUE) {
+        const int nt = peek_tile();
+        const uint32_t g2 = (uint32_t)nt * TILE_ROWS + row;
+        if (nt >= 0 && (long long)g2 < total) {
+          const uint32_t pb2 = g2 / (uint32_t)p.T, pj2 = g2 - pb2 * (uint32_t)p.T;
+          const char* pa = reinterpret_cast<const char*>(p.actions + (((size_t)pb2 * p.Tcap + pj2) * p.H) * A);
+          const int nbytes = p.H * A * 4;
+          for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + nbytes - 4));
         }
-        fence_proxy_async_smem();
-        mbar_arrive(za_full);
       }
 
       // CTA-pair mailbox (global memory): rows [z_t | a_t] of this tile, Q1, and one flag word per slot
@@ -1039,7 +1095,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             float an[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) an[a] = 0.0f;
-            if (chain == CH_DYN && p.mode == MODE_VALUE && !(flags & F_LAST_STEP) && valid) {
+            // more than 8 action dimensions (both dims even): the pair path of the z' epilogue below, lane = action pair
+            const bool act2 = WIDE && A > 8 && !((A | L) & 1);
+            if (chain == CH_DYN && p.mode == MODE_VALUE && !(flags & F_LAST_STEP) && valid && !act2) {
 #pragma unroll
               for (int a = 0; a < 8; ++a) if (a < A) an[a] = __ldg(act_row + (size_t)(t + 1) * A + a);
             }
@@ -1057,6 +1115,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             if (epi_only) { mbar_wait(d3_full, d3_phase, 15); d3_phase ^= 1; }
             else acc_wait();
             tcgen05_fence_after();
+#ifdef TDMPC_TRACE_L3
+            if (tr) trp[0] = clock64();
+#endif
             const uint32_t l3src = epi_only ? tlane + TM_A : tlane + TM_ACC + b * 128;
             if (chain == CH_DYN) {
               // z' = acc + b3 -> [z', a_{t+1}, 0...] row of the next step.  Columns >= L+A of the row are
@@ -1092,20 +1153,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
                   }
                 }
               }
-              if (next_act) {
+#if defined(TDMPC_TRACE_L3) && TDMPC_TRACE_L3 >= 2
+              if (tr) trp[0] = clock64();
+#endif
+              if (next_act && act2) {
+                // Dog-run dims (A = 38).  With lane = row every load instruction touches 32 cache lines and every bf16 store
+                // recomputes a swizzled address: 14 k cycles per step on one warp per scheduler.  Here lane = action PAIR: one
+                // 8-byte load per row fetches the row's next actions as contiguous bytes (sixteen rows in flight), and the
+                // bf16x2 store address is a per-lane constant plus a per-row constant (the row's low bits are compile-time).
+                const int a2 = 2 * lane, k = L + a2, kb = k >> 6, kk = k & 63;
+                const bool on = a2 < A, cmp = kb == ckb;
+                const uint32_t lane_part = smem_u32(za) + (uint32_t)kb * TILE_BYTES + (uint32_t)(kk & 7) * 2u + (cmp ? (uint32_t)(kk >> 3) * 128u : 0u);
+                const uint32_t xk = cmp ? 0u : (uint32_t)(kk >> 3) << 4, xmask = cmp ? 0u : 0x70u;
+                const uint32_t P1 = cmp ? 256u : 1024u, P2 = cmp ? 16u : 128u;       // tc_prims.cuh: k16_offset / sw128_offset
+                const uint32_t wpart = lane_part + (uint32_t)(q * 4) * P1;
+                // Every load is UNCONDITIONAL (rows past the end of the launch read row 0, lanes past the last pair read pair 0):
+                // a `cond ? __ldg(p) : 0` compiles to a predicated load plus a move of its result, and that move makes the warp
+                // wait for each load before it issues the next one -- sixteen memory round trips instead of one (seen in the SASS).
+                const unsigned long long mine_p = (unsigned long long)(uintptr_t)(valid ? act_row + (size_t)(t + 1) * A : p.actions);
+                const int lsel = on ? lane : 0;
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += 16) {
+                  float2 av[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const unsigned long long rp = __shfl_sync(0xffffffffu, mine_p, r0 + i);
+                    av[i] = __ldg(reinterpret_cast<const float2*>((uintptr_t)rp) + lsel);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (on) {
+                      const uint32_t addr = wpart + (uint32_t)((r0 + i) >> 3) * P1 + (uint32_t)(i & 7) * P2 + ((xk ^ ((uint32_t)(i & 7) << 4)) & xmask);
+                      asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(av[i].x, av[i].y)) : "memory");
+                      if (pub) *reinterpret_cast<float2*>(mb_rows + ((size_t)(t + 1) * 128 + q * 32 + r0 + i) * m.K1p + L + a2) = av[i];
+                    }
+#if defined(TDMPC_TRACE_L3) && TDMPC_TRACE_L3 == 3
+                  if (tr && r0 == 0) ktrace[((1 + (grp ^ 1)) * MAX_JOBS + j) * 2] = clock64();
+#endif
+                }
+#if defined(TDMPC_TRACE_L3) && TDMPC_TRACE_L3 == 3
+                if (tr) ktrace[((1 + (grp ^ 1)) * MAX_JOBS + j) * 2 + 1] = clock64();
+#endif
+              } else if (next_act) {
 #pragma unroll
                 for (int a = 0; a < 8; ++a) if (a < A) { za_store1(za, row, L + a, an[a], ckb); if (pub) mrow[L + a] = an[a]; }
-                // action dimensions 8 .. A-1 (dog-run: 38): eight loads in flight at a time -- one load per iteration put ~30
-                // dependent global-memory round trips into every step's layer-3 epilogue (-6 % on the launch at dog-run dims).
-                // (Fetching them before the accumulator wait like an[] was measured too: 32 more live registers spill, +6 %.)
+                // action dimensions 8 .. A-1 (dog-run: 38).  (Fetching them before the accumulator wait like an[] was measured:
+                // 32 more live registers spill, +6 %.)
 #pragma unroll 1
-                for (int a0 = 8; a0 < A; a0 += 8) {
+                for (int a0 = 8; WIDE && a0 < A; a0 += 8) {  // odd dims only (the pair path above takes the even ones)
                   float av[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) av[i] = (valid && a0 + i < A) ? __ldg(act_row + (size_t)(t + 1) * A + a0 + i) : 0.0f;
+                  for (int i = 0; i < 8; ++i) av[i] = __ldg((valid ? act_row + (size_t)(t + 1) * A : p.actions) + (a0 + i < A ? a0 + i : 0));   // unconditional
 #pragma unroll
                   for (int i = 0; i < 8; ++i)
-                    if (a0 + i < A) { za_store1(za, row, L + a0 + i, av[i], ckb); if (pub) mrow[L + a0 + i] = av[i]; }
+                    if (a0 + i < A) { za_store1(za, row, L + a0 + i, valid ? av[i] : 0.0f, ckb); if (pub) mrow[L + a0 + i] = valid ? av[i] : 0.0f; }
                 }
               }
             } else {
@@ -1172,6 +1273,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
             }
           }
           epi_bar_sync();
+          // Last job of a tile (F_TILE_END): the [z,a] operand was last read by the layer-1 MMAs of this Q head, which both groups
+          // have seen complete -- group 0 writes the NEXT tile's rows now, while this layer's MMAs run.
+          const bool tile_end = !first && (flags & F_TILE_END);
+          const bool early_rel = tile_end && !DRNN;      // (the GRU kernel's next job parks gate products in the h1 region)
+          if (tile_end && grp == 0) {
+            const int nt = peek_tile();
+            if (nt >= 0) { fill_za(nt); prefilled = true; }
+          }
           float sum = 0.0f, ssq = 0.0f;
           for (int c = grp; c < 4; c += 2) {
             float4 x0[8];
@@ -1229,6 +1338,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
             });
             if (first) { fence_proxy_async_smem(); mbar_arrive(&xs_full[c]); }
+            // F_TILE_END: my accumulator buffer (chunk c = grp) goes back as soon as it is read.  The next job is the next
+            // tile's first layer 1, which writes buffers 0 / 1 only; the h1 region (chunks 2 - 3) is not written before both
+            // groups have passed the barrier below.
+            if (early_rel && c == grp) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
           }
           if (!first) {
             sts1(m_dot, qdot);
@@ -1248,8 +1361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_tc_kernel(const __grid_co
               }
             }
           }
-          tcgen05_fence_before();
-          mbar_arrive(&acc_empty[grp]);
+          if (!early_rel) { tcgen05_fence_before(); mbar_arrive(&acc_empty[grp]); }
           if (tr) trp[1] = clock64();
         }
       }
@@ -1396,7 +1508,7 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0, 
     j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
     j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
     j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
-    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, F_TILE_END));
     return j;
   }
   if (mode == MODE_VALUE && !getenv("TDMPC_TC_OVERLAP")) {
@@ -1414,7 +1526,7 @@ std::vector<uint32_t> build_jobs(int mode, int H, bool drnn = false, int A = 0, 
     j.push_back(tc_job(J_QL1, CH_Q1, 0, 0, F_WAIT_ZA));
     j.push_back(tc_job(J_QL2, CH_Q1, 0, 0, 0));
     j.push_back(tc_job(J_QL1, CH_Q2, 0, 0, 0));
-    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, 0));
+    j.push_back(tc_job(J_QL2, CH_Q2, 0, 0, F_TILE_END));
   } else if (mode == MODE_VALUE) {
     // Overlapped schedule (TDMPC_TC_OVERLAP=1; measured slower).  The two MLPs of a step share one TMEM h1
     // buffer, which forces dyn and reward to alternate and leaves the tensor pipe idle during every layer-1 epilogue.  Here
@@ -1631,16 +1743,26 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   m.smem_bytes = (size_t)fixed + (size_t)stages * TILE_BYTES;
   // The attribute is per function AND per device, not per handle: always raise it to the fixed maximum, so handles with
   // different shapes (or on different GPUs of one process) cannot shrink each other's limit.
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   m.alt_sched = (!drnn && (getenv("TDMPC_TC_OVERLAP") || getenv("TDMPC_TC_SPLIT"))) ? 1 : 0;
   m.pair_mode = (!drnn && !m.alt_sched && !getenv("TDMPC_TC_NOPAIR")) ? 1 : 0;
   m.pair_rows = out->pair_rows; m.pair_flags = out->pair_flags;          // kept across re-packs of the same handle
@@ -1699,23 +1821,26 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   const int grid = kp.pair ? 2 * kp.num_tiles : (kp.num_tiles < num_sms ? kp.num_tiles : num_sms);
   if (kp.njobs <= 0 || kp.njobs + kp.njobs1 > MAX_JOBS || !m.jobs_host) return -1;
   memcpy(kp.jw, m.jobs_host + m.jobs_off[kp.pair ? 2 : p.mode][p.H], sizeof(uint32_t) * (kp.njobs + kp.njobs1));
+  const bool wide = m.A > 8;
+#define LAUNCH_TC(...) do { if (wide) rollout_tc_kernel<__VA_ARGS__, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp); \
+                            else rollout_tc_kernel<__VA_ARGS__, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp); } while (0)
   if (kp.trace) {
     // the stamping build: default precision mode, plain schedule only (tools/trace_rollout.py)
     if (kp.pair || m.alt_sched || m.exact_act) return -1;
-    if (m.drnn) rollout_tc_kernel<true, false, false, false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<false, false, false, false, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    if (m.drnn) LAUNCH_TC(true, false, false, false, true);
+    else LAUNCH_TC(false, false, false, false, true);
   } else if (m.drnn) {
-    if (m.exact_act) rollout_tc_kernel<true, true, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<true, false, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+    if (m.exact_act) LAUNCH_TC(true, true, false, false, false);
+    else LAUNCH_TC(true, false, false, false, false);
   } else {
     if (kp.pair) {
-      if (m.exact_act) rollout_tc_kernel<false, true, true, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-      else rollout_tc_kernel<false, false, true, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+      if (m.exact_act) LAUNCH_TC(false, true, true, false, false);
+      else LAUNCH_TC(false, false, true, false, false);
     } else if (m.alt_sched) {
-      if (m.exact_act) rollout_tc_kernel<false, true, false, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-      else rollout_tc_kernel<false, false, false, true, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    } else if (m.exact_act) rollout_tc_kernel<false, true, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
-    else rollout_tc_kernel<false, false, false, false, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp);
+      if (m.exact_act) LAUNCH_TC(false, true, false, true, false);
+      else LAUNCH_TC(false, false, false, true, false);
+    } else if (m.exact_act) LAUNCH_TC(false, true, false, false, false);
+    else LAUNCH_TC(false, false, false, false, false);
   }
   return 1;
 }

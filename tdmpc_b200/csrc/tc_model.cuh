@@ -42,10 +42,12 @@ enum TcJobFlags {
   // (F_KLO, no epilogue), which are written first, and later over the rest (F_KHI, epilogue as usual).  The tensor pipe
   // then has two half-jobs of work while the layer-1 epilogue is still producing h1 chunks 2-3.
   F_KLO = 32768,     // J_L2: k-blocks 0-3 only; acquires the accumulator, no commit, no epilogue
-  F_KHI = 65536      // J_L2: k-blocks 4-7 onto the accumulator its F_KLO half started; commit + epilogue
+  F_KHI = 65536,     // J_L2: k-blocks 4-7 onto the accumulator its F_KLO half started; commit + epilogue
+  F_TILE_END = 131072  // J_QL2, last job of a value-mode tile: epilogue group 0 writes the NEXT tile's [z0, a0] rows while this
+                     //   job's MMAs run, and each group hands its accumulator buffer back right after reading its first chunk
 };
 
-// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,28)
+// job word: type [0,3) | chain [3,6) | chunk [6,8) | t [8,13) | flags [13,31)
 __host__ __device__ inline uint32_t tc_job(int type, int chain, int chunk, int t, int flags) {
   return (uint32_t)type | ((uint32_t)chain << 3) | ((uint32_t)chunk << 6) | ((uint32_t)t << 8) | ((uint32_t)flags << 13);
 }
