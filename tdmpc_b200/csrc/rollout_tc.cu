@@ -1748,23 +1748,19 @@ int tc_pack(const tdmpc_model_cfg& c, const tdmpc_weights& w, const ModelFp32& m
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<false, true, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<false, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(rollout_tc_kernel<true, true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return -1;
-  m.alt_sched = (!drnn && (getenv("TDMPC_TC_OVERLAP") || getenv("TDMPC_TC_SPLIT"))) ? 1 : 0;
-  m.pair_mode = (!drnn && !m.alt_sched && !getenv("TDMPC_TC_NOPAIR")) ? 1 : 0;
+  // (the WIDE kernels, A > 8, exist for the plain schedule only: no experiment schedules, no CTA pairs there)
+  m.alt_sched = (!drnn && A <= 8 && (getenv("TDMPC_TC_OVERLAP") || getenv("TDMPC_TC_SPLIT"))) ? 1 : 0;
+  m.pair_mode = (!drnn && A <= 8 && !m.alt_sched && !getenv("TDMPC_TC_NOPAIR")) ? 1 : 0;
   m.pair_rows = out->pair_rows; m.pair_flags = out->pair_flags;          // kept across re-packs of the same handle
   if (m.pair_mode && !m.pair_rows) {
     const size_t rows = (size_t)PAIR_MAX_TILES * (TDMPC_MAX_H + 1) * 128 * m.K1p + (size_t)PAIR_MAX_TILES * 128;
@@ -1824,21 +1820,23 @@ int launch_rollout_tc(const TcModel& m, const RolloutParams& p, int num_sms, cud
   const bool wide = m.A > 8;
 #define LAUNCH_TC(...) do { if (wide) rollout_tc_kernel<__VA_ARGS__, true><<<grid, NTHREADS, m.smem_bytes, st>>>(kp); \
                             else rollout_tc_kernel<__VA_ARGS__, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp); } while (0)
+#define LAUNCH_TC_NARROW(...) do { if (wide) return -1; rollout_tc_kernel<__VA_ARGS__, false><<<grid, NTHREADS, m.smem_bytes, st>>>(kp); } while (0)
   if (kp.trace) {
     // the stamping build: default precision mode, plain schedule only (tools/trace_rollout.py)
     if (kp.pair || m.alt_sched || m.exact_act) return -1;
-    if (m.drnn) LAUNCH_TC(true, false, false, false, true);
+    if (m.drnn && wide) return -1;
+    if (m.drnn) LAUNCH_TC_NARROW(true, false, false, false, true);
     else LAUNCH_TC(false, false, false, false, true);
   } else if (m.drnn) {
     if (m.exact_act) LAUNCH_TC(true, true, false, false, false);
     else LAUNCH_TC(true, false, false, false, false);
   } else {
     if (kp.pair) {
-      if (m.exact_act) LAUNCH_TC(false, true, true, false, false);
-      else LAUNCH_TC(false, false, true, false, false);
+      if (m.exact_act) LAUNCH_TC_NARROW(false, true, true, false, false);
+      else LAUNCH_TC_NARROW(false, false, true, false, false);
     } else if (m.alt_sched) {
-      if (m.exact_act) LAUNCH_TC(false, true, false, true, false);
-      else LAUNCH_TC(false, false, false, true, false);
+      if (m.exact_act) LAUNCH_TC_NARROW(false, true, false, true, false);
+      else LAUNCH_TC_NARROW(false, false, false, true, false);
     } else if (m.exact_act) LAUNCH_TC(false, true, false, false, false);
     else LAUNCH_TC(false, false, false, false, false);
   }
