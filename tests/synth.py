@@ -33,6 +33,11 @@ def make_cfg(name="cfg1", **over):
         "cfg2s": dict(obs_shape=(223,), action_dim=38),                   # dog-run with L=50, I=6
         "cfg3": dict(obs_shape=(18,), action_dim=4),                      # quadrotor xyz_vxyz_R_omega
         "k80": dict(obs_shape=(18,), action_dim=6, latent_dim=64, iterations=2),   # L+A = 70 -> 64 + 16: compact SECOND k-block
+        # WIDE instantiations of the tcgen05 kernel (action_dim > 8): odd dims take the scalar fallback of the z' epilogue,
+        # even dims the action-pair path -- with a swizzled second k-block (L+A = 90 -> 64 + 32) and a compact one (70 -> 64 + 16)
+        "wide_odd": dict(obs_shape=(18,), action_dim=11, latent_dim=51, iterations=2),
+        "wide_sw": dict(obs_shape=(18,), action_dim=30, latent_dim=60, iterations=2),
+        "wide_ck": dict(obs_shape=(18,), action_dim=20, latent_dim=50, iterations=2),
         "cfg4": dict(obs_shape=(18,), action_dim=4, horizon=10, num_samples=1024, num_elites=32,
                      mixture_coef=0.5, horizon_schedule="linear(2, 10, 25000, 0)", normalize=True),
         "tiny": dict(obs_shape=(7,), action_dim=3, latent_dim=24, horizon=3, num_samples=96,

@@ -212,7 +212,7 @@ def _integer_model(cfg, seed):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-@pytest.mark.parametrize("cfg_name", ["tiny", "cfg3", "cfg2", "k80"])
+@pytest.mark.parametrize("cfg_name", ["tiny", "cfg3", "cfg2", "k80", "wide_odd", "wide_sw", "wide_ck"])
 def test_integer_exact_rollout(cfg_name, precision):
     """Known-answer test: bit-exact trajectory values through H steps of dynamics + reward."""
     gu = _gu()
