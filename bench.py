@@ -297,7 +297,8 @@ def update_forward_extra(dev, batch=512):
 
 def train_step_extra(dev, batch=512):
     """SURVEY 8(f) row 2, whole: one TDMPC.update (forward, backward through time, clip, both Adams, update_pi, ema) through
-    tdmpc_update (fp32 CUDA) next to the same step run eagerly by torch on this GPU (autograd + the oracle's op sequence) and on
+    tdmpc_update (fp32 in / fp32 out; the GEMMs as split-bf16 tcgen05 MMAs with fp32 accumulation, replayed as one CUDA graph)
+    next to the same step run eagerly by torch on this GPU (autograd + the oracle's op sequence) and on
     the host cores."""
     from oracle import tdmpc_oracle as O
     from tdmpc_b200 import TDMPC
@@ -329,7 +330,8 @@ def train_step_extra(dev, batch=512):
     tgt = H * (2 * f_enc + f_pi + 2 * f_q)                            # TD targets (no gradient)
     upi = (H + 1) * (f_pi + 2 * f_q)                                  # update_pi forward; backward: 2x policy, 1x Q (data gradients only)
     flop = batch * (3 * fwd + tgt + upi + (H + 1) * (2 * f_pi + 2 * f_q))
-    return {"workload": f"TDMPC.update whole (forward, backward, clip, Adam x2, update_pi, ema): cfg3 dims, batch {batch}, H = {H}, fp32",
+    return {"workload": f"TDMPC.update whole (forward, backward, clip, Adam x2, update_pi, ema): cfg3 dims, batch {batch}, H = {H}, fp32 "
+                        "(GEMMs: hi/lo bf16 split, 3 tcgen05 MMAs per product, fp32 TMEM accumulators; one CUDA graph per step)",
             "ms_per_step": ms, "launches_per_step": launches, "flop_per_step": flop, "tflops_fp32": flop / (ms * 1e-3) / 1e12,
             "gpu_eager_ms": ms_e, "cpu_port_ms": ms_c, "cpu_threads": torch.get_num_threads(),
             "d2h_bytes_per_step": 32, "note": "parameters of the torch modules are updated in place; one 8-float metrics read per step"}
