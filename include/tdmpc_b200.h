@@ -323,6 +323,11 @@ TDMPC_API int tdmpc_update_forward(tdmpc_handle* online, tdmpc_handle* target, c
  * update_pi (:165-178), torch.nn.utils.clip_grad_norm_, torch.optim.Adam.step (both optimisers, default betas / eps, no weight
  * decay) and helper.ema (helper.py:48-52) for one replay batch -- forward, backward through the H-step latent unroll, optimiser
  * and target update -- fp32 on the device.  State observations, MLP dynamics, plain encoder (no LayerNorm variant).
+ * The GEMMs run on the tensor cores at fp32 accuracy (every fp32 operand split into hi + lo bf16, three tcgen05 MMAs per product
+ * into an fp32 accumulator: ~3e-6 relative; environment TDMPC_TRAIN_GEMM=simt selects the fp32 CUDA-core GEMM instead), and the
+ * step's launch sequence is captured once per (shapes, hyper-parameters, persistent pointers) and replayed as a CUDA graph
+ * (TDMPC_TRAIN_GRAPH=0: direct launches).  The caller's input tensors may live anywhere on the device and change every call: they are
+ * copied into the workspace first.  Not thread-safe across concurrent calls on the same device (one graph cache per process).
  *
  * The PARAMETERS ARE UPDATED IN PLACE through the pointers of `online` (model) and `target` (model_target): the const in
  * tdmpc_weights is cast away.  After the call every handle that packed these parameters must be given them again
