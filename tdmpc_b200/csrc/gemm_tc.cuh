@@ -221,22 +221,41 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll 1
-    for (int r = warp; r < BM; r += THREADS / 32) {
-      const int gm = m0 + r;
-      if (gm >= M) break;
-      float* crow = C + (size_t)gm * ldc;
+    // four rows x BN / 32 column groups per pass: 8 - 16 independent load -> bias -> ELU -> store chains per thread (one row at a time
+    // left the two warps per scheduler waiting on each chain's latency: 15 us of a 16 us one-k-block launch were this loop)
+    constexpr int CG = BN / 32;
+    float bv[CG];
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        const int col = cc * 32 + lane, gn = n0 + col;
-        if (gn < N) {
-          float x = tc::lds1(base + (uint32_t)(r * LDT + col) * 4u);
-          if (bias) x += __ldg(bias + gn);
-          if (beta != 0.0f) x += beta * crow[gn];
-          if (elu) x = elu1(x);
-          crow[gn] = x;
-        }
+    for (int cc = 0; cc < CG; ++cc) bv[cc] = bias ? __ldg(bias + min(n0 + cc * 32 + lane, N - 1)) : 0.0f;
+#pragma unroll 1
+    for (int r0 = warp; r0 < BM; r0 += 4 * (THREADS / 32)) {
+      float x[4][CG];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int cc = 0; cc < CG; ++cc) x[u][cc] = tc::lds1(base + (uint32_t)((r0 + u * (THREADS / 32)) * LDT + cc * 32 + lane) * 4u) + bv[cc];
+      if (beta != 0.0f) {                                                     // CTA-uniform
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int cc = 0; cc < CG; ++cc) {
+            const int gm = m0 + r0 + u * (THREADS / 32), gn = n0 + cc * 32 + lane;
+            if (gm < M && gn < N) x[u][cc] += beta * C[(size_t)gm * ldc + gn];
+          }
       }
+      if (elu) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int cc = 0; cc < CG; ++cc) x[u][cc] = elu1(x[u][cc]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int cc = 0; cc < CG; ++cc) {
+          const int gm = m0 + r0 + u * (THREADS / 32), gn = n0 + cc * 32 + lane;
+          if (gm < M && gn < N) C[(size_t)gm * ldc + gn] = x[u][cc];
+        }
     }
   }
   tc::tcgen05_fence_before();
