@@ -96,7 +96,10 @@ template <int ROWS, bool KC> struct Loader {
       }
     }
   }
-  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int row0, int nrows) const {
+  // SUM: also adds the (masked) elements this thread stages to `acc` -- for a [K, M] operand every task of a thread has the same row
+  // m = tid % ROWS, so acc is a partial row sum over k (the bias gradient rides along with the weight-gradient GEMM)
+  template <bool SUM>
+  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int row0, int nrows, float& acc) const {
     const bool interior = klen >= BK && row0 + ROWS <= nrows;      // CTA-uniform
 #pragma unroll
     for (int i = 0; i < TASKS; ++i) {
@@ -104,12 +107,20 @@ template <int ROWS, bool KC> struct Loader {
       map(i, row, chunk);
       const uint32_t off = tc::sw128_offset(row, chunk * 8);
       if (interior) {
+        if (SUM) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += v[i][j];
+        }
         split_store(v[i], hi_base + off, lo_base + off);
       } else {
         const bool rv = row0 + row < nrows;
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = (rv && chunk * 8 + j < klen) ? v[i][j] : 0.0f;
+        if (SUM) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += x[j];
+        }
         split_store(x, hi_base + off, lo_base + off);
       }
     }
@@ -119,7 +130,7 @@ template <int ROWS, bool KC> struct Loader {
 template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(THREADS + 32, 1)
 gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, float beta,
-            const float* __restrict__ bias, int elu, int kslice) {
+            const float* __restrict__ bias, int elu, int kslice, long long zstride, float* __restrict__ bsum) {
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzled blocks need 1024-byte alignment
@@ -128,7 +139,7 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   int kbeg = 0;
-  if (kslice > 0) { kbeg = blockIdx.z * kslice; K = min(K, kbeg + kslice); C += (size_t)blockIdx.z * M * ldc; }
+  if (kslice > 0) { kbeg = blockIdx.z * kslice; K = min(K, kbeg + kslice); C += (size_t)blockIdx.z * zstride; if (bsum) bsum += (size_t)blockIdx.z * zstride; }
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branch a uniform branch and the global
   // loads' memory descriptor in a uniform register (without it: two R2UR moves in front of every LDG of the producer loop)
@@ -176,6 +187,9 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
     const bool b_vec = TB && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (kbeg % 4 == 0);
     Loader<BM, !TA> la0, la1;
     Loader<BN, TB> lb0, lb1;
+    // bias gradient (TA products only): the first column tile's CTAs also sum their A tile over k (CTA-uniform switch)
+    const bool do_sum = TA && bsum != nullptr && blockIdx.x == 0;
+    float rsum = 0.0f;
     la0.load(A, lda, m0, M, kbeg, K, a_vec);
     lb0.load(B, ldb, n0, N, kbeg, K, b_vec);
     if (nkb > 1) {
@@ -186,8 +200,9 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
       const int s = kb & 1;
       const uint32_t st = base + s * S::STAGE;
       if (kb >= 2) tc::mbar_wait(&bars[2 + s], ((kb >> 1) - 1) & 1);          // the MMAs of block kb - 2 have read this stage
-      la.store(st, st + S::A_BYTES, m0, M);
-      lb.store(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, n0, N);
+      if (TA && do_sum) la.template store<true>(st, st + S::A_BYTES, m0, M, rsum);
+      else la.template store<false>(st, st + S::A_BYTES, m0, M, rsum);
+      lb.template store<false>(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, n0, N, rsum);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&bars[s]);
       if (kb + 2 < nkb) {
@@ -206,6 +221,8 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
     tc::mbar_wait(&bars[4], 0);
     tc::tcgen05_fence_after();
     constexpr int LDT = BN + 1;
+    const uint32_t xch = base + 2 * S::STAGE - 1024;                          // 256 floats behind the staging tile
+    if (TA && do_sum) tc::sts1(xch + tid * 4u, rsum);
     {
       constexpr int HALF = BN / 2;                                            // columns per warp: 32 (BN = 64) or 64 (BN = 128)
       const int q = warp & 3, half = warp >> 2;
@@ -221,6 +238,8 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (TA && do_sum && tid < BM && m0 + tid < M)                             // threads tid and tid + 128 staged the two halves of row tid's chunks
+      bsum[m0 + tid] = tc::lds1(xch + tid * 4u) + tc::lds1(xch + (tid + BM) * 4u);
     // four rows x BN / 32 column groups per pass: 8 - 16 independent load -> bias -> ELU -> store chains per thread (one row at a time
     // left the two warps per scheduler waiting on each chain's latency: 15 us of a 16 us one-k-block launch were this loop)
     constexpr int CG = BN / 32;
@@ -266,8 +285,9 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
 // true: launched.  false: shape not covered (caller falls back to the SIMT kernel).
 template <int BN>
 inline bool launch_bn(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float beta,
-                      const float* bias, bool elu, int kslice, int nz, cudaStream_t st) {
+                      const float* bias, bool elu, int kslice, int nz, cudaStream_t st, long long zstride = 0, float* bsum = nullptr) {
   using S = Smem<BN>;
+  if (zstride == 0) zstride = (long long)M * ldc;
   static bool configured[16][4] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -282,7 +302,7 @@ inline bool launch_bn(bool ta, bool tb, int M, int N, int K, const float* A, int
   {                                                                                                                               \
     auto kern = gemm_kernel<TA_, TB_, BN>;                                                                                       \
     if (!conf(kern, SLOT_)) return false;                                                                                        \
-    kern<<<grid, THREADS + 32, S::TOTAL, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0, kslice);                     \
+    kern<<<grid, THREADS + 32, S::TOTAL, st>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, bias, elu ? 1 : 0, kslice, zstride, bsum);                     \
     return true;                                                                                                                  \
   }
   if (!ta && tb) TDMPC_GEMM_TC_LAUNCH(false, true, 0)

@@ -134,18 +134,27 @@ void gemm_bm(Ctx& c, bool ta, bool tb, int M, int N, int K, const float* A, int 
 }
 // C[i] = beta * C[i] + sum_z P[z][i]  (fixed order: the split-k result does not depend on scheduling)
 __global__ void splitk_reduce_kernel(const float* __restrict__ P, int nz, size_t n, float* __restrict__ C, float beta,
-                                     const float* __restrict__ bias = nullptr, int N = 1, int elu = 0) {
+                                     const float* __restrict__ bias = nullptr, int N = 1, int elu = 0, size_t zstride = 0,
+                                     float* __restrict__ db = nullptr, int db_n = 0, int db_acc = 0) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (zstride == 0) zstride = n;
+  if (i >= n + (size_t)db_n) return;
   float s = 0.0f;
-  for (int z = 0; z < nz; ++z) s += P[(size_t)z * n + i];
+  for (int z = 0; z < nz; ++z) s += P[(size_t)z * zstride + i];
+  if (i >= n) {                                                      // the row sums that rode along with a weight-gradient GEMM: db
+    const size_t j = i - n;
+    db[j] = db_acc ? db[j] + s : s;
+    return;
+  }
   if (bias) s += __ldg(bias + (int)(i % (size_t)N));               // same order as the GEMM epilogues: bias, beta C, ELU
   if (beta != 0.0f) s += beta * C[i];
   if (elu) s = elu1(s);
   C[i] = s;
 }
+// db / db_acc / db_done: optional bias gradient db[m] (+)= sum_k op(A)[m][k] of a weight-gradient product (ta && !tb); *db_done says
+// whether this call produced it (only the split-k tensor-core path does; the caller runs colsum otherwise)
 void gemm(Ctx& c, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float beta = 0.0f,
-          const float* bias = nullptr, bool elu = false) {
+          const float* bias = nullptr, bool elu = false, float* db = nullptr, bool db_acc = false, bool* db_done = nullptr) {
   // Tensor-core path (gemm_tc.cuh): every GEMM with a tile's worth of rows and columns; the few-row / few-column products (the last
   // Linear of the reward and Q heads, the policy's A-wide output) stay on the SIMT kernel.
   if (c.gemm_mode == 1 && !(ta && tb) && M >= 32 && N >= 16 && K >= 16) {
@@ -166,14 +175,20 @@ void gemm(Ctx& c, bool ta, bool tb, int M, int N, int K, const float* A, int lda
       if (nz >= 2) { out = c.splitk; ldo = N; b = 0.0f; } else { nz = 1; kslice = 0; }
     }
     const bool part = nz >= 2;
-    const bool done = BN == 128 ? gemm_tc::launch_bn<128>(ta, tb, M, N, K, A, lda, B, ldb, out, ldo, b, part ? nullptr : bias, part ? false : elu, kslice, nz, c.st)
-                                : gemm_tc::launch_bn<64>(ta, tb, M, N, K, A, lda, B, ldb, out, ldo, b, part ? nullptr : bias, part ? false : elu, kslice, nz, c.st);
+    const size_t mn = (size_t)M * N;
+    const bool fuse = part && db && ta && !tb && (size_t)nz * (mn + M) <= c.splitk_floats;
+    const long long zs = part ? (long long)(mn + (fuse ? M : 0)) : 0;
+    float* bsum = fuse ? c.splitk + mn : nullptr;
+    const bool done = BN == 128 ? gemm_tc::launch_bn<128>(ta, tb, M, N, K, A, lda, B, ldb, out, ldo, b, part ? nullptr : bias, part ? false : elu, kslice, nz, c.st, zs, bsum)
+                                : gemm_tc::launch_bn<64>(ta, tb, M, N, K, A, lda, B, ldb, out, ldo, b, part ? nullptr : bias, part ? false : elu, kslice, nz, c.st, zs, bsum);
     if (done) {
       c.check();
       if (part) {
-        const size_t n = (size_t)M * N;
-        splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(c.splitk, nz, n, C, beta, bias, N, elu ? 1 : 0);
+        const size_t tot = mn + (fuse ? M : 0);
+        splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(c.splitk, nz, mn, C, beta, bias, N, elu ? 1 : 0, (size_t)zs, fuse ? db : nullptr,
+                                                                               fuse ? M : 0, db_acc ? 1 : 0);
         c.check();
+        if (fuse && db_done) *db_done = true;
       }
       return;
     }
@@ -309,8 +324,9 @@ void colsum_prod(Ctx& c, const float* X, const float* Y, int rows, int N, float*
 // nn.Linear backward: dW (+)= dY^T X, db (+)= colsum(dY), dX = dY W (optional, (+)= with beta_x)
 void linear_bwd(Ctx& c, int rows, int N, int K, const float* dY, int ldy, const float* X, int ldx, const float* W, float* dW, float* db, bool accumulate,
                 float* dX, int lddx, float beta_x = 0.0f) {
-  if (dW) gemm(c, true, false, N, K, rows, dY, ldy, X, ldx, dW, K, accumulate ? 1.0f : 0.0f);
-  if (db) colsum(c, dY, rows, N, ldy, db, accumulate);
+  bool db_done = false;
+  if (dW) gemm(c, true, false, N, K, rows, dY, ldy, X, ldx, dW, K, accumulate ? 1.0f : 0.0f, nullptr, false, db, accumulate, &db_done);
+  if (db && !db_done) colsum(c, dY, rows, N, ldy, db, accumulate);
   if (dX) gemm(c, false, false, rows, K, N, dY, ldy, W, K, dX, lddx, beta_x);
 }
 
