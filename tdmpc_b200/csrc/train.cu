@@ -1,10 +1,12 @@
 // The TOLD training step on the device: TDMPC.update (algorithm/tdmpc.py:191-245) -- forward over
 // the H-step latent unroll, TD targets (_td_target, :180-189), backward through time, clip_grad_norm_, Adam, the policy update
-// (update_pi, :165-178) and the target EMA (helper.ema, helper.py:48-52) -- for one replay batch, fp32 on the CUDA cores.
+// (update_pi, :165-178) and the target EMA (helper.ema, helper.py:48-52) -- for one replay batch, fp32 tensors throughout.
 //
 // Layer-by-layer over the whole batch (rows = batch, or horizon x batch where the steps are independent): every nn.Linear is one
-// call of a tiled fp32 GEMM (forward Y = X W^T + b, data gradient dX = dY W, weight gradient dW += dY^T X), the activations the
-// backward pass needs stay in a caller-provided workspace.  Only the dynamics chain is sequential in t; the reward and Q heads
+// GEMM call (forward Y = X W^T + b, data gradient dX = dY W, weight gradient dW += dY^T X) -- on the tensor cores at fp32 accuracy
+// (gemm_tc.cuh: operands split into hi + lo bf16, three tcgen05 MMAs per product) with the tiled fp32 CUDA-core kernel below for the
+// few-row / few-column products; the activations the backward pass needs stay in a caller-provided workspace.  The step's launch
+// sequence is captured once and replayed as a CUDA graph (launch_train_step at the end of this file).  Only the dynamics chain is sequential in t; the reward and Q heads
 // of all steps, the TD targets of all steps and the policy update over all H + 1 latents run as single batched passes.
 //
 // Parity: tests/test_gpu_train.py against oracle/tdmpc_oracle.py::update_step (torch autograd over the oracle's forward) and the
