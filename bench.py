@@ -334,6 +334,12 @@ def train_step_extra(dev, batch=512):
                         "(GEMMs: hi/lo bf16 split, 3 tcgen05 MMAs per product, fp32 TMEM accumulators; one CUDA graph per step)",
             "ms_per_step": ms, "launches_per_step": launches, "flop_per_step": flop, "tflops_fp32": flop / (ms * 1e-3) / 1e12,
             "gpu_eager_ms": ms_e, "cpu_port_ms": ms_c, "cpu_threads": torch.get_num_threads(),
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc::gemm_kernel (91 of the step's ~270 launches), whole step timed",
+                         "achieved": flop / (ms * 1e-3) / 1e12, "peak": measured_peaks()[0], "unit": "TFLOP/s",
+                         "frac": flop / (ms * 1e-3) / 1e12 / measured_peaks()[0], "traffic": None,
+                         "note": "useful (fp32-equivalent) flops of the whole step over its wall time; the tensor pipe executes 3x that "
+                                 "(hi/lo bf16 split).  The step is latency-bound -- ~270 dependent graph nodes x 7 us, tensor pipe 5-20 % "
+                                 "active inside the GEMM (profiles/r2d_gemm_tc_ncu_summary.json) -- not tensor- or HBM-bound"},
             "d2h_bytes_per_step": 32, "note": "parameters of the torch modules are updated in place; one 8-float metrics read per step"}
 
 
